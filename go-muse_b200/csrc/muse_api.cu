@@ -1,0 +1,907 @@
+// muse_api.cu -- the C ABI of include/muse_b200.h: handles, device memory, launches.
+//
+// Host code here only moves bytes, sizes launches and finishes the <= top_n sized tail
+// (sorting the selected records); all arithmetic on series data happens in the kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/muse_b200.h"
+#include "muse_exact.cuh"
+#include "muse_select.cuh"
+#include "muse_synth.cuh"
+
+using namespace muse;
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? MUSE_ERR_OUT_OF_MEMORY : MUSE_ERR_CUDA,  \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *muse_last_error(void) { return g_err; }
+extern "C" const char *muse_version(void) { return "muse_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------
+struct muse_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+};
+
+struct muse_group {
+    muse_ctx *ctx;
+    int64_t N;          // series length
+    int64_t ld;         // row stride in doubles (multiple of 16 -> 128-byte rows)
+    int64_t cap, size;
+    double *slab;       // [cap][ld]
+    int nkeys;
+    int32_t *labels;    // [nkeys][cap]
+    int32_t max_id[16];
+    int64_t global_offset;
+};
+
+struct muse_batch {
+    muse_ctx *ctx;
+    muse_group *g;
+    int64_t N, n;
+    int log2m;
+    double *d_ref;      // padded copy of the reference row
+    cd *Xt, *twM, *twn;
+    int32_t *d_flag;
+    // per-run scratch (sized to the group on demand)
+    int64_t scratch_cap;
+    double *d_score;
+    int32_t *d_lag;
+    int64_t *d_slot;
+    unsigned long long *d_ckey, *d_skey;
+    int32_t *d_cidx, *d_sidx;
+    unsigned long long *d_counters;   // [0] ncand, [1] nselected
+    SelectState *d_sel;
+    // group table
+    int64_t table_cap;
+    unsigned long long *d_gmax, *d_hkeys;
+    int32_t *d_gidx;
+    cudaEvent_t ev[4];
+    muse_timing timing;
+};
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {}
+};
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+extern "C" int muse_ctx_create(int device, muse_ctx **out) {
+    if (!out) return fail(MUSE_ERR_INVALID_ARG, "muse_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MUSE_ERR_NO_DEVICE, "no CUDA device (%s); muse_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(MUSE_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+    CU(cudaSetDevice(device));
+    muse_ctx *c = new muse_ctx();
+    c->device = device;
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return MUSE_OK;
+}
+
+extern "C" void muse_ctx_destroy(muse_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int muse_ctx_synchronize(muse_ctx *c) {
+    if (!c) return fail(MUSE_ERR_INVALID_ARG, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return MUSE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// series store
+// ------------------------------------------------------------------------------------
+static int group_reserve(muse_group *g, int64_t want) {
+    if (want <= g->cap) return MUSE_OK;
+    int64_t ncap = std::max<int64_t>(want, g->cap + g->cap / 2);
+    ncap = std::max<int64_t>(ncap, 16);
+    double *nslab = nullptr;
+    int32_t *nlab = nullptr;
+    CU(cudaMalloc(&nslab, sizeof(double) * (size_t)ncap * (size_t)g->ld));
+    if (g->nkeys > 0) CU(cudaMalloc(&nlab, sizeof(int32_t) * (size_t)ncap * (size_t)g->nkeys));
+    if (g->size > 0) {
+        CU(cudaMemcpyAsync(nslab, g->slab, sizeof(double) * (size_t)g->size * (size_t)g->ld, cudaMemcpyDeviceToDevice,
+                           g->ctx->stream));
+        for (int k = 0; k < g->nkeys; k++)
+            CU(cudaMemcpyAsync(nlab + (size_t)k * ncap, g->labels + (size_t)k * g->cap, sizeof(int32_t) * (size_t)g->size,
+                               cudaMemcpyDeviceToDevice, g->ctx->stream));
+        CU(cudaStreamSynchronize(g->ctx->stream));
+    }
+    if (g->slab) cudaFree(g->slab);
+    if (g->labels) cudaFree(g->labels);
+    g->slab = nslab;
+    g->labels = nlab;
+    g->cap = ncap;
+    return MUSE_OK;
+}
+
+extern "C" int muse_group_create(muse_ctx *ctx, int64_t series_len, int32_t n_label_keys, int64_t capacity_hint,
+                                 muse_group **out) {
+    if (!ctx || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_group_create: NULL argument");
+    if (series_len < 2)
+        return fail(MUSE_ERR_INVALID_ARG, "series length %lld: the sample std needs at least 2 samples (xcorr.go:88)",
+                    (long long)series_len);
+    if (n_label_keys < 0 || n_label_keys > 16) return fail(MUSE_ERR_INVALID_ARG, "n_label_keys %d not in [0,16]", n_label_keys);
+    CU(cudaSetDevice(ctx->device));
+    muse_group *g = new muse_group();
+    memset(g, 0, sizeof(*g));
+    g->ctx = ctx;
+    g->N = series_len;
+    g->ld = (series_len + 15) / 16 * 16;
+    g->nkeys = n_label_keys;
+    for (int k = 0; k < 16; k++) g->max_id[k] = -1;
+    int rc = group_reserve(g, std::max<int64_t>(capacity_hint, 16));
+    if (rc != MUSE_OK) {
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return MUSE_OK;
+}
+
+extern "C" void muse_group_destroy(muse_group *g) {
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    if (g->slab) cudaFree(g->slab);
+    if (g->labels) cudaFree(g->labels);
+    delete g;
+}
+
+extern "C" int muse_group_append(muse_group *g, const double *rows, int64_t n_series, int64_t series_len,
+                                 const int32_t *label_ids) {
+    if (!g || (!rows && n_series > 0)) return fail(MUSE_ERR_INVALID_ARG, "muse_group_append: NULL argument");
+    if (n_series < 0) return fail(MUSE_ERR_INVALID_ARG, "n_series < 0");
+    if (series_len != g->N)   // group.go:45-51
+        return fail(MUSE_ERR_LENGTH_MISMATCH, "Timeseries has length %lld, but current group has length %lld",
+                    (long long)series_len, (long long)g->N);
+    if (g->nkeys > 0 && !label_ids && n_series > 0) return fail(MUSE_ERR_INVALID_ARG, "label_ids is NULL but the group has %d label keys", g->nkeys);
+    if (n_series == 0) return MUSE_OK;
+    if (g->size + n_series > 0x7fffffffLL) return fail(MUSE_ERR_UNSUPPORTED, "more than 2^31-1 series in one store");
+    CU(cudaSetDevice(g->ctx->device));
+    int rc = group_reserve(g, g->size + n_series);
+    if (rc != MUSE_OK) return rc;
+    cudaStream_t st = g->ctx->stream;
+    CU(cudaMemcpy2DAsync(g->slab + (size_t)g->size * g->ld, sizeof(double) * (size_t)g->ld, rows,
+                         sizeof(double) * (size_t)g->N, sizeof(double) * (size_t)g->N, (size_t)n_series,
+                         cudaMemcpyHostToDevice, st));
+    if (g->nkeys > 0) {
+        // host [n_series][nkeys] -> device SoA [nkeys][cap]
+        std::vector<int32_t> col((size_t)n_series);
+        for (int k = 0; k < g->nkeys; k++) {
+            int32_t mx = g->max_id[k];
+            for (int64_t i = 0; i < n_series; i++) {
+                int32_t v = label_ids[(size_t)i * g->nkeys + k];
+                if (v < -1) v = -1;
+                col[(size_t)i] = v;
+                mx = std::max(mx, v);
+            }
+            g->max_id[k] = mx;
+            CU(cudaMemcpyAsync(g->labels + (size_t)k * g->cap + g->size, col.data(), sizeof(int32_t) * (size_t)n_series,
+                               cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));   // col is reused
+        }
+    }
+    CU(cudaStreamSynchronize(st));
+    g->size += n_series;
+    return MUSE_OK;
+}
+
+__global__ void max_id_kernel(const int32_t *ids, int64_t n, int32_t *out) {
+    int32_t m = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, ids[i]);
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__global__ void transpose_labels_kernel(const int32_t *src, int64_t n, int nkeys, int32_t *dst, int64_t cap, int64_t off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < nkeys; k++) dst[(size_t)k * cap + off + i] = max(src[(size_t)i * nkeys + k], -1);
+}
+
+static int refresh_max_ids(muse_group *g, int64_t off, int64_t n) {
+    if (g->nkeys == 0 || n == 0) return MUSE_OK;
+    int32_t *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(int32_t) * 16));
+    CU(cudaMemsetAsync(d, 0xff, sizeof(int32_t) * 16, g->ctx->stream));
+    for (int k = 0; k < g->nkeys; k++)
+        max_id_kernel<<<256, 256, 0, g->ctx->stream>>>(g->labels + (size_t)k * g->cap + off, n, d + k);
+    int32_t h[16];
+    CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, g->ctx->stream));
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    cudaFree(d);
+    for (int k = 0; k < g->nkeys; k++) g->max_id[k] = std::max(g->max_id[k], h[k]);
+    return MUSE_OK;
+}
+
+extern "C" int muse_group_append_device(muse_group *g, const double *d_rows, int64_t n_series, int64_t series_len,
+                                        const int32_t *d_label_ids) {
+    if (!g || (!d_rows && n_series > 0)) return fail(MUSE_ERR_INVALID_ARG, "muse_group_append_device: NULL argument");
+    if (series_len != g->N)
+        return fail(MUSE_ERR_LENGTH_MISMATCH, "Timeseries has length %lld, but current group has length %lld",
+                    (long long)series_len, (long long)g->N);
+    if (g->nkeys > 0 && !d_label_ids && n_series > 0) return fail(MUSE_ERR_INVALID_ARG, "d_label_ids is NULL");
+    if (n_series <= 0) return n_series == 0 ? MUSE_OK : fail(MUSE_ERR_INVALID_ARG, "n_series < 0");
+    if (g->size + n_series > 0x7fffffffLL) return fail(MUSE_ERR_UNSUPPORTED, "more than 2^31-1 series in one store");
+    CU(cudaSetDevice(g->ctx->device));
+    int rc = group_reserve(g, g->size + n_series);
+    if (rc != MUSE_OK) return rc;
+    cudaStream_t st = g->ctx->stream;
+    CU(cudaMemcpy2DAsync(g->slab + (size_t)g->size * g->ld, sizeof(double) * (size_t)g->ld, d_rows,
+                         sizeof(double) * (size_t)g->N, sizeof(double) * (size_t)g->N, (size_t)n_series,
+                         cudaMemcpyDeviceToDevice, st));
+    if (g->nkeys > 0) {
+        transpose_labels_kernel<<<(unsigned)((n_series + 255) / 256), 256, 0, st>>>(d_label_ids, n_series, g->nkeys, g->labels,
+                                                                                  g->cap, g->size);
+        CU(cudaGetLastError());
+        rc = refresh_max_ids(g, g->size, n_series);
+        if (rc != MUSE_OK) return rc;
+    }
+    CU(cudaStreamSynchronize(st));
+    g->size += n_series;
+    return MUSE_OK;
+}
+
+// one block per series row; coalesced 8-byte stores
+__global__ void synth_rows_kernel(double *slab, int64_t ld, int64_t N, int64_t row0, int64_t n_series, uint64_t seed,
+                                  int64_t first_index, int32_t *lab0, int32_t *lab1) {
+    for (int64_t r = blockIdx.x; r < n_series; r += gridDim.x) {
+        const int64_t gi = first_index + r;
+        const SynthSeries sp = synth_params(seed, gi, N);
+        double *row = slab + (size_t)(row0 + r) * ld;
+        for (int64_t t = threadIdx.x; t < ld; t += blockDim.x) row[t] = t < N ? synth_value(seed, gi, sp, t) : 0.0;
+        if (threadIdx.x == 0) {
+            if (lab0) lab0[row0 + r] = (int32_t)(gi / 1000);
+            if (lab1) lab1[row0 + r] = (int32_t)(gi % 1000);
+        }
+    }
+}
+
+extern "C" int muse_group_append_synthetic(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index) {
+    if (!g || n_series < 0) return fail(MUSE_ERR_INVALID_ARG, "muse_group_append_synthetic: bad argument");
+    if (n_series == 0) return MUSE_OK;
+    if (g->size + n_series > 0x7fffffffLL) return fail(MUSE_ERR_UNSUPPORTED, "more than 2^31-1 series in one store");
+    CU(cudaSetDevice(g->ctx->device));
+    int rc = group_reserve(g, g->size + n_series);
+    if (rc != MUSE_OK) return rc;
+    int32_t *l0 = g->nkeys >= 1 ? g->labels : nullptr;
+    int32_t *l1 = g->nkeys >= 2 ? g->labels + (size_t)g->cap : nullptr;
+    if (g->nkeys > 2)
+        CU(cudaMemsetAsync(g->labels + (size_t)2 * g->cap, 0, sizeof(int32_t) * (size_t)g->cap * (size_t)(g->nkeys - 2), g->ctx->stream));
+    const unsigned grid = (unsigned)std::min<int64_t>(n_series, (int64_t)g->ctx->sm_count * 16);
+    synth_rows_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, g->N, g->size, n_series, seed, first_index, l0, l1);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    if (g->nkeys >= 1) g->max_id[0] = std::max<int32_t>(g->max_id[0], (int32_t)((first_index + n_series - 1) / 1000));
+    if (g->nkeys >= 2) g->max_id[1] = std::max<int32_t>(g->max_id[1], (int32_t)std::min<int64_t>(999, first_index + n_series - 1));
+    for (int k = 2; k < g->nkeys; k++) g->max_id[k] = std::max(g->max_id[k], 0);
+    g->size += n_series;
+    return MUSE_OK;
+}
+
+extern "C" void muse_synth_row(uint64_t seed, int64_t index, int64_t series_len, double *out_row) {
+    const SynthSeries sp = synth_params(seed, index, series_len);
+    for (int64_t t = 0; t < series_len; t++) out_row[t] = synth_value(seed, index, sp, t);
+}
+
+extern "C" void muse_synth_reference(uint64_t seed, int64_t series_len, double *out_row) {
+    for (int64_t t = 0; t < series_len; t++) out_row[t] = synth_ref_value(seed, series_len, t);
+}
+
+extern "C" int64_t muse_group_size(const muse_group *g) { return g ? g->size : 0; }
+extern "C" int64_t muse_group_series_len(const muse_group *g) { return g ? g->N : 0; }
+
+extern "C" int muse_group_set_global_offset(muse_group *g, int64_t first_global_index) {
+    if (!g || first_global_index < 0) return fail(MUSE_ERR_INVALID_ARG, "muse_group_set_global_offset: bad argument");
+    g->global_offset = first_global_index;
+    return MUSE_OK;
+}
+
+extern "C" int muse_group_read_row(muse_group *g, int64_t local_index, double *out_row) {
+    if (!g || !out_row || local_index < 0 || local_index >= g->size) return fail(MUSE_ERR_INVALID_ARG, "muse_group_read_row: bad argument");
+    CU(cudaSetDevice(g->ctx->device));
+    CU(cudaMemcpyAsync(out_row, g->slab + (size_t)local_index * g->ld, sizeof(double) * (size_t)g->N, cudaMemcpyDeviceToHost,
+                       g->ctx->stream));
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    return MUSE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// exact kernel dispatch
+// ------------------------------------------------------------------------------------
+template <int LOG2M, int MODE>
+static cudaError_t launch_exact_t(const ExactParams &p, cudaStream_t st) {
+    constexpr int LOG2P = LOG2M < 4 ? LOG2M : 4;
+    using C = ExactCfg<LOG2M, LOG2P>;
+    auto kern = score_exact_kernel<LOG2M, LOG2P, MODE>;
+    if (C::SMEM > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+    }
+    const int64_t blocks = (p.count + C::SPB - 1) / C::SPB;
+    kern<<<(unsigned)blocks, C::TB, C::SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_exact(int log2m, const ExactParams &p, cudaStream_t st) {
+    switch (log2m) {
+#define MUSE_CASE(L) case L: return launch_exact_t<L, MODE>(p, st);
+        MUSE_CASE(0) MUSE_CASE(1) MUSE_CASE(2) MUSE_CASE(3) MUSE_CASE(4) MUSE_CASE(5) MUSE_CASE(6)
+        MUSE_CASE(7) MUSE_CASE(8) MUSE_CASE(9) MUSE_CASE(10) MUSE_CASE(11) MUSE_CASE(12) MUSE_CASE(13)
+#undef MUSE_CASE
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------
+// batch
+// ------------------------------------------------------------------------------------
+static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 <= v < 2^29
+    int64_t n = 1;
+    while (n < v) n <<= 1;
+    return n;
+}
+
+extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out) {
+    if (!ctx || !g || !ref || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_create: NULL argument");
+    if (g->ctx != ctx) return fail(MUSE_ERR_INVALID_ARG, "group belongs to another context");
+    if (ref_len != g->N)   // muse_batch.go:24-28
+        return fail(MUSE_ERR_LENGTH_MISMATCH, "comparison group series (length %lld) does not have the same length as the reference (%lld)",
+                    (long long)g->N, (long long)ref_len);
+    const int64_t n = next_pow2(ref_len);   // muse_batch.go:35
+    if (n > MUSE_MAX_FFT_LEN) return fail(MUSE_ERR_UNSUPPORTED, "FFT length %lld > %d", (long long)n, MUSE_MAX_FFT_LEN);
+    CU(cudaSetDevice(ctx->device));
+    muse_batch *b = new muse_batch();
+    memset(b, 0, sizeof(*b));
+    b->ctx = ctx;
+    b->g = g;
+    b->N = ref_len;
+    b->n = n;
+    const int64_t M = n / 2;
+    int l = 0;
+    while ((1LL << l) < M) l++;
+    b->log2m = l;
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < 4; i++) CU(cudaEventCreate(&b->ev[i]));
+    CU(cudaMalloc(&b->d_ref, sizeof(double) * (size_t)g->ld));
+    CU(cudaMalloc(&b->Xt, sizeof(cd) * (size_t)(M + 1)));
+    CU(cudaMalloc(&b->twM, sizeof(cd) * (size_t)M));
+    CU(cudaMalloc(&b->twn, sizeof(cd) * (size_t)(M / 2 + 1)));
+    CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
+    CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
+    CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
+    CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
+    // twiddle tables, correctly rounded from long double
+    std::vector<cd> twM((size_t)M), twn((size_t)(M / 2 + 1));
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    for (int64_t k = 0; k < M; k++) twM[(size_t)k] = cd{(double)cosl(-PI2 * k / M), (double)sinl(-PI2 * k / M)};
+    for (int64_t k = 0; k <= M / 2; k++) twn[(size_t)k] = cd{(double)cosl(-PI2 * k / n), (double)sinl(-PI2 * k / n)};
+    CU(cudaMemcpyAsync(b->twM, twM.data(), sizeof(cd) * (size_t)M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->twn, twn.data(), sizeof(cd) * (size_t)(M / 2 + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(b->d_ref, 0, sizeof(double) * (size_t)g->ld, st));
+    CU(cudaMemcpyAsync(b->d_ref, ref, sizeof(double) * (size_t)ref_len, cudaMemcpyHostToDevice, st));
+    // X on the device through the same forward path the series take
+    ExactParams p;
+    memset(&p, 0, sizeof(p));
+    p.slab = b->d_ref;
+    p.ld = g->ld;
+    p.count = 1;
+    p.N = (int)ref_len;
+    p.twM = b->twM;
+    p.twn = b->twn;
+    p.out_X = b->Xt;
+    p.out_flag = b->d_flag;
+    CU(launch_exact<MODE_REF>(b->log2m, p, st));
+    int32_t flag = 0;
+    CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag) {   // muse_batch.go:38-41
+        muse_batch_destroy(b);
+        return fail(MUSE_ERR_STDDEV_ZERO, "Invalid input query, Standard deviation of zero");
+    }
+    *out = b;
+    return MUSE_OK;
+}
+
+static void free_scratch(muse_batch *b) {
+    cudaFree(b->d_score); cudaFree(b->d_lag); cudaFree(b->d_slot);
+    cudaFree(b->d_ckey); cudaFree(b->d_skey); cudaFree(b->d_cidx); cudaFree(b->d_sidx);
+    b->d_score = nullptr; b->d_lag = nullptr; b->d_slot = nullptr;
+    b->d_ckey = b->d_skey = nullptr; b->d_cidx = b->d_sidx = nullptr;
+    b->scratch_cap = 0;
+}
+
+extern "C" void muse_batch_destroy(muse_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    free_scratch(b);
+    cudaFree(b->d_gmax); cudaFree(b->d_hkeys); cudaFree(b->d_gidx);
+    cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
+    cudaFree(b->d_flag); cudaFree(b->d_counters); cudaFree(b->d_sel);
+    for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    delete b;
+}
+
+extern "C" int64_t muse_batch_fft_len(const muse_batch *b) { return b ? b->n : 0; }
+
+static int ensure_scratch(muse_batch *b) {
+    const int64_t S = b->g->size;
+    if (S <= b->scratch_cap) return MUSE_OK;
+    free_scratch(b);
+    const int64_t cap = std::max<int64_t>(S, 1024);
+    CU(cudaMalloc(&b->d_score, sizeof(double) * (size_t)cap));
+    CU(cudaMalloc(&b->d_lag, sizeof(int32_t) * (size_t)cap));
+    CU(cudaMalloc(&b->d_slot, sizeof(int64_t) * (size_t)cap));
+    CU(cudaMalloc(&b->d_ckey, sizeof(unsigned long long) * (size_t)cap));
+    CU(cudaMalloc(&b->d_skey, sizeof(unsigned long long) * (size_t)cap));
+    CU(cudaMalloc(&b->d_cidx, sizeof(int32_t) * (size_t)cap));
+    CU(cudaMalloc(&b->d_sidx, sizeof(int32_t) * (size_t)cap));
+    b->scratch_cap = cap;
+    return MUSE_OK;
+}
+
+static int check_batch(muse_batch *b) {
+    if (!b) return fail(MUSE_ERR_INVALID_ARG, "batch is NULL");
+    if (b->g->N != b->N)
+        return fail(MUSE_ERR_LENGTH_MISMATCH, "comparison group length %lld != reference length %lld", (long long)b->g->N, (long long)b->N);
+    return MUSE_OK;
+}
+
+// All series of the store through the exact kernel -> d_score / d_lag.
+static int score_exact_all(muse_batch *b, int signed_scores, const int32_t *idx, int64_t count) {
+    ExactParams p;
+    memset(&p, 0, sizeof(p));
+    p.slab = b->g->slab;
+    p.ld = b->g->ld;
+    p.count = count;
+    p.idx = idx;
+    p.N = (int)b->N;
+    p.signed_scores = signed_scores;
+    p.Xt = b->Xt;
+    p.twM = b->twM;
+    p.twn = b->twn;
+    p.out_score = b->d_score;
+    p.out_lag = b->d_lag;
+    if (count > 0) {
+        CU(launch_exact<MODE_SCORE>(b->log2m, p, b->ctx->stream));
+        b->timing.n_launches++;
+    }
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_score_all(muse_batch *b, int32_t signed_scores, double *scores, int32_t *lags) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!scores || !lags) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_score_all: NULL output");
+    CU(cudaSetDevice(b->ctx->device));
+    rc = ensure_scratch(b);
+    if (rc) return rc;
+    const int64_t S = b->g->size;
+    rc = score_exact_all(b, signed_scores, nullptr, S);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(scores, b->d_score, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, b->ctx->stream));
+    CU(cudaMemcpyAsync(lags, b->d_lag, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, b->ctx->stream));
+    CU(cudaStreamSynchronize(b->ctx->stream));
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, int32_t *std_zero) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!cc || local_index < 0 || local_index >= b->g->size) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_xcorr: bad argument");
+    CU(cudaSetDevice(b->ctx->device));
+    double *d_cc = nullptr;
+    CU(cudaMalloc(&d_cc, sizeof(double) * (size_t)b->n));
+    ExactParams p;
+    memset(&p, 0, sizeof(p));
+    p.slab = b->g->slab + (size_t)local_index * b->g->ld;
+    p.ld = b->g->ld;
+    p.count = 1;
+    p.N = (int)b->N;
+    p.Xt = b->Xt;
+    p.twM = b->twM;
+    p.twn = b->twn;
+    p.out_score = d_cc;
+    p.out_flag = b->d_flag;
+    CU(launch_exact<MODE_CC>(b->log2m, p, b->ctx->stream));
+    int32_t flag = 0;
+    CU(cudaMemcpyAsync(cc, d_cc, sizeof(double) * (size_t)b->n, cudaMemcpyDeviceToHost, b->ctx->stream));
+    CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, b->ctx->stream));
+    CU(cudaStreamSynchronize(b->ctx->stream));
+    cudaFree(d_cc);
+    if (std_zero) *std_zero = flag;
+    return MUSE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Run: scores -> group max -> filter -> top-N
+// ------------------------------------------------------------------------------------
+struct RunArgs {
+    const int32_t *key_cols;
+    int32_t n_key_cols;
+    int64_t max_lag, top_n;
+    double threshold;
+    int32_t sign_filter, mode, signed_scores;
+};
+
+struct Rec {
+    unsigned long long key;
+    int32_t idx;
+};
+
+static int setup_group_table(muse_batch *b, const RunArgs &a, KeyCols &kc, GroupTable &gt) {
+    muse_group *g = b->g;
+    if (a.n_key_cols > 4) return fail(MUSE_ERR_UNSUPPORTED, "grouping by more than 4 label keys");
+    kc.ncols = a.n_key_cols;
+    kc.bits = 64 / a.n_key_cols;
+    long double prod = 1;
+    for (int c = 0; c < a.n_key_cols; c++) {
+        const int col = a.key_cols[c];
+        if (col < 0 || col >= g->nkeys) return fail(MUSE_ERR_INVALID_ARG, "key column %d not in [0,%d)", col, g->nkeys);
+        kc.col[c] = g->labels + (size_t)col * g->cap;
+        const int64_t card = (int64_t)g->max_id[col] + 2;
+        if (kc.bits < 64 && card > (1LL << kc.bits)) return fail(MUSE_ERR_UNSUPPORTED, "label cardinality %lld does not fit %d key bits", (long long)card, kc.bits);
+        gt.radix[c] = card;
+        prod *= (long double)card;
+    }
+    const int64_t S = g->size;
+    const int64_t dense_limit = std::max<int64_t>(4 * S, 1 << 20);
+    int64_t slots;
+    if (prod <= (long double)dense_limit) {
+        gt.dense = 1;
+        slots = (int64_t)prod;
+    } else {
+        gt.dense = 0;
+        slots = 1;
+        while (slots < 2 * S) slots <<= 1;
+    }
+    if (slots > b->table_cap) {
+        cudaFree(b->d_gmax); cudaFree(b->d_gidx); cudaFree(b->d_hkeys);
+        b->d_gmax = b->d_hkeys = nullptr; b->d_gidx = nullptr; b->table_cap = 0;
+        CU(cudaMalloc(&b->d_gmax, sizeof(unsigned long long) * (size_t)slots));
+        CU(cudaMalloc(&b->d_hkeys, sizeof(unsigned long long) * (size_t)slots));
+        CU(cudaMalloc(&b->d_gidx, sizeof(int32_t) * (size_t)slots));
+        b->table_cap = slots;
+    }
+    gt.slots = slots;
+    gt.gmax = b->d_gmax;
+    gt.gidx = b->d_gidx;
+    gt.hkeys = b->d_hkeys;
+    cudaStream_t st = b->ctx->stream;
+    CU(cudaMemsetAsync(gt.gmax, 0, sizeof(unsigned long long) * (size_t)slots, st));
+    CU(cudaMemsetAsync(gt.gidx, 0x7f, sizeof(int32_t) * (size_t)slots, st));
+    if (!gt.dense) CU(cudaMemsetAsync(gt.hkeys, 0, sizeof(unsigned long long) * (size_t)slots, st));
+    return MUSE_OK;
+}
+
+// Produces the selected records on the host (unsorted).  apply_filter == 0 keeps every
+// representative (grouped multi-GPU partials).
+static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t limit, std::vector<Rec> &recs) {
+    muse_group *g = b->g;
+    const int64_t S = g->size;
+    cudaStream_t st = b->ctx->stream;
+    recs.clear();
+    if (S == 0) return MUSE_OK;
+    const unsigned blocks = (unsigned)((S + 255) / 256);
+    GroupTable gt;
+    memset(&gt, 0, sizeof(gt));
+    KeyCols kc;
+    memset(&kc, 0, sizeof(kc));
+    const bool grouped = a.n_key_cols > 0;
+    if (grouped) {
+        int rc = setup_group_table(b, a, kc, gt);
+        if (rc) return rc;
+        group_max_kernel<<<blocks, 256, 0, st>>>(gt, kc, b->d_score, S, b->d_slot);
+        group_rep_kernel<<<blocks, 256, 0, st>>>(gt, b->d_score, S, b->d_slot);
+        b->timing.n_launches += 2;
+    }
+    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
+    FilterArgs f{a.max_lag, a.threshold, a.sign_filter, apply_filter};
+    Cand cand{b->d_ckey, b->d_cidx, b->d_counters};
+    emit_candidates_kernel<<<blocks, 256, 0, st>>>(gt, grouped ? b->d_slot : nullptr, b->d_score, b->d_lag, S, f, cand);
+    b->timing.n_launches++;
+    CU(cudaGetLastError());
+    unsigned long long ncand = 0;
+    CU(cudaMemcpyAsync(&ncand, b->d_counters, sizeof(ncand), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const unsigned long long *src_key = b->d_ckey;
+    const int32_t *src_idx = b->d_cidx;
+    unsigned long long nsel = ncand;
+    if (limit >= 0 && ncand > (unsigned long long)limit && ncand > 4096ull) {
+        // device radix select of the `limit` best by (|score| desc, index asc)
+        if (limit == 0) return MUSE_OK;
+        SelectState init;
+        CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
+        unsigned long long want = (unsigned long long)limit;
+        CU(cudaMemcpyAsync(&b->d_sel->want, &want, sizeof(want), cudaMemcpyHostToDevice, st));
+        (void)init;
+        const unsigned sblocks = (unsigned)((ncand + 1023ull) / 1024ull);
+        for (int r = 0; r < 6; r++) select_round_kernel<<<sblocks, 1024, 0, st>>>(b->d_sel, b->d_ckey, b->d_cidx, ncand, r);
+        select_gather_kernel<<<sblocks, 1024, 0, st>>>(b->d_sel, b->d_ckey, b->d_cidx, ncand, b->d_skey, b->d_sidx, b->d_counters + 1);
+        b->timing.n_launches += 7;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&nsel, b->d_counters + 1, sizeof(nsel), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        src_key = b->d_skey;
+        src_idx = b->d_sidx;
+    }
+    if (nsel == 0) return MUSE_OK;
+    std::vector<unsigned long long> hk((size_t)nsel);
+    std::vector<int32_t> hi((size_t)nsel);
+    CU(cudaMemcpyAsync(hk.data(), src_key, sizeof(unsigned long long) * (size_t)nsel, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hi.data(), src_idx, sizeof(int32_t) * (size_t)nsel, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    recs.resize((size_t)nsel);
+    for (size_t i = 0; i < (size_t)nsel; i++) recs[i] = Rec{hk[i], hi[i]};
+    auto better = [](const Rec &x, const Rec &y) { return x.key != y.key ? x.key > y.key : x.idx < y.idx; };
+    if (limit >= 0 && recs.size() > (size_t)limit) {
+        std::nth_element(recs.begin(), recs.begin() + limit, recs.end(), better);
+        recs.resize((size_t)limit);
+    }
+    std::sort(recs.begin(), recs.end(), better);
+    return MUSE_OK;
+}
+
+// Fetch (score, lag) of the selected series from the device score arrays.
+static int fetch_scores(muse_batch *b, const std::vector<Rec> &recs, std::vector<double> &sc, std::vector<int32_t> &lg) {
+    const size_t k = recs.size();
+    sc.resize(k);
+    lg.resize(k);
+    if (k == 0) return MUSE_OK;
+    cudaStream_t st = b->ctx->stream;
+    if (k > 4096) {   // bulk: copy everything once
+        const int64_t S = b->g->size;
+        std::vector<double> all((size_t)S);
+        std::vector<int32_t> alll((size_t)S);
+        CU(cudaMemcpyAsync(all.data(), b->d_score, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(alll.data(), b->d_lag, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < k; i++) { sc[i] = all[(size_t)recs[i].idx]; lg[i] = alll[(size_t)recs[i].idx]; }
+        return MUSE_OK;
+    }
+    for (size_t i = 0; i < k; i++) {
+        CU(cudaMemcpyAsync(&sc[i], b->d_score + recs[i].idx, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&lg[i], b->d_lag + recs[i].idx, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return MUSE_OK;
+}
+
+static int run_scores(muse_batch *b, const RunArgs &a) {
+    int rc = ensure_scratch(b);
+    if (rc) return rc;
+    memset(&b->timing, 0, sizeof(b->timing));
+    cudaStream_t st = b->ctx->stream;
+    CU(cudaEventRecord(b->ev[0], st));
+    b->timing.mode = MUSE_MODE_EXACT;
+    rc = score_exact_all(b, a.signed_scores, nullptr, b->g->size);
+    if (rc) return rc;
+    CU(cudaEventRecord(b->ev[1], st));
+    CU(cudaEventRecord(b->ev[2], st));
+    return MUSE_OK;
+}
+
+static int finish_timing(muse_batch *b) {
+    cudaStream_t st = b->ctx->stream;
+    CU(cudaEventRecord(b->ev[3], st));
+    CU(cudaEventSynchronize(b->ev[3]));
+    cudaEventElapsedTime(&b->timing.total_ms, b->ev[0], b->ev[3]);
+    cudaEventElapsedTime(&b->timing.score_ms, b->ev[0], b->ev[1]);
+    cudaEventElapsedTime(&b->timing.rescore_ms, b->ev[1], b->ev[2]);
+    cudaEventElapsedTime(&b->timing.select_ms, b->ev[2], b->ev[3]);
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n,
+                                 double threshold, int32_t sign_filter, int32_t mode, int32_t signed_scores, double *scores,
+                                 int64_t *lags, int64_t *series_idx, int64_t *n_out) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!n_out || (top_n > 0 && (!scores || !lags || !series_idx))) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run: NULL output");
+    if (n_key_cols < 0 || (n_key_cols > 0 && !key_cols)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run: bad key columns");
+    if (top_n < 0) top_n = 0;
+    CU(cudaSetDevice(b->ctx->device));
+    RunArgs a{key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, signed_scores};
+    *n_out = 0;
+    rc = run_scores(b, a);
+    if (rc) return rc;
+    std::vector<Rec> recs;
+    rc = run_select(b, a, 1, top_n, recs);
+    if (rc) return rc;
+    std::vector<double> sc;
+    std::vector<int32_t> lg;
+    rc = fetch_scores(b, recs, sc, lg);
+    if (rc) return rc;
+    for (size_t i = 0; i < recs.size(); i++) {
+        scores[i] = sc[i];
+        lags[i] = lg[i];
+        series_idx[i] = b->g->global_offset + recs[i].idx;
+    }
+    *n_out = (int64_t)recs.size();
+    return finish_timing(b);
+}
+
+extern "C" int muse_batch_run(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n,
+                              double threshold, int32_t sign_filter, double *scores, int64_t *lags, int64_t *series_idx,
+                              int64_t *n_out) {
+    return muse_batch_run_ex(b, key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, MUSE_MODE_AUTO, 0, scores, lags,
+                             series_idx, n_out);
+}
+
+// ------------------------------------------------------------------------------------
+// multi-GPU partials
+// ------------------------------------------------------------------------------------
+extern "C" int64_t muse_batch_partial_capacity(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols, int64_t top_n) {
+    (void)key_cols;
+    if (!b) return 0;
+    if (n_key_cols <= 0) return std::min<int64_t>(std::max<int64_t>(top_n, 0), b->g->size);
+    return b->g->size;   // at most one representative per series
+}
+
+static int host_keys(muse_batch *b, const RunArgs &a, const std::vector<Rec> &recs, std::vector<uint64_t> &keys) {
+    // canonical group key of each record's series (labels fetched per record)
+    keys.resize(recs.size());
+    muse_group *g = b->g;
+    const int bits = 64 / a.n_key_cols;
+    cudaStream_t st = b->ctx->stream;
+    std::vector<int32_t> ids(recs.size() * (size_t)a.n_key_cols);
+    if (recs.size() > 4096) {
+        std::vector<int32_t> col((size_t)g->size);
+        for (int c = 0; c < a.n_key_cols; c++) {
+            CU(cudaMemcpyAsync(col.data(), g->labels + (size_t)a.key_cols[c] * g->cap, sizeof(int32_t) * (size_t)g->size, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (size_t i = 0; i < recs.size(); i++) ids[i * a.n_key_cols + c] = col[(size_t)recs[i].idx];
+        }
+    } else {
+        for (size_t i = 0; i < recs.size(); i++)
+            for (int c = 0; c < a.n_key_cols; c++)
+                CU(cudaMemcpyAsync(&ids[i * a.n_key_cols + c], g->labels + (size_t)a.key_cols[c] * g->cap + recs[i].idx, sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    for (size_t i = 0; i < recs.size(); i++) {
+        uint64_t key = 0;
+        for (int c = 0; c < a.n_key_cols; c++) {
+            const uint64_t v = (uint64_t)(ids[i * a.n_key_cols + c] + 1);
+            key = bits == 64 ? v : ((key << bits) | v);
+        }
+        keys[i] = key;
+    }
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_run_partial(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n,
+                                      double threshold, int32_t sign_filter, int32_t mode, muse_partial *out, int64_t capacity,
+                                      int64_t *n_out) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!n_out || (!out && capacity > 0)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_partial: NULL output");
+    if (n_key_cols < 0 || (n_key_cols > 0 && !key_cols)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_partial: bad key columns");
+    if (top_n < 0) top_n = 0;
+    CU(cudaSetDevice(b->ctx->device));
+    RunArgs a{key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, 0};
+    *n_out = 0;
+    rc = run_scores(b, a);
+    if (rc) return rc;
+    std::vector<Rec> recs;
+    const bool grouped = n_key_cols > 0;
+    // grouped: every representative, unfiltered (the filter needs the GLOBAL group max);
+    // ungrouped: the shard's own filtered top_n is enough
+    rc = run_select(b, a, grouped ? 0 : 1, grouped ? -1 : top_n, recs);
+    if (rc) return rc;
+    if ((int64_t)recs.size() > capacity) return fail(MUSE_ERR_INVALID_ARG, "partial capacity %lld < %zu records", (long long)capacity, recs.size());
+    std::vector<double> sc;
+    std::vector<int32_t> lg;
+    rc = fetch_scores(b, recs, sc, lg);
+    if (rc) return rc;
+    std::vector<uint64_t> keys;
+    if (grouped) {
+        rc = host_keys(b, a, recs, keys);
+        if (rc) return rc;
+    }
+    for (size_t i = 0; i < recs.size(); i++) {
+        out[i].series_idx = b->g->global_offset + recs[i].idx;
+        out[i].group_key = grouped ? keys[i] : (uint64_t)out[i].series_idx;
+        out[i].score = sc[i];
+        out[i].lag = lg[i];
+        out[i].flags = 0;
+    }
+    *n_out = (int64_t)recs.size();
+    return finish_timing(b);
+}
+
+extern "C" int muse_merge_partials(const muse_partial *parts, int64_t n_parts, int64_t max_lag, int64_t top_n, double threshold,
+                                   int32_t sign_filter, double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out) {
+    if (!n_out || (n_parts > 0 && !parts)) return fail(MUSE_ERR_INVALID_ARG, "muse_merge_partials: NULL argument");
+    if (top_n < 0) top_n = 0;
+    if (top_n > 0 && (!scores || !lags || !series_idx)) return fail(MUSE_ERR_INVALID_ARG, "muse_merge_partials: NULL output");
+    // group max across shards first (muse_batch.go:87-89), ties -> lowest global series index
+    std::unordered_map<uint64_t, muse_partial> best;
+    best.reserve((size_t)n_parts * 2 + 1);
+    for (int64_t i = 0; i < n_parts; i++) {
+        const muse_partial &p = parts[i];
+        if ((p.flags & 1) || p.score != p.score) continue;
+        auto it = best.find(p.group_key);
+        if (it == best.end()) best.emplace(p.group_key, p);
+        else {
+            muse_partial &q = it->second;
+            if (fabs(p.score) > fabs(q.score) || (fabs(p.score) == fabs(q.score) && p.series_idx < q.series_idx)) q = p;
+        }
+    }
+    std::vector<muse_partial> v;
+    v.reserve(best.size());
+    for (auto &kv : best) {
+        const muse_partial &p = kv.second;
+        const int64_t al = p.lag < 0 ? -(int64_t)p.lag : (int64_t)p.lag;   // results.go:46-52
+        const bool ok = al <= max_lag && fabs(p.score) >= threshold &&
+                        (sign_filter == 0 || (p.score > 0 && sign_filter == 1) || (p.score < 0 && sign_filter == -1));
+        if (ok) v.push_back(p);
+    }
+    auto better = [](const muse_partial &x, const muse_partial &y) {
+        return fabs(x.score) != fabs(y.score) ? fabs(x.score) > fabs(y.score) : x.series_idx < y.series_idx;
+    };
+    if ((int64_t)v.size() > top_n) {
+        std::nth_element(v.begin(), v.begin() + top_n, v.end(), better);
+        v.resize((size_t)top_n);
+    }
+    std::sort(v.begin(), v.end(), better);
+    for (size_t i = 0; i < v.size(); i++) {
+        scores[i] = v[i].score;
+        lags[i] = v[i].lag;
+        series_idx[i] = v[i].series_idx;
+    }
+    *n_out = (int64_t)v.size();
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_last_timing(const muse_batch *b, muse_timing *out) {
+    if (!b || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_last_timing: NULL argument");
+    *out = b->timing;
+    return MUSE_OK;
+}

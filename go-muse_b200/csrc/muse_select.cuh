@@ -1,0 +1,232 @@
+// muse_select.cuh -- everything downstream of the per-series scores: group keys,
+// group max BEFORE the filter (muse_batch.go:87-89), the Results filter
+// (results.go:46-52) and the top-N selection (results.go:55-87), on the device.
+//
+// Ordering rules (the reference is nondeterministic on ties because Go map iteration
+// is random; we fix one admissible order):
+//   group representative: highest |score|, ties -> lowest series index
+//   top-N:                highest |score|, ties -> lowest series index
+// NaN scores never pass results.go:46-52 and are left out of the group max.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+
+namespace muse {
+
+__device__ __forceinline__ unsigned long long score_bits(double s) {
+    // |s| as ordered bits: non-negative doubles order like their uint64 patterns
+    return (unsigned long long)__double_as_longlong(fabs(s));
+}
+
+// Canonical group key of series i from its label ids: (id+1) packed in 64/ncols bits per
+// column (id < 0 -> 0: "label absent", all such series share a group as labels.go:61-65
+// skips absent keys).  Rank independent, so shards can be merged on it.
+struct KeyCols {
+    const int32_t *col[4];
+    int ncols;
+    int bits;   // 64 / ncols
+};
+
+__device__ __forceinline__ unsigned long long canonical_key(const KeyCols &kc, int64_t i) {
+    unsigned long long key = 0;
+    for (int c = 0; c < kc.ncols; c++) {
+        const unsigned long long v = (unsigned long long)(kc.col[c][i] + 1);
+        key = (kc.bits == 64) ? v : ((key << kc.bits) | v);
+    }
+    return key;
+}
+
+// slot of a key in the group table: dense (mixed radix over the per-column cardinalities)
+// or an open-addressing hash table keyed by the canonical key.
+struct GroupTable {
+    unsigned long long *gmax;   // [slots] best |score| bits
+    int32_t *gidx;              // [slots] representative (local series index)
+    unsigned long long *hkeys;  // [slots] hash mode: canonical key + 1 (0 = empty)
+    int64_t slots;              // power of two in hash mode
+    int dense;                  // 1: dense index
+    int64_t radix[4];           // dense: cardinality (max id + 2) per column
+};
+
+__device__ __forceinline__ int64_t table_slot(const GroupTable &gt, const KeyCols &kc, int64_t i) {
+    if (gt.dense) {
+        int64_t s = 0;
+        for (int c = 0; c < kc.ncols; c++) s = s * gt.radix[c] + (int64_t)(kc.col[c][i] + 1);
+        return s;
+    }
+    const unsigned long long key = canonical_key(kc, i) + 1ull;
+    unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+    int64_t s = (int64_t)(h & (unsigned long long)(gt.slots - 1));
+    for (;;) {
+        const unsigned long long cur = gt.hkeys[s];
+        if (cur == key) return s;
+        if (cur == 0ull) {
+            const unsigned long long old = atomicCAS(&gt.hkeys[s], 0ull, key);
+            if (old == 0ull || old == key) return s;
+        }
+        s = (s + 1) & (gt.slots - 1);
+    }
+}
+
+// pass 1: slot per series + atomicMax of |score| bits
+__global__ void group_max_kernel(GroupTable gt, KeyCols kc, const double *__restrict__ score, int64_t S,
+                                 int64_t *__restrict__ slot_of) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const int64_t s = table_slot(gt, kc, i);
+    slot_of[i] = s;
+    const double sc = score[i];
+    if (sc == sc) atomicMax(&gt.gmax[s], score_bits(sc));
+}
+
+// pass 2: lowest series index among the members that hold the group max
+__global__ void group_rep_kernel(GroupTable gt, const double *__restrict__ score, int64_t S,
+                                 const int64_t *__restrict__ slot_of) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const double sc = score[i];
+    if (sc != sc) return;
+    const int64_t s = slot_of[i];
+    if (score_bits(sc) == gt.gmax[s]) atomicMin(&gt.gidx[s], (int32_t)i);
+}
+
+struct FilterArgs {
+    int64_t max_lag;
+    double threshold;
+    int sign_filter;
+    int apply;   // 0: emit every representative unfiltered (multi-GPU grouped partials)
+};
+
+__device__ __forceinline__ bool passed(const FilterArgs &f, double sc, int lag) {
+    // results.go:46-52
+    const int64_t al = lag < 0 ? -(int64_t)lag : (int64_t)lag;
+    return al <= f.max_lag && fabs(sc) >= f.threshold &&
+           (f.sign_filter == 0 || (sc > 0.0 && f.sign_filter == 1) || (sc < 0.0 && f.sign_filter == -1));
+}
+
+// Candidate = a group representative that passed the filter.
+struct Cand {
+    unsigned long long *key;   // |score| bits
+    int32_t *idx;              // local series index
+    unsigned long long *n;     // counter
+};
+
+// Emit candidates.  slot_of == NULL: ungrouped (every series is its own representative).
+__global__ void emit_candidates_kernel(GroupTable gt, const int64_t *__restrict__ slot_of,
+                                       const double *__restrict__ score, const int32_t *__restrict__ lag,
+                                       int64_t S, FilterArgs f, Cand out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool emit = false;
+    double sc = 0.0;
+    if (i < S) {
+        sc = score[i];
+        emit = (sc == sc);
+        if (emit && slot_of) emit = (gt.gidx[slot_of[i]] == (int32_t)i);
+        if (emit && f.apply) emit = passed(f, sc, lag[i]);
+    }
+    // warp-aggregated append
+    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(out.n, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (emit) {
+        const unsigned long long pos = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+        out.key[pos] = score_bits(sc);
+        out.idx[pos] = (int32_t)i;
+    }
+}
+
+// ---- radix select of the top_n candidates by (key desc, idx asc) ---------------------
+// 96-bit composite (key, ~idx) examined 16 bits at a time, most significant first.
+// State lives on the device; round r narrows [prefix] and the remaining rank.
+struct SelectState {
+    unsigned long long prefix_key;   // decided high bits of key
+    unsigned int prefix_idx;         // decided high bits of ~idx
+    unsigned long long want;         // how many still to take inside the current bucket
+    unsigned int hist[65536];
+    unsigned int done_blocks;
+};
+
+__device__ __forceinline__ unsigned digit_of(unsigned long long key, unsigned nidx, int r) {
+    return r < 4 ? (unsigned)((key >> (48 - 16 * r)) & 0xffffull) : (unsigned)((nidx >> (16 * (5 - r))) & 0xffffu);
+}
+__device__ __forceinline__ bool prefix_match(const SelectState *st, unsigned long long key, unsigned nidx, int r) {
+    if (r == 0) return true;
+    if (r <= 4) {
+        const int sh = 64 - 16 * r;
+        return sh >= 64 ? true : ((key >> sh) == (st->prefix_key >> sh));
+    }
+    if (key != st->prefix_key) return false;
+    const int sh = 32 - 16 * (r - 4);
+    return (nidx >> sh) == (st->prefix_idx >> sh);
+}
+
+__global__ void select_round_kernel(SelectState *st, const unsigned long long *__restrict__ key,
+                                    const int32_t *__restrict__ idx, unsigned long long ncand, int r) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncand) {
+        const unsigned long long k = key[i];
+        const unsigned ni = ~(unsigned)idx[i];
+        if (prefix_match(st, k, ni, r)) atomicAdd(&st->hist[digit_of(k, ni, r)], 1u);
+    }
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&st->done_blocks, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // the last block scans the histogram from the top digit down (single thread per 64 bins
+    // then a serial pass over 1024 partials is plenty for a 64K table)
+    __shared__ unsigned long long part[1024];
+    unsigned long long s = 0;
+    for (int b = 0; b < 64; b++) s += st->hist[threadIdx.x * 64 + b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long want = st->want, acc = 0;
+        int g = 1023;
+        for (; g > 0; g--) {
+            if (acc + part[g] >= want) break;
+            acc += part[g];
+        }
+        int d = g * 64 + 63;
+        for (; d > g * 64; d--) {
+            if (acc + st->hist[d] >= want) break;
+            acc += st->hist[d];
+        }
+        // digit d holds the boundary; everything above it is taken outright
+        st->want = want - acc;
+        if (r < 4) st->prefix_key |= ((unsigned long long)d) << (48 - 16 * r);
+        else st->prefix_idx |= ((unsigned)d) << (16 * (5 - r));
+        st->done_blocks = 0;
+    }
+    __syncthreads();
+    for (int b = 0; b < 64; b++) st->hist[threadIdx.x * 64 + b] = 0;
+}
+
+// Gather every candidate whose composite is >= the selected boundary.
+__global__ void select_gather_kernel(const SelectState *st, const unsigned long long *__restrict__ key,
+                                     const int32_t *__restrict__ idx, unsigned long long ncand,
+                                     unsigned long long *__restrict__ out_key, int32_t *__restrict__ out_idx,
+                                     unsigned long long *out_n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncand) return;
+    const unsigned long long k = key[i];
+    const unsigned ni = ~(unsigned)idx[i];
+    const bool take = k > st->prefix_key || (k == st->prefix_key && ni >= st->prefix_idx);
+    if (take) {
+        const unsigned long long pos = atomicAdd(out_n, 1ull);
+        out_key[pos] = k;
+        out_idx[pos] = idx[i];
+    }
+}
+
+}  // namespace muse
+#endif

@@ -1,0 +1,191 @@
+/*
+ * muse_b200.h -- C ABI of the B200-native go-muse Batch.Run hot path.
+ *
+ * This is the drop-in boundary: a Go facade that keeps go-muse's exported API
+ * (NewSeries / NewGroup / Group.Add / NewBatch / Batch.Run / Results.Fetch) binds
+ * exactly these entry points through cgo (INTEGRATION.md shows the stub).  The
+ * reference has no FFI of its own -- it is a pure-Go package -- so every entry
+ * point cites the Go function (file:line in aouyang1/go-muse) whose work it
+ * takes over.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; opaque handles; no C++/torch types.
+ *   - every call returns an int status (MUSE_OK == 0); muse_last_error() gives
+ *     the message of the calling thread's last failure.  Nothing throws.
+ *   - host buffers passed in are COPIED before the call returns (cgo may not
+ *     retain Go pointers); host output buffers are owned by the caller.
+ *   - calls may come from any OS thread (the library selects the device on
+ *     entry); calls on ONE group/batch must not overlap in time.
+ *   - strings never cross the boundary: label values are dictionary-encoded to
+ *     int32 ids by the host facade (id < 0 == "series does not have this key").
+ *   - there is no CPU fallback: without a CUDA device muse_ctx_create fails.
+ */
+#ifndef MUSE_B200_H
+#define MUSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUSE_OK                  0
+#define MUSE_ERR_INVALID_ARG     1
+#define MUSE_ERR_CUDA            2
+#define MUSE_ERR_LENGTH_MISMATCH 3  /* muse_batch.go:24-28, group.go:45-51 */
+#define MUSE_ERR_STDDEV_ZERO     4  /* muse_batch.go:38-41 "Invalid input query" */
+#define MUSE_ERR_NO_DEVICE       5
+#define MUSE_ERR_UNSUPPORTED     6  /* e.g. nextPowOf2(len) > MUSE_MAX_FFT_LEN */
+#define MUSE_ERR_OUT_OF_MEMORY   7
+
+#define MUSE_MAX_FFT_LEN 16384      /* n = nextPowOf2(series length), xcorr.go:19-24 */
+
+/* results.go:20-26 */
+#define MUSE_SIGN_ANY  0
+#define MUSE_SIGN_POS  1
+#define MUSE_SIGN_NEG -1
+
+/* muse_batch_run_ex() modes: how the per-series scores are produced */
+#define MUSE_MODE_AUTO   0  /* screened when the shape has a screening kernel, else exact */
+#define MUSE_MODE_EXACT  1  /* every series through the fp64 kernel */
+#define MUSE_MODE_SCREEN 2  /* fp32 spectral upper bound for all + fp64 re-score of survivors;
+                               results are identical to MUSE_MODE_EXACT */
+
+typedef struct muse_ctx   muse_ctx;    /* one device, its streams and scratch */
+typedef struct muse_group muse_group;  /* series store: group.go:7-12 Group.registry */
+typedef struct muse_batch muse_batch;  /* muse_batch.go:13-19 Batch (n, x, Comparison) */
+
+/* One (group, representative) record; the unit exchanged between GPUs.
+ * muse_batch.go:79-89: the Score a scoreSingle goroutine sends for its group. */
+typedef struct muse_partial {
+    uint64_t group_key;   /* packed label-id key of the group (series index when ungrouped) */
+    double   score;       /* min(|peak|, 1), muse_batch.go:74-77 */
+    int64_t  series_idx;  /* GLOBAL index of the representative series */
+    int32_t  lag;         /* xcorr.go:189-194 */
+    int32_t  flags;       /* bit0: score is NaN (never passes results.go:46-52) */
+} muse_partial;
+
+/* Per-run device timings (CUDA events on the library's own stream). */
+typedef struct muse_timing {
+    float total_ms;        /* first launch -> results on host */
+    float score_ms;        /* the dominant full-slab kernel (exact or screening pass) */
+    float rescore_ms;      /* fp64 re-scoring of screened survivors (0 in exact mode) */
+    float select_ms;       /* group max + filter + top-N */
+    int64_t n_rescored;    /* series that went through the fp64 kernel after screening */
+    int32_t mode;          /* MUSE_MODE_EXACT or MUSE_MODE_SCREEN actually used */
+    int32_t n_launches;    /* kernels launched by this run */
+} muse_timing;
+
+const char *muse_last_error(void);
+const char *muse_version(void);
+
+/* ---- context --------------------------------------------------------------- */
+int  muse_ctx_create(int device, muse_ctx **out);
+void muse_ctx_destroy(muse_ctx *ctx);
+int  muse_ctx_synchronize(muse_ctx *ctx);
+
+/* ---- series store ----------------------------------------------------------
+ * Replaces Group{registry} + Series{y, labels} (group.go:7-56, series.go:8-42):
+ * a device-resident fp64 slab, one 128-byte-aligned row per series, plus an
+ * int32 label-id table [n_label_keys][capacity] (SoA).  Duplicate-UID and
+ * empty-label checks (group.go:33-41) stay in the host facade, which owns the
+ * strings.  capacity_hint is a reservation, the store grows on demand. */
+int  muse_group_create(muse_ctx *ctx, int64_t series_len, int32_t n_label_keys,
+                       int64_t capacity_hint, muse_group **out);
+void muse_group_destroy(muse_group *g);
+
+/* Group.Add (group.go:31-56): append n_series rows (row-major [n_series][series_len]
+ * fp64, HOST memory) and their label ids ([n_series][n_label_keys], may be NULL
+ * when n_label_keys == 0).  series_len must equal the group's (group.go:45-51 ->
+ * MUSE_ERR_LENGTH_MISMATCH).  The copy is staged through pinned memory and is
+ * complete when the call returns. */
+int  muse_group_append(muse_group *g, const double *rows, int64_t n_series, int64_t series_len,
+                       const int32_t *label_ids);
+
+/* Same, from DEVICE memory already on the context's device (row-major rows). */
+int  muse_group_append_device(muse_group *g, const double *d_rows, int64_t n_series,
+                              int64_t series_len, const int32_t *d_label_ids);
+
+/* Synthetic siggen-style rows generated on the device (benchmarks at sizes that do
+ * not fit in host memory).  Series i (global index
+ * first_index + k) is kind i%3: rect+noise / line+noise / noise, from a counter-based
+ * generator keyed (seed, i, t); muse_synth_row() gives the identical row on the host.
+ * Label ids: key 0 = i / 1000 ("graph"), key 1 = i % 1000 ("host") when the group has
+ * >= 2 label keys. */
+int  muse_group_append_synthetic(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index);
+void muse_synth_row(uint64_t seed, int64_t index, int64_t series_len, double *out_row);
+void muse_synth_reference(uint64_t seed, int64_t series_len, double *out_row);
+
+int64_t muse_group_size(const muse_group *g);        /* number of series, len(registry) */
+int64_t muse_group_series_len(const muse_group *g);  /* Group.Length(), group.go:24-26 */
+/* Global index of this store's first series (multi-GPU shards); default 0. */
+int  muse_group_set_global_offset(muse_group *g, int64_t first_global_index);
+/* Read one row back (tests). */
+int  muse_group_read_row(muse_group *g, int64_t local_index, double *out_row);
+
+/* ---- batch -----------------------------------------------------------------
+ * NewBatch (muse_batch.go:23-52): checks ref_len against the group
+ * (MUSE_ERR_LENGTH_MISMATCH), n = nextPowOf2(ref_len), computes on the device
+ * X = rfft(zeroPad(zNormalize(ref)/(N-1), n)); std(ref)==0 -> MUSE_ERR_STDDEV_ZERO.
+ * The reference row is copied; unlike go-muse nothing is mutated in place. */
+int  muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len,
+                       muse_batch **out);
+void muse_batch_destroy(muse_batch *b);
+int64_t muse_batch_fft_len(const muse_batch *b);     /* Batch.n */
+
+/* Batch.Run + Results filter/top-N for one Run on a fresh Results
+ * (muse_batch.go:99-130, results.go:46-87).
+ *   key_cols[n_key_cols]: label-key columns to group by (Group.indexLabelValues,
+ *       group.go:76-104); n_key_cols == 0: every series is its own group.
+ *   per group the member with the highest min(|peak|,1) is kept BEFORE the filter
+ *   (muse_batch.go:87-89, lowest series index wins ties), then |lag| <= max_lag,
+ *   score >= threshold and the sign filter are applied (results.go:46-52) and the
+ *   top_n by score are returned in DESCENDING order (results.go:81-85), ties by
+ *   ascending series index.
+ * Outputs (host, capacity top_n each): scores, lags, series_idx (global index of
+ * the representative series -> the facade maps it to that series' *Labels,
+ * muse_batch.go:80); *n_out = number written. */
+int  muse_batch_run(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
+                    int64_t max_lag, int64_t top_n, double threshold, int32_t sign_filter,
+                    double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
+
+/* As muse_batch_run with an explicit scoring mode (MUSE_MODE_*) and signed scores:
+ * signed_scores != 0 keeps the sign and clamps to [-1, 1] as Muse.Run does
+ * (muse.go:72-76, group max by |score| :86) instead of abs+clamp. */
+int  muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
+                       int64_t max_lag, int64_t top_n, double threshold, int32_t sign_filter,
+                       int32_t mode, int32_t signed_scores,
+                       double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
+
+/* Per-series (score, lag) of every series in the store, exact fp64 path
+ * (xCorrWithX + abs/clamp per series; what scoreSingle's loop computes,
+ * muse_batch.go:68-77).  Host outputs of muse_group_size() entries. */
+int  muse_batch_score_all(muse_batch *b, int32_t signed_scores, double *scores, int32_t *lags);
+
+/* The full cross-correlation vector cc[n] of one series (xcorr.go:160-197's first
+ * return value; KAT support).  *std_zero is set when xcorr.go:165-168 applies. */
+int  muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, int32_t *std_zero);
+
+/* ---- multi-GPU: shard-local partials and their merge -------------------------
+ * One store per GPU holds a contiguous block of the series (global offset set with
+ * muse_group_set_global_offset).  run_partial produces this shard's group
+ * representatives BEFORE the filter, or -- ungrouped -- its local top_n
+ * AFTER the filter; the caller all-gathers the records (NCCL) and every rank calls
+ * muse_merge_partials on the concatenation. */
+int  muse_batch_run_partial(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
+                            int64_t max_lag, int64_t top_n, double threshold, int32_t sign_filter,
+                            int32_t mode, muse_partial *out, int64_t capacity, int64_t *n_out);
+/* Upper bound on the records run_partial can emit for these arguments. */
+int64_t muse_batch_partial_capacity(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
+                                    int64_t top_n);
+int  muse_merge_partials(const muse_partial *parts, int64_t n_parts,
+                         int64_t max_lag, int64_t top_n, double threshold, int32_t sign_filter,
+                         double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
+
+/* Timings of the batch's most recent run. */
+int  muse_batch_last_timing(const muse_batch *b, muse_timing *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSE_B200_H */

@@ -1,0 +1,105 @@
+"""CPU-side checks of the boundary: the C-ABI library builds, loads and exports every
+symbol include/muse_b200.h declares; host-side facade logic (labels, group, results)
+mirrors the reference's tests.  No compute calls (no GPU here)."""
+import os
+import re
+
+import pytest
+
+import muse_b200 as mb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "muse_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(muse_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    mb.build()
+    L = mb.lib()
+    decl = _declared_symbols()
+    assert len(decl) >= 25
+    for name in decl:
+        assert hasattr(L, name), name
+    assert sorted(mb.ABI.keys()) == decl       # the ctypes table covers the whole header
+    assert b"sm_100a" in L.muse_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mb.MuseError) as e:
+        mb.Context(0)
+    assert e.value.code == mb.MUSE_ERR_NO_DEVICE
+
+
+def test_merge_partials_host_logic():
+    import numpy as np
+    parts = np.zeros(7, dtype=mb.PARTIAL_DTYPE)
+    # two shards report group 5; the higher score wins BEFORE the lag filter
+    parts[0] = (5, 0.70, 10, 0, 0)
+    parts[1] = (5, 0.90, 2000, 99, 0)      # best of group 5 but lag 99 -> group 5 rejected
+    parts[2] = (6, 0.60, 11, -3, 0)
+    parts[3] = (7, 0.60, 7, 2, 0)          # ties with group 6 -> lower series index first
+    parts[4] = (8, 0.10, 12, 0, 0)         # below threshold
+    parts[5] = (9, float("nan"), 13, 0, 0)
+    parts[6] = (6, 0.60, 3000, 1, 0)       # same score as idx 11 -> lowest index keeps
+    sc, lg, ix = mb.merge_partials(parts, 10, 5, 0.5)
+    assert ix.tolist() == [7, 11] and lg.tolist() == [2, -3] and sc.tolist() == [0.6, 0.6]
+    sc, lg, ix = mb.merge_partials(parts, 100, 1, 0.0)
+    assert ix.tolist() == [2000]
+
+
+def test_facade_labels_group_results(kats):
+    for c in kats["labels_id"]["cases"]:
+        gb = list(c["group_by"]) if c["group_by"] else None
+        assert mb.NewLabels(c["labels"]).ID(gb) == c["expected"]
+    k = kats["series"]
+    assert mb.NewSeries([0.1, 0.2, 0.3], None).Labels().Keys() == [k["default_label"]]
+    for c in k["uid_cases"]:
+        assert mb.NewSeries([0.1], mb.NewLabels(c["labels"])).UID() == c["expected"]
+    k = kats["group_add"]
+    g = mb.NewGroup("test")
+    for c in k["cases"]:
+        s = mb.NewSeries(k["y"], mb.NewLabels(c["labels"]))
+        if c["expect_error"]:
+            with pytest.raises(mb.MuseError):
+                g.Add(s)
+        else:
+            g.Add(s)
+    with pytest.raises(mb.MuseError) as e:
+        g.Add(mb.NewSeries([1.0, 2.0], mb.NewLabels({"zz": "1"})))
+    assert e.value.code == mb.MUSE_ERR_LENGTH_MISMATCH
+    k = kats["index_label_values"]
+    g = mb.NewGroup("test")
+    for l in k["labels"]:
+        g.Add(mb.NewSeries(k["y"], mb.NewLabels(l)))
+    for labels, want in k["filter_cases"]:
+        assert len(g.FilterByLabelValues(mb.NewLabels(labels))) == want
+    # results.go:55-87
+    r = mb.NewResults(5, 3, 0.2, mb.SignFilter_ANY)
+    lab = mb.NewLabels({"a": "b"})
+    for sc, lag in [(0.5, 0), (0.9, 1), (0.1, 0), (0.7, 6), (0.3, -5), (0.6, 2), (0.5, 3)]:
+        r.Update(mb.Score(lab, lag, sc))
+    r.Update(mb.Score(None, 0, 1.0))
+    out, mean = r.Fetch()
+    assert [s.PercentScore for s in out] == [0.9, 0.6, 0.5] and out[2].Lag == 0
+    import math
+    out, mean = r.Fetch()
+    assert out == [] and math.isnan(mean)
+
+
+def test_kernel_phases_on_cpu():
+    """The per-thread phases of the CUDA kernels, compiled as host code and run for all
+    'threads' of a series, against a direct O(n^2) long-double cross correlation."""
+    import subprocess
+    exe = "/tmp/muse_emulate_kernel"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "go-muse_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "cpp", "emulate_kernel.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "ALL OK" in out.stdout

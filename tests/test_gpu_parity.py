@@ -1,0 +1,298 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  Needs a B200."""
+import numpy as np
+import pytest
+
+import muse_b200 as mb
+from oracle import c_oracle as co
+from oracle import muse_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-9   # north_star: scores within 1e-9 absolute in fp64
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return mb.default_context(0)
+
+
+def _mk(entries):
+    return [mb.NewSeries(e["y"], mb.NewLabels(e["labels"])) for e in entries]
+
+
+def _compare_scores(scores, expected, tol):
+    # muse_test.go:11-39 compareScores (+ the F4 tie-lag allowance)
+    assert len(scores) == len(expected)
+    for got, want in zip(scores, expected):
+        assert got.Lag in want.get("tie_lags", [want["lag"]])
+        assert abs(got.PercentScore - want["score"]) <= tol
+        assert got.Labels.labels == want["labels"]
+
+
+@pytest.mark.parametrize("name", ["batch_run_simple", "batch_run_multi_dimensional"])
+def test_reference_batch_kats(kats, name):
+    # muse_batch_test.go:9-82 through NewSeries/NewGroup/NewBatch/Run/Fetch
+    k = kats[name]
+    ref = mb.NewSeries(k["ref"]["y"], mb.NewLabels(k["ref"]["labels"]))
+    g = mb.NewGroup("targets")
+    assert g.Add(*_mk(k["comp"])) is None
+    r = k["results"]
+    b = mb.NewBatch(ref, g, mb.NewResults(r["max_lag"], r["top_n"], r["threshold"], r["sign_filter"]), k["concurrency"])
+    assert b.Run(list(k["group_by"])) is None
+    scores, _ = b.Results.Fetch()
+    _compare_scores(scores, k["expected"], k["score_tol"])
+
+
+def test_reference_batch_errors(kats):
+    # muse_batch_test.go:83-102 and muse_batch.go:38-41
+    k = kats["batch_run_with_larger_group"]
+    g = mb.NewGroup("targets")
+    g.Add(*_mk(k["comp"]))
+    with pytest.raises(mb.MuseError) as e:
+        mb.NewBatch(mb.NewSeries(k["ref"]["y"], mb.NewLabels(k["ref"]["labels"])), g, mb.NewResults(10, 20, 0, 0), 1)
+    assert e.value.code == mb.MUSE_ERR_LENGTH_MISMATCH
+    g = mb.NewGroup("t")
+    g.Add(mb.NewSeries([1.0, 2.0, 3.0, 4.0], mb.NewLabels({"a": "b"})))
+    with pytest.raises(mb.MuseError) as e:
+        mb.NewBatch(mb.NewSeries([2.0, 2.0, 2.0, 2.0]), g, mb.NewResults(1, 1, 0, 0), 1)
+    assert e.value.code == mb.MUSE_ERR_STDDEV_ZERO and "Invalid input query" in str(e.value)
+
+
+def test_example_structure(kats):
+    # example_test.go:9-94 shape (C1): Run(nil) / ["graph"] / ["host"] on one Batch, Results reused
+    rng = np.random.default_rng(5)
+    N = 480
+
+    def rect(amp, mid, width):
+        y = np.zeros(N)
+        y[mid - width // 2: mid - width // 2 + width] = amp
+        return y
+
+    noise = lambda: 0.1 * (rng.random(N) - 0.5)
+    ref = mb.NewSeries(rect(1.5, 240, 10) + noise(), mb.NewLabels({"graph": "CallTime99Pct", "host": "host1"}))
+    comp = mb.NewGroup("comparison")
+    comp.Add(ref,
+             mb.NewSeries(rect(1.5, 242, 7) + noise(), mb.NewLabels({"graph": "CallTime99Pct", "host": "host2"})),
+             mb.NewSeries(rect(43, 240, 10) + noise(), mb.NewLabels({"graph": "ErrorRate", "host": "host1"})),
+             mb.NewSeries(np.full(N, 0.1) + noise(), mb.NewLabels({"graph": "ErrorRate", "host": "host2"})),
+             mb.NewSeries(np.full(N, 0.1), mb.NewLabels({"graph": "ErrorRate", "host": "host3"})))
+    Y = np.stack([s.Values() for s in comp.series])
+    m = mb.NewBatch(ref, comp, mb.NewResults(15, 4, 0.0, mb.SignFilter_ANY), 2)
+    graph_ids = np.array([0, 0, 1, 1, 1])
+    host_ids = np.array([0, 1, 0, 1, 2])
+    for group_by, gids in ((None, None), (["graph"], graph_ids), (["host"], host_ids)):
+        m.Run(group_by)
+        res, _ = m.Results.Fetch()
+        sc, lg, ix = mo.batch_run_arrays(ref.Values(), Y, gids, 15, 4, 0.0)
+        assert [comp.series[int(i)].UID() for i in ix] == [s.Labels.ID(list(s.Labels.Keys())) for s in res]
+        for s, a, l in zip(res, sc, lg):
+            assert abs(s.PercentScore - a) <= SCORE_TOL and s.Lag == l
+    # structure pinned by the Example: the constant series scores 0.000 at lag 0
+    m.Run(None)
+    res, _ = m.Results.Fetch()
+    assert res[0].PercentScore == pytest.approx(1.0, abs=1e-12) and res[0].Lag == 0
+    ids = [s.Labels.ID(list(s.Labels.Keys())) for s in res]
+    assert "graph:ErrorRate,host:host3" in ids
+    z = res[ids.index("graph:ErrorRate,host:host3")]
+    assert z.PercentScore == 0.0 and z.Lag == 0
+
+
+def _siggen(rng, S, N, pulse_every=3):
+    ref = np.zeros(N)
+    ref[N // 2 - min(5, N // 4): N // 2 + max(1, min(5, N // 4))] = 1.5
+    ref += 0.1 * (rng.random(N) - 0.5)
+    Y = 0.1 * (rng.random((S, N)) - 0.5)
+    for i in range(0, S, pulse_every):
+        w = int(rng.integers(1, max(2, min(20, N // 2))))
+        m = int(rng.integers(0, max(1, N - w)))
+        Y[i, m:m + w] += rng.uniform(0.5, 40)
+    for i in range(1, S, pulse_every):
+        Y[i] += rng.uniform(-0.01, 0.01) * np.arange(N) + rng.uniform(0, 100)
+    return ref, Y
+
+
+def _check_scores(ref, Y, sc, lg, tol=SCORE_TOL):
+    want_s, want_l, ties = mo.score_series_batch(ref, Y, want_ties=True)
+    assert np.max(np.abs(sc - want_s)) <= tol
+    for i in range(Y.shape[0]):
+        assert lg[i] == want_l[i] or lg[i] in ties[i], (i, lg[i], want_l[i])
+
+
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 8, 12, 31, 33, 100, 255, 480, 1000, 1440, 2500, 5000, 10080])
+def test_score_all_matches_oracle(ctx, N):
+    # every FFT size the kernels are instantiated for, odd and even lengths
+    rng = np.random.default_rng(N)
+    S = 257 if N <= 2500 else 37
+    ref, Y = _siggen(rng, S, N)
+    if N >= 8:
+        Y[3] = 7.25                      # constant -> score 0, lag 0 (xcorr.go:165-168)
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    b = mb.DeviceBatch(ctx, store, ref)
+    assert b.fft_len() == mo.next_pow_of2(float(N))
+    sc, lg = b.score_all()
+    _check_scores(ref, Y, sc, lg)
+    if N >= 8:
+        assert sc[3] == 0.0 and lg[3] == 0
+    # signed scores (muse.go:72-76)
+    ssc, slg = b.score_all(signed_scores=True)
+    want_s, want_l = mo.score_series_batch(ref, Y, signed=True)
+    assert np.max(np.abs(ssc - want_s)) <= SCORE_TOL
+    np.testing.assert_array_equal(np.abs(ssc), sc)
+
+
+def test_xcorr_vector_kats(ctx, kats):
+    # TestXCorrWithX inputs (xcorr_test.go:204-286) through the Batch path: N=5 -> n=8
+    # (NewBatch always pads to a power of two); full cc vector against the oracle, plus the
+    # lag/sign expectations that do not depend on n.
+    k = kats["x_corr_with_x"]
+    for c in k["cases"]:
+        x, y = np.array(c["x"], dtype=float), np.array(c["y"], dtype=float)
+        store = mb.DeviceStore(ctx, 5, 0, 1)
+        store.append(y)
+        b = mb.DeviceBatch(ctx, store, x)
+        cc, std_zero = b.xcorr(0)
+        X, n = mo.ref_spectrum(x)
+        want_cc, want_lag, want_mv = mo.x_corr_with_x(X, y, n)
+        if c["cc"] is None:
+            assert std_zero and cc is None and want_cc is None
+            continue
+        assert np.max(np.abs(cc - want_cc)) <= 1e-12
+        sc, lg = b.score_all(signed_scores=True)
+        assert lg[0] == c["lag"] and np.sign(sc[0]) == c["sign"]
+        assert abs(sc[0] - max(-1.0, min(1.0, want_mv))) <= 1e-12 and lg[0] == want_lag
+
+
+def test_run_matches_oracle_ungrouped_and_grouped(ctx):
+    rng = np.random.default_rng(11)
+    S, N = 6000, 480
+    ref, Y = _siggen(rng, S, N)
+    graph = (np.arange(S) // 50).astype(np.int32)
+    host = (np.arange(S) % 50).astype(np.int32)
+    colo = rng.integers(0, 3, S).astype(np.int32)
+    ids = np.stack([graph, host, colo], axis=1)
+    store = mb.DeviceStore(ctx, N, 3, S)
+    store.append(Y, ids)
+    b = mb.DeviceBatch(ctx, store, ref)
+    sl = mo.score_series_batch(ref, Y)
+
+    def dense(*cols):
+        _, inv = np.unique(np.stack(cols, axis=1), axis=0, return_inverse=True)
+        # first-appearance order
+        first = {}
+        out = np.zeros(S, dtype=np.int64)
+        for i, g in enumerate(inv.ravel()):
+            out[i] = first.setdefault(int(g), len(first))
+        return out
+
+    cases = [([], None), ([0], dense(graph)), ([1], dense(host)), ([0, 2], dense(graph, colo)),
+             ([0, 1, 2], dense(graph, host, colo))]
+    for cols, gids in cases:
+        for max_lag, top_n, thr in ((10, 20, 0.0), (60, 100, 0.5), (240, 5, 0.2), (3, 7000, 0.0)):
+            sc, lg, ix = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_EXACT)
+            wsc, wlg, wix = mo.batch_run_arrays(ref, Y, gids, max_lag, top_n, thr, scores_lags=sl)
+            assert len(sc) == len(wsc), (cols, max_lag, top_n, thr)
+            assert np.max(np.abs(sc - wsc), initial=0.0) <= SCORE_TOL
+            np.testing.assert_array_equal(ix, wix)
+            np.testing.assert_array_equal(lg, wlg)
+    t = b.timing()
+    assert t.n_launches >= 2 and t.total_ms > 0
+
+
+def test_top_n_device_select_with_ties(ctx):
+    # > 4096 candidates and heavy ties: many exact duplicates of a few rows -> the device
+    # radix select must cut by (score desc, index asc)
+    rng = np.random.default_rng(2)
+    N = 64
+    ref, base = _siggen(rng, 8, N, pulse_every=1)
+    S = 20000
+    Y = base[rng.integers(0, 8, S)]
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    b = mb.DeviceBatch(ctx, store, ref)
+    sl = mo.score_series_batch(ref, Y)
+    for top_n in (1, 100, 4500, 12345):
+        sc, lg, ix = b.run([], N, top_n, 0.0, mode=mb.MODE_EXACT)
+        wsc, wlg, wix = mo.batch_run_arrays(ref, Y, None, N, top_n, 0.0, scores_lags=sl)
+        assert len(sc) == len(wsc)
+        np.testing.assert_array_equal(ix, wix)
+        assert np.max(np.abs(sc - wsc), initial=0.0) <= SCORE_TOL
+
+
+def test_hash_group_table(ctx):
+    # label cardinalities whose product exceeds the dense table -> open-addressing path
+    rng = np.random.default_rng(3)
+    S, N = 3000, 100
+    ref, Y = _siggen(rng, S, N)
+    a = rng.integers(0, 2_000_000, S).astype(np.int32)
+    a[::7] = a[0]                      # some real groups
+    c = rng.integers(0, 1_000_000, S).astype(np.int32)
+    c[::7] = c[0]
+    a[5], c[5] = -1, -1                # absent labels share the "" group (labels.go:61-65)
+    a[6], c[6] = -1, -1
+    store = mb.DeviceStore(ctx, N, 2, S)
+    store.append(Y, np.stack([a, c], axis=1))
+    b = mb.DeviceBatch(ctx, store, ref)
+    key = {}
+    gids = np.array([key.setdefault((int(x), int(y)), len(key)) for x, y in zip(a, c)])
+    sc, lg, ix = b.run([0, 1], 100, 50, 0.0, mode=mb.MODE_EXACT)
+    wsc, wlg, wix = mo.batch_run_arrays(ref, Y, gids, 100, 50, 0.0)
+    np.testing.assert_array_equal(ix, wix)
+    assert np.max(np.abs(sc - wsc)) <= SCORE_TOL
+
+
+def test_synthetic_rows_identical_on_host_and_device(ctx):
+    N, S, seed, first = 1440, 64, 20261018, 999_990
+    store = mb.DeviceStore(ctx, N, 2, S)
+    store.append_synthetic(S, seed, first)
+    for i in (0, 1, 2, 9, 10, 63):
+        np.testing.assert_array_equal(store.read_row(i), mb.synth_row(seed, first + i, N))
+    kinds = [np.ptp(mb.synth_row(seed, first + i, N)) for i in range(3)]
+    assert max(kinds) > 0.4                      # a rect pulse is in there
+    ref = mb.synth_reference(seed, N)
+    assert ref[N // 2] > 1.4 and abs(ref[10]) <= 0.05
+
+
+def test_sharded_partials_merge_equals_single_store(ctx):
+    # two shards with global offsets -> partials -> merge == one store (F2: group max before filter)
+    rng = np.random.default_rng(17)
+    S, N = 4000, 256
+    ref, Y = _siggen(rng, S, N)
+    graph = rng.integers(0, 40, S).astype(np.int32)      # groups straddle the shard boundary
+    ids = graph[:, None]
+    whole = mb.DeviceStore(ctx, N, 1, S)
+    whole.append(Y, ids)
+    bw = mb.DeviceBatch(ctx, whole, ref)
+    cut = 1700
+    shards = []
+    for lo, hi in ((0, cut), (cut, S)):
+        st = mb.DeviceStore(ctx, N, 1, hi - lo)
+        st.append(Y[lo:hi], ids[lo:hi])
+        st.set_global_offset(lo)
+        shards.append(mb.DeviceBatch(ctx, st, ref))
+    for cols in ([], [0]):
+        for max_lag, top_n, thr in ((20, 10, 0.0), (128, 100, 0.3)):
+            parts = np.concatenate([s.run_partial(cols, max_lag, top_n, thr, mode=mb.MODE_EXACT) for s in shards])
+            sc, lg, ix = mb.merge_partials(parts, max_lag, top_n, thr)
+            wsc, wlg, wix = bw.run(cols, max_lag, top_n, thr, mode=mb.MODE_EXACT)
+            np.testing.assert_array_equal(ix, wix)
+            np.testing.assert_array_equal(lg, wlg)
+            np.testing.assert_array_equal(sc, wsc)
+
+
+def test_c_oracle_agrees_at_larger_size(ctx):
+    # the fast C oracle as checker at a size the numpy form would take long on
+    rng = np.random.default_rng(23)
+    S, N = 20000, 1440
+    ref, Y = _siggen(rng, S, N)
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    b = mb.DeviceBatch(ctx, store, ref)
+    sc, lg = b.score_all()
+    wsc, wlg = co.score_all(ref, Y)
+    assert np.max(np.abs(sc - wsc)) <= SCORE_TOL
+    bad = np.nonzero(lg != wlg)[0]
+    for i in bad[:50]:      # any lag mismatch must be a tie within tolerance
+        _, _, ties = mo.score_series_batch(ref, Y[i:i + 1], want_ties=True)
+        assert lg[i] in ties[0]
+    assert bad.size <= 50
