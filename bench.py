@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- series-samples/s of Batch.Run on synthetic siggen-style data.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun)
+    python bench.py --impl reference ...                   (CPU arm: the oracle port)
+
+Workload (BASELINE.json configs[2], "C3", the configuration the north-star target is
+quoted on): S = 1,000,000 series x 1440 fp64 samples PER GPU (weak scaling: rank r owns
+global series [r*S, (r+1)*S)), reference = Rect(1.5, 720, 10)+noise, maxLag 60, topN 100,
+threshold 0.5, ungrouped.  A step is one Batch.Run over the resident slab; at N>1 each
+rank runs its shard, the shard partials are all-gathered over NCCL and merged.
+
+One JSON line is printed by rank 0 (see the repo prompt for the contract).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "go-muse_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "series-samples/sec (and % HBM roofline) for Batch.Run at 1/2/4/8 B200 vs host Go"
+UNIT = "series-samples/s"
+SEED = 20261018
+
+
+def workload(args):
+    return {
+        "workload": "C3: %d series x %d fp64 samples per GPU, maxLag=%d, topN=%d, threshold=%g, ungrouped "
+                    "(BASELINE.json configs[2])" % (args.series, args.length, args.max_lag, args.top_n, args.threshold),
+        "series_per_gpu": args.series, "series_len": args.length, "fft_len": int(2 ** int(np.ceil(np.log2(args.length)))),
+        "max_lag": args.max_lag, "top_n": args.top_n, "threshold": args.threshold, "group_by": None,
+        "mode": args.mode,
+        "l2": "inputs (%.2f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (args.series * args.length * 8 / 1e9),
+    }
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(args, Y, ref, steps, warmup, nthreads):
+    """The reference algorithm on the host cores: the C oracle port (go-muse itself is Go and
+    cannot be built here).  Returns (series-samples/s, ms per step)."""
+    from oracle import c_oracle as co
+    S, N = Y.shape
+    for _ in range(max(0, warmup)):
+        co.batch_run(ref, Y, None, args.max_lag, args.top_n, args.threshold, 0, nthreads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        co.batch_run(ref, Y, None, args.max_lag, args.top_n, args.threshold, 0, nthreads)
+    dt = (time.perf_counter() - t0) / steps
+    return S * N / dt, dt * 1e3
+
+
+def host_sample(args, n_rows):
+    import muse_b200 as mb
+    Y = np.empty((n_rows, args.length))
+    for i in range(n_rows):
+        Y[i] = mb.synth_row(SEED, i, args.length)
+    return Y
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import muse_b200 as mb
+    from oracle import c_oracle as co
+    cores = co.max_threads()
+    n_rows = min(args.series, args.cpu_sample)
+    Y = host_sample(args, n_rows)
+    ref = mb.synth_reference(SEED, args.length)
+    value, ms = cpu_arm(args, Y, ref, args.steps, args.warmup, cores)
+    sample = "first %d of the %d series of the workload per step (bounded so the run ends in minutes)" % (n_rows, args.series)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "go-muse is Go and no Go toolchain exists in this image: this arm times oracle/muse_oracle.c, a C "
+                "restatement of the reference path (pthreads, one worker per label group as muse_batch.go:104-128)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--series", type=int, default=1_000_000)
+    ap.add_argument("--length", type=int, default=1440)
+    ap.add_argument("--max-lag", type=int, default=60)
+    ap.add_argument("--top-n", type=int, default=100)
+    ap.add_argument("--threshold", type=float, default=0.5)
+    ap.add_argument("--mode", default="auto", choices=["auto", "exact", "screen"])
+    ap.add_argument("--cpu-sample", type=int, default=131072)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import muse_b200 as mb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: muse_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mode = {"auto": mb.MODE_AUTO, "exact": mb.MODE_EXACT, "screen": mb.MODE_SCREEN}[args.mode]
+
+    ctx = mb.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)          # library kernels and NCCL deps on one stream: one event bracket
+    S, N = args.series, args.length
+    store = mb.DeviceStore(ctx, N, 2, S)
+    store.append_synthetic(S, SEED, rank * S)
+    store.set_global_offset(rank * S)
+    ref = mb.synth_reference(SEED, N)
+    batch = mb.DeviceBatch(ctx, store, ref)
+
+    gather_buf = None
+
+    def step():
+        if world == 1:
+            return batch.run([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)
+        parts = batch.run_partial([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)
+        # one small all-gather of fixed-size partial records (top_n per rank, padded)
+        nonlocal gather_buf
+        rec = np.zeros(args.top_n, dtype=mb.PARTIAL_DTYPE)
+        rec["flags"] = 1
+        rec[:len(parts)] = parts
+        t = torch.from_numpy(rec.view(np.uint8)).cuda(non_blocking=True)
+        if gather_buf is None:
+            gather_buf = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(gather_buf, t)
+        allp = gather_buf.cpu().numpy().view(mb.PARTIAL_DTYPE)
+        return mb.merge_partials(allp, args.max_lag, args.top_n, args.threshold, 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    score_ms, launches, n_rescored = [], 0, 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        out = step()
+        tm = batch.timing()
+        score_ms.append(tm.score_ms)
+        launches += tm.n_launches
+        n_rescored += tm.n_rescored
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.finish()
+    total_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * S * N / (ms_per_step * 1e-3)
+    used_mode = {mb.MODE_EXACT: "exact", mb.MODE_SCREEN: "screen"}.get(batch.timing().mode, "?")
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), H2D inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((S, N), dtype=torch.float64, pin_memory=True)
+        store.read_rows_ptr(0, S, host.data_ptr())          # same rows as the resident slab, now on the host
+        ids = torch.zeros((S, 2), dtype=torch.int32, pin_memory=True)
+        ids[:, 0] = torch.arange(S, dtype=torch.int32) // 1000
+        ids[:, 1] = torch.arange(S, dtype=torch.int32) % 1000
+        st2 = mb.DeviceStore(ctx, N, 2, S)
+
+        def e2e_step():
+            st2.clear()
+            st2.append_host_ptr(host.data_ptr(), S, N, ids.data_ptr())     # Group.Add: H2D of the step's inputs
+            st2.set_global_offset(rank * S)
+            b2 = mb.DeviceBatch(ctx, st2, ref)                               # NewBatch
+            if world == 1:
+                r = b2.run([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)   # Run; results land on the host
+            else:
+                parts = b2.run_partial([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)
+                rec = np.zeros(args.top_n, dtype=mb.PARTIAL_DTYPE)
+                rec["flags"] = 1
+                rec[:len(parts)] = parts
+                tt = torch.from_numpy(rec.view(np.uint8)).cuda()
+                gb = torch.empty(world * tt.numel(), dtype=torch.uint8, device="cuda")
+                dist.all_gather_into_tensor(gb, tt)
+                r = mb.merge_partials(gb.cpu().numpy().view(mb.PARTIAL_DTYPE), args.max_lag, args.top_n, args.threshold, 0)
+            b2.close()
+            return r
+
+        r = e2e_step()
+        assert np.array_equal(r[2], out[2]) and np.array_equal(r[0], out[0]), "e2e result differs from the resident run"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * S * N / dt, "unit": UNIT, "h2d_bytes_per_step": int(S * N * 8 + S * 2 * 4 + N * 8),
+               "d2h_bytes_per_step": int(len(out[0]) * 24), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "api": "muse_group_clear + muse_group_append(pinned host rows) + muse_batch_create + muse_batch_run"}
+        st2.close()
+        del host
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        alg_bytes = S * (8 * N + 16)
+        k_ms = float(np.mean(score_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(used_mode, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "score_exact_kernel" if used_mode == "exact" else "score_screen_kernel",
+                    "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "frac_of_nominal_8TBps": achieved / 8000.0}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            from oracle import c_oracle as co
+            n_rows = min(S, args.cpu_sample)
+            Y = store.read_rows(0, n_rows)
+            cores = co.max_threads()
+            v, ms = cpu_arm(args, Y, ref, 2, 1, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "first %d of the %d series, 2 timed passes (%.0f ms each) of oracle/muse_oracle.c on %d threads"
+                             % (n_rows, S, ms, cores)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dict(workload(args), mode_used=used_mode,
+                                                rescored_per_step=n_rescored / max(1, args.steps)),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "top": {"score": float(out[0][0]) if len(out[0]) else None, "n": int(len(out[0]))},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

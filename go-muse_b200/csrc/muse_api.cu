@@ -49,7 +49,8 @@ extern "C" const char *muse_version(void) { return "muse_b200 0.1 (sm_100a)"; }
 struct muse_ctx {
     int device;
     int sm_count;
-    cudaStream_t stream;
+    cudaStream_t stream;       // the stream in use
+    cudaStream_t own_stream;   // created with the context
 };
 
 struct muse_group {
@@ -114,7 +115,8 @@ extern "C" int muse_ctx_create(int device, muse_ctx **out) {
     muse_ctx *c = new muse_ctx();
     c->device = device;
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     *out = c;
     return MUSE_OK;
 }
@@ -122,7 +124,7 @@ extern "C" int muse_ctx_create(int device, muse_ctx **out) {
 extern "C" void muse_ctx_destroy(muse_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -131,6 +133,24 @@ extern "C" int muse_ctx_synchronize(muse_ctx *c) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     return MUSE_OK;
+}
+
+extern "C" int muse_ctx_set_stream(muse_ctx *c, void *cuda_stream) {
+    if (!c) return fail(MUSE_ERR_INVALID_ARG, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return MUSE_OK;
+}
+
+extern "C" int muse_host_alloc(void **out, int64_t bytes) {
+    if (!out || bytes < 0) return fail(MUSE_ERR_INVALID_ARG, "muse_host_alloc: bad argument");
+    CU(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return MUSE_OK;
+}
+
+extern "C" void muse_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 // ------------------------------------------------------------------------------------
@@ -342,6 +362,25 @@ extern "C" int muse_group_set_global_offset(muse_group *g, int64_t first_global_
     return MUSE_OK;
 }
 
+extern "C" int muse_group_clear(muse_group *g) {
+    if (!g) return fail(MUSE_ERR_INVALID_ARG, "group is NULL");
+    CU(cudaSetDevice(g->ctx->device));
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    g->size = 0;
+    for (int k = 0; k < 16; k++) g->max_id[k] = -1;
+    return MUSE_OK;
+}
+
+extern "C" int muse_group_read_rows(muse_group *g, int64_t first, int64_t n_rows, double *out_rows) {
+    if (!g || !out_rows || first < 0 || n_rows < 0 || first + n_rows > g->size) return fail(MUSE_ERR_INVALID_ARG, "muse_group_read_rows: bad argument");
+    if (n_rows == 0) return MUSE_OK;
+    CU(cudaSetDevice(g->ctx->device));
+    CU(cudaMemcpy2DAsync(out_rows, sizeof(double) * (size_t)g->N, g->slab + (size_t)first * g->ld, sizeof(double) * (size_t)g->ld,
+                         sizeof(double) * (size_t)g->N, (size_t)n_rows, cudaMemcpyDeviceToHost, g->ctx->stream));
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    return MUSE_OK;
+}
+
 extern "C" int muse_group_read_row(muse_group *g, int64_t local_index, double *out_row) {
     if (!g || !out_row || local_index < 0 || local_index >= g->size) return fail(MUSE_ERR_INVALID_ARG, "muse_group_read_row: bad argument");
     CU(cudaSetDevice(g->ctx->device));
@@ -354,11 +393,10 @@ extern "C" int muse_group_read_row(muse_group *g, int64_t local_index, double *o
 // ------------------------------------------------------------------------------------
 // exact kernel dispatch
 // ------------------------------------------------------------------------------------
-template <int LOG2M, int MODE>
-static cudaError_t launch_exact_t(const ExactParams &p, cudaStream_t st) {
-    constexpr int LOG2P = LOG2M < 4 ? LOG2M : 4;
+template <int LOG2M, int LOG2P, int MODE, int MINB>
+static cudaError_t launch_exact_cfg(const ExactParams &p, cudaStream_t st) {
     using C = ExactCfg<LOG2M, LOG2P>;
-    auto kern = score_exact_kernel<LOG2M, LOG2P, MODE>;
+    auto kern = score_exact_kernel<LOG2M, LOG2P, MODE, MINB>;
     if (C::SMEM > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
@@ -366,6 +404,18 @@ static cudaError_t launch_exact_t(const ExactParams &p, cudaStream_t st) {
     const int64_t blocks = (p.count + C::SPB - 1) / C::SPB;
     kern<<<(unsigned)blocks, C::TB, C::SMEM, st>>>(p);
     return cudaGetLastError();
+}
+
+// points per thread of the exact kernel for each FFT size (also fixes the twiddle layout)
+static int exact_log2p(int log2m) { return log2m < 4 ? log2m : 4; }
+
+template <int LOG2M, int MODE>
+static cudaError_t launch_exact_t(const ExactParams &p, cudaStream_t st) {
+    constexpr int LOG2P = LOG2M < 4 ? LOG2M : 4;
+    // 512 resident threads per SM = a 128-register cap: measured best on B200 at n = 2048
+    // (16 warps/SM, 12.3 ms per 1M series vs 15.5 ms uncapped at 8 warps/SM; profiles/r01_tune_exact.txt)
+    constexpr int MINB = 512 / ExactCfg<LOG2M, LOG2P>::TB > 0 ? 512 / ExactCfg<LOG2M, LOG2P>::TB : 1;
+    return launch_exact_cfg<LOG2M, LOG2P, MODE, MINB>(p, st);
 }
 
 template <int MODE>
@@ -411,18 +461,22 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&b->ev[i]));
     CU(cudaMalloc(&b->d_ref, sizeof(double) * (size_t)g->ld));
     CU(cudaMalloc(&b->Xt, sizeof(cd) * (size_t)(M + 1)));
-    CU(cudaMalloc(&b->twM, sizeof(cd) * (size_t)M));
+    const int log2p = exact_log2p(b->log2m);
+    std::vector<cd> twM((size_t)M + 16);
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    fill_pass_twiddles(b->log2m, log2p, twM.data(), [&](long long num, long long den) {
+        return cd{(double)cosl(-PI2 * num / den), (double)sinl(-PI2 * num / den)};
+    });
+    CU(cudaMalloc(&b->twM, sizeof(cd) * twM.size()));
     CU(cudaMalloc(&b->twn, sizeof(cd) * (size_t)(M / 2 + 1)));
     CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
     CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
     CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
     CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
     // twiddle tables, correctly rounded from long double
-    std::vector<cd> twM((size_t)M), twn((size_t)(M / 2 + 1));
-    const long double PI2 = 6.283185307179586476925286766559005768L;
-    for (int64_t k = 0; k < M; k++) twM[(size_t)k] = cd{(double)cosl(-PI2 * k / M), (double)sinl(-PI2 * k / M)};
+    std::vector<cd> twn((size_t)(M / 2 + 1));
     for (int64_t k = 0; k <= M / 2; k++) twn[(size_t)k] = cd{(double)cosl(-PI2 * k / n), (double)sinl(-PI2 * k / n)};
-    CU(cudaMemcpyAsync(b->twM, twM.data(), sizeof(cd) * (size_t)M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->twM, twM.data(), sizeof(cd) * twM.size(), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b->twn, twn.data(), sizeof(cd) * (size_t)(M / 2 + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(b->d_ref, 0, sizeof(double) * (size_t)g->ld, st));
     CU(cudaMemcpyAsync(b->d_ref, ref, sizeof(double) * (size_t)ref_len, cudaMemcpyHostToDevice, st));

@@ -114,8 +114,8 @@ __device__ __forceinline__ void fft_to_last(cd *v, cd *sm, int t, const cd *__re
     }
 }
 
-template <int LOG2M, int LOG2P, int MODE>
-__global__ void __launch_bounds__(ExactCfg<LOG2M, LOG2P>::TB)
+template <int LOG2M, int LOG2P, int MODE, int MINB = 1>
+__global__ void __launch_bounds__(ExactCfg<LOG2M, LOG2P>::TB, MINB)
 score_exact_kernel(const ExactParams prm) {
     using G = Geo<LOG2M, LOG2P>;
     using C = ExactCfg<LOG2M, LOG2P>;

@@ -133,10 +133,38 @@ struct Geo {
     MUSE_HD static constexpr int log2r(int pass) {
         return (LOG2M - LOG2P * pass) < LOG2P ? (LOG2M - LOG2P * pass) : LOG2P;
     }
+    // Per-pass twiddle tables, concatenated.  Pass i (not the last) owns (R-1) rows of
+    // NCUR/R entries: row j-1, column p holds W_NCUR^(j*p).  With p = b >> LS and b the
+    // butterfly index, lanes of a warp read consecutive columns in pass 0 (coalesced) and
+    // a handful of distinct columns in later passes (broadcast) -- the flat W_M^k table
+    // read at stride j cost up to 60 L1 wavefronts per load.
+    MUSE_HD static constexpr int tw_cols(int pass) { return 1 << (LOG2M - LOG2P * pass - log2r(pass)); }
+    MUSE_HD static constexpr int tw_size(int pass) {
+        return (LOG2P * pass + log2r(pass) == LOG2M) ? 0 : ((1 << log2r(pass)) - 1) * tw_cols(pass);
+    }
+    MUSE_HD static constexpr int tw_off(int pass) { return pass == 0 ? 0 : tw_off(pass - 1) + tw_size(pass - 1); }
+    static constexpr int TW_TOTAL = tw_off(NPASS);
 };
 
+// Host-side fill of the per-pass twiddle tables (TW has .x/.y): W_NCUR^(j*p) = exp(-2*pi*i*j*p/NCUR).
+template <typename TW, typename FN>
+inline void fill_pass_twiddles(int log2m, int log2p, TW *out, FN unit_root /* (num, den) -> TW */) {
+    int off = 0;
+    for (int pass = 0;; pass++) {
+        const int ls = log2p * pass;
+        if (ls >= log2m && !(log2m == 0 && pass == 0)) break;
+        int lr = log2m - ls < log2p ? log2m - ls : log2p;
+        if (ls + lr == log2m) break;   // last pass: no twiddles
+        const int R = 1 << lr, ncur = 1 << (log2m - ls), cols = ncur / R;
+        for (int j = 1; j < R; j++)
+            for (int p = 0; p < cols; p++) out[off + (j - 1) * cols + p] = unit_root((long long)j * p, (long long)ncur);
+        off += (R - 1) * cols;
+    }
+}
+
 // One thread's share of one FFT pass: DFTs in registers, twiddles, scatter to smem.
-// v[c*R + j] holds input j of butterfly b = t + c*T.  tw[k] = exp(-2*pi*i*k/M).
+// v[c*R + j] holds input j of butterfly b = t + c*T.  tw = the per-pass tables of
+// Geo::tw_off / fill_pass_twiddles.
 template <int LOG2M, int LOG2P, int PASS, typename F, typename TW>
 MUSE_HD void fft_pass_compute_store(cx<F> *v, cx<F> *sm, int t, const TW *tw) {
     using G = Geo<LOG2M, LOG2P>;
@@ -145,6 +173,8 @@ MUSE_HD void fft_pass_compute_store(cx<F> *v, cx<F> *sm, int t, const TW *tw) {
     constexpr int R = 1 << LR;
     constexpr int NB = G::P / R;
     constexpr bool LAST = (LS + LR == LOG2M);
+    constexpr int COLS = G::tw_cols(PASS);
+    const TW *twp = tw + G::tw_off(PASS);
 #pragma unroll
     for (int c = 0; c < NB; c++) {
         Dft<R, F>::run(v + c * R);
@@ -155,8 +185,7 @@ MUSE_HD void fft_pass_compute_store(cx<F> *v, cx<F> *sm, int t, const TW *tw) {
         for (int j = 0; j < R; j++) {
             cx<F> val = v[c * R + Perm<R>::at(j)];
             if (!LAST && j > 0) {
-                // W_NCUR^(j*p) = W_M^(j*p*S); j*p < NCUR so the index stays below M
-                const TW w = tw[(j * p) << LS];
+                const TW w = twp[(j - 1) * COLS + p];     // W_NCUR^(j*p)
                 val = cmul(val, cx<F>{(F)w.x, (F)w.y});
             }
             sm[G::pad(q + ((R * p + j) << LS))] = val;

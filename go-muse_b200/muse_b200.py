@@ -93,6 +93,9 @@ ABI = {
     "muse_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "muse_ctx_destroy": (None, [_vp]),
     "muse_ctx_synchronize": (C.c_int, [_vp]),
+    "muse_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "muse_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_int64]),
+    "muse_host_free": (None, [_vp]),
     "muse_group_create": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_int64, C.POINTER(_vp)]),
     "muse_group_destroy": (None, [_vp]),
     "muse_group_append": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp]),
@@ -103,7 +106,9 @@ ABI = {
     "muse_group_size": (C.c_int64, [_vp]),
     "muse_group_series_len": (C.c_int64, [_vp]),
     "muse_group_set_global_offset": (C.c_int, [_vp, C.c_int64]),
+    "muse_group_clear": (C.c_int, [_vp]),
     "muse_group_read_row": (C.c_int, [_vp, C.c_int64, _dp]),
+    "muse_group_read_rows": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp]),
     "muse_batch_create": (C.c_int, [_vp, _vp, _dp, C.c_int64, C.POINTER(_vp)]),
     "muse_batch_destroy": (None, [_vp]),
     "muse_batch_fft_len": (C.c_int64, [_vp]),
@@ -158,6 +163,10 @@ class Context:
 
     def synchronize(self):
         _check(lib().muse_ctx_synchronize(self.h))
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Run on the given cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(lib().muse_ctx_set_stream(self.h, _vp(cuda_stream) if cuda_stream else None))
 
     def close(self):
         if self.h:
@@ -217,6 +226,18 @@ class DeviceStore:
 
     def size(self) -> int:
         return int(lib().muse_group_size(self.h))
+
+    def clear(self):
+        _check(lib().muse_group_clear(self.h))
+
+    def read_rows(self, first: int, n_rows: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((n_rows, self.series_len))
+        _check(lib().muse_group_read_rows(self.h, first, n_rows, out.ctypes.data_as(_vp)))
+        return out
+
+    def read_rows_ptr(self, first: int, n_rows: int, ptr: int):
+        _check(lib().muse_group_read_rows(self.h, first, n_rows, _vp(ptr)))
 
     def read_row(self, i: int) -> np.ndarray:
         out = np.zeros(self.series_len)

@@ -83,6 +83,12 @@ const char *muse_version(void);
 int  muse_ctx_create(int device, muse_ctx **out);
 void muse_ctx_destroy(muse_ctx *ctx);
 int  muse_ctx_synchronize(muse_ctx *ctx);
+/* Run all of this context's work on the caller's CUDA stream (a cudaStream_t, e.g. the
+ * host framework's current stream) instead of the context's own; NULL restores it. */
+int  muse_ctx_set_stream(muse_ctx *ctx, void *cuda_stream);
+/* Page-locked host memory for rows handed to muse_group_append (full-rate DMA). */
+int  muse_host_alloc(void **out, int64_t bytes);
+void muse_host_free(void *p);
 
 /* ---- series store ----------------------------------------------------------
  * Replaces Group{registry} + Series{y, labels} (group.go:7-56, series.go:8-42):
@@ -120,8 +126,11 @@ int64_t muse_group_size(const muse_group *g);        /* number of series, len(re
 int64_t muse_group_series_len(const muse_group *g);  /* Group.Length(), group.go:24-26 */
 /* Global index of this store's first series (multi-GPU shards); default 0. */
 int  muse_group_set_global_offset(muse_group *g, int64_t first_global_index);
-/* Read one row back (tests). */
+/* Forget every series but keep the allocation (refill with muse_group_append). */
+int  muse_group_clear(muse_group *g);
+/* Read rows back to the host: one row, or n_rows consecutive rows (dense [n_rows][len]). */
 int  muse_group_read_row(muse_group *g, int64_t local_index, double *out_row);
+int  muse_group_read_rows(muse_group *g, int64_t first, int64_t n_rows, double *out_rows);
 
 /* ---- batch -----------------------------------------------------------------
  * NewBatch (muse_batch.go:23-52): checks ref_len against the group

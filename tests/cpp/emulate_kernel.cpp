@@ -65,8 +65,10 @@ static int run_case(int N, unsigned seed, double tol, bool even_path) {
     std::vector<double> ref(N), y(N + 2);
     for (int i = 0; i < N; i++) { ref[i] = U(rng) + (i > N / 3 && i < N / 3 + 5 ? 3.0 : 0.0); y[i] = 50.0 + U(rng) + (i > N / 2 && i < N / 2 + 4 ? 2.5 : 0.0); }
     // tables
-    std::vector<cd> twM(M), twn(M / 2 + 1);
-    for (int k = 0; k < M; k++) twM[k] = cd{(double)cosl(-2 * PI_L * k / M), (double)sinl(-2 * PI_L * k / M)};
+    std::vector<cd> twM(G::TW_TOTAL + 1), twn(M / 2 + 1);
+    fill_pass_twiddles(LOG2M, LOG2P, twM.data(), [](long long num, long long den) {
+        return cd{(double)cosl(-2 * PI_L * num / den), (double)sinl(-2 * PI_L * num / den)};
+    });
     for (int k = 0; k <= M / 2; k++) twn[k] = cd{(double)cosl(-2 * PI_L * k / n), (double)sinl(-2 * PI_L * k / n)};
 
     // ---- reference spectrum through the same phases (MODE_REF of the kernel) ----
