@@ -14,6 +14,7 @@
 
 #include "../../include/muse_b200.h"
 #include "muse_exact.cuh"
+#include "muse_screen.cuh"
 #include "muse_select.cuh"
 #include "muse_synth.cuh"
 
@@ -82,6 +83,13 @@ struct muse_batch {
     int32_t *d_cidx, *d_sidx;
     unsigned long long *d_counters;   // [0] ncand, [1] nselected
     SelectState *d_sel;
+    // fp32 screening pass (n = 2048 / 512 ...): tables, bounds, survivor lists
+    int screen_ok;
+    cf *twp_f, *twn_f;
+    float *A_f;
+    float *d_U;
+    int32_t *d_list;
+    unsigned char *d_done;
     // group table
     int64_t table_cap;
     unsigned long long *d_gmax, *d_hkeys;
@@ -438,6 +446,42 @@ static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 
     return n;
 }
 
+// fp32 tables of the screening kernel; leaves screen_ok = 0 when the shape has no screening kernel
+static int screen_log2m_supported(int log2m) { return log2m == 10 || log2m == 8; }
+
+static int rc_screen_tables(muse_batch *b) {
+    b->screen_ok = 0;
+    if (!screen_log2m_supported(b->log2m) || (b->N & 1)) return MUSE_OK;
+    const int64_t M = b->n / 2;
+    const int log2p = b->log2m / 2;
+    cudaStream_t st = b->ctx->stream;
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    std::vector<cf> twp((size_t)M + 64), twn((size_t)M);
+    fill_pass_twiddles(b->log2m, log2p, twp.data(), [&](long long num, long long den) {
+        return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
+    });
+    for (int64_t k = 0; k < M; k++) twn[(size_t)k] = cf{(float)cosl(-PI2 * k / b->n), (float)sinl(-PI2 * k / b->n)};
+    std::vector<cd> X((size_t)M + 1);
+    CU(cudaMemcpyAsync(X.data(), b->Xt, sizeof(cd) * (size_t)(M + 1), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<float> A((size_t)M + 1);
+    for (int64_t k = 0; k <= M; k++) {
+        const double a = hypot(X[(size_t)k].x, X[(size_t)k].y) * ((k == 0 || k == M) ? 1.0 : 2.0);
+        float f = (float)a;
+        if ((double)f < a) f = nextafterf(f, INFINITY);   // round up: the bound must not shrink
+        A[(size_t)k] = f;
+    }
+    CU(cudaMalloc(&b->twp_f, sizeof(cf) * twp.size()));
+    CU(cudaMalloc(&b->twn_f, sizeof(cf) * twn.size()));
+    CU(cudaMalloc(&b->A_f, sizeof(float) * A.size()));
+    CU(cudaMemcpyAsync(b->twp_f, twp.data(), sizeof(cf) * twp.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->twn_f, twn.data(), sizeof(cf) * twn.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->A_f, A.data(), sizeof(float) * A.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    b->screen_ok = 1;
+    return MUSE_OK;
+}
+
 extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out) {
     if (!ctx || !g || !ref || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_create: NULL argument");
     if (g->ctx != ctx) return fail(MUSE_ERR_INVALID_ARG, "group belongs to another context");
@@ -499,6 +543,7 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
         muse_batch_destroy(b);
         return fail(MUSE_ERR_STDDEV_ZERO, "Invalid input query, Standard deviation of zero");
     }
+    rc_screen_tables(b);
     *out = b;
     return MUSE_OK;
 }
@@ -506,6 +551,8 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
 static void free_scratch(muse_batch *b) {
     cudaFree(b->d_score); cudaFree(b->d_lag); cudaFree(b->d_slot);
     cudaFree(b->d_ckey); cudaFree(b->d_skey); cudaFree(b->d_cidx); cudaFree(b->d_sidx);
+    cudaFree(b->d_U); cudaFree(b->d_list); cudaFree(b->d_done);
+    b->d_U = nullptr; b->d_list = nullptr; b->d_done = nullptr;
     b->d_score = nullptr; b->d_lag = nullptr; b->d_slot = nullptr;
     b->d_ckey = b->d_skey = nullptr; b->d_cidx = b->d_sidx = nullptr;
     b->scratch_cap = 0;
@@ -518,6 +565,7 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
     cudaFree(b->d_gmax); cudaFree(b->d_hkeys); cudaFree(b->d_gidx);
     cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
     cudaFree(b->d_flag); cudaFree(b->d_counters); cudaFree(b->d_sel);
+    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f);
     for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
 }
@@ -536,6 +584,9 @@ static int ensure_scratch(muse_batch *b) {
     CU(cudaMalloc(&b->d_skey, sizeof(unsigned long long) * (size_t)cap));
     CU(cudaMalloc(&b->d_cidx, sizeof(int32_t) * (size_t)cap));
     CU(cudaMalloc(&b->d_sidx, sizeof(int32_t) * (size_t)cap));
+    CU(cudaMalloc(&b->d_U, sizeof(float) * (size_t)cap));
+    CU(cudaMalloc(&b->d_list, sizeof(int32_t) * (size_t)cap));
+    CU(cudaMalloc(&b->d_done, (size_t)cap));
     b->scratch_cap = cap;
     return MUSE_OK;
 }
@@ -742,6 +793,33 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
     return MUSE_OK;
 }
 
+__global__ void gather_scores_kernel(const int32_t *__restrict__ idx, unsigned long long n, const double *__restrict__ score,
+                                     const int32_t *__restrict__ lag, double *__restrict__ out_s, int32_t *__restrict__ out_l) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out_s[i] = score[idx[i]];
+        out_l[i] = lag[idx[i]];
+    }
+}
+
+// (score, lag) of the series listed in d_idx (device) -> host vectors, one gather + two copies.
+// Uses d_skey / d_slot as staging (both are free at the call sites).
+static int gather_to_host(muse_batch *b, const int32_t *d_idx, size_t k, std::vector<double> &sc, std::vector<int32_t> &lg) {
+    sc.resize(k);
+    lg.resize(k);
+    if (k == 0) return MUSE_OK;
+    cudaStream_t st = b->ctx->stream;
+    double *ds = reinterpret_cast<double *>(b->d_skey);
+    int32_t *dl = reinterpret_cast<int32_t *>(b->d_slot);
+    gather_scores_kernel<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(d_idx, k, b->d_score, b->d_lag, ds, dl);
+    b->timing.n_launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sc.data(), ds, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(lg.data(), dl, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MUSE_OK;
+}
+
 // Fetch (score, lag) of the selected series from the device score arrays.
 static int fetch_scores(muse_batch *b, const std::vector<Rec> &recs, std::vector<double> &sc, std::vector<int32_t> &lg) {
     const size_t k = recs.size();
@@ -749,21 +827,180 @@ static int fetch_scores(muse_batch *b, const std::vector<Rec> &recs, std::vector
     lg.resize(k);
     if (k == 0) return MUSE_OK;
     cudaStream_t st = b->ctx->stream;
-    if (k > 4096) {   // bulk: copy everything once
-        const int64_t S = b->g->size;
-        std::vector<double> all((size_t)S);
-        std::vector<int32_t> alll((size_t)S);
-        CU(cudaMemcpyAsync(all.data(), b->d_score, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(alll.data(), b->d_lag, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        for (size_t i = 0; i < k; i++) { sc[i] = all[(size_t)recs[i].idx]; lg[i] = alll[(size_t)recs[i].idx]; }
-        return MUSE_OK;
+    std::vector<int32_t> hidx(k);
+    for (size_t i = 0; i < k; i++) hidx[i] = recs[i].idx;
+    CU(cudaMemcpyAsync(b->d_sidx, hidx.data(), sizeof(int32_t) * k, cudaMemcpyHostToDevice, st));
+    return gather_to_host(b, b->d_sidx, k, sc, lg);
+}
+
+template <int LOG2M>
+static cudaError_t launch_screen_t(const ScreenParams &p, cudaStream_t st) {
+    using C = ScreenCfg<LOG2M>;
+    auto kern = score_screen_kernel<LOG2M, 4>;
+    if (C::SMEM > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
     }
-    for (size_t i = 0; i < k; i++) {
-        CU(cudaMemcpyAsync(&sc[i], b->d_score + recs[i].idx, sizeof(double), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(&lg[i], b->d_lag + recs[i].idx, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    const int64_t blocks = (p.count + C::SPB - 1) / C::SPB;
+    kern<<<(unsigned)blocks, C::TB, C::SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_screen(int log2m, const ScreenParams &p, cudaStream_t st) {
+    switch (log2m) {
+        case 10: return launch_screen_t<10>(p, st);
+        case 8: return launch_screen_t<8>(p, st);
     }
+    return cudaErrorInvalidValue;
+}
+
+// idx list of every series with lo <= U (and not yet exact-scored); marks them done
+__global__ void survivors_kernel(const float *__restrict__ U, int64_t S, float lo, unsigned char *done,
+                                 int32_t *__restrict__ out, unsigned long long *n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = i < S && !done[i] && U[i] >= lo;
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) {
+        out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
+        done[i] = 1;
+    }
+}
+
+// candidates for the pilot: (U bits << 32, idx) of every series with U >= lo
+__global__ void pilot_candidates_kernel(const float *__restrict__ U, int64_t S, float lo, Cand out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = i < S && U[i] >= lo;
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(out.n, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) {
+        const unsigned long long pos = base + __popc(mask & ((1u << lane) - 1u));
+        out.key[pos] = ((unsigned long long)__float_as_uint(U[i])) << 32;   // U >= 0: bits order like values
+        out.idx[pos] = (int32_t)i;
+    }
+}
+
+__global__ void mark_done_kernel(const int32_t *__restrict__ idx, unsigned long long n, unsigned char *done) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) done[idx[i]] = 1;
+}
+
+// Screened scoring (ungrouped runs).  Every series gets the fp32 upper bound U; series that can
+// still reach the top_n cut-off are re-scored by the exact fp64 kernel; everything else keeps a
+// NaN score, which the selection stage ignores.  The result of the run is identical to
+// score_exact_all + selection:
+//   1. pilot: the K series with the largest U (U >= threshold) are scored exactly; the top_n-th
+//      best PASSING exact score among them is a valid lower bound `cut` on the final cut-off
+//      (threshold if fewer than top_n pass);
+//   2. every other series with U >= cut is scored exactly; a series with U < cut has an exact
+//      score < cut and cannot be among the top_n.
+static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
+    muse_group *g = b->g;
+    const int64_t S = g->size;
+    cudaStream_t st = b->ctx->stream;
+    *fell_back = false;
+    ScreenParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.slab = g->slab;
+    sp.ld = g->ld;
+    sp.count = S;
+    sp.N = (int)b->N;
+    sp.twp = b->twp_f;
+    sp.twn = b->twn_f;
+    sp.A = b->A_f;
+    sp.out_U = b->d_U;
+    CU(launch_screen(b->log2m, sp, st));
+    b->timing.n_launches++;
+    CU(cudaEventRecord(b->ev[1], st));
+    // scores default to NaN (= "cannot be in the result"), nothing exact-scored yet
+    CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));
+    CU(cudaMemsetAsync(b->d_lag, 0, sizeof(int32_t) * (size_t)S, st));
+    CU(cudaMemsetAsync(b->d_done, 0, (size_t)S, st));
+    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
+    const unsigned blocks = (unsigned)((S + 255) / 256);
+    const float thr_lo = a.threshold > 0 ? (float)a.threshold * 0.999999f : 0.f;   // never above the fp64 threshold
+    // ---- pilot: the ~K series with the largest bounds (any set works; a good one gives a tight cut) ----
+    const int64_t K = std::min<int64_t>(S, std::max<int64_t>(4 * a.top_n, 4096));
+    unsigned int *d_hist = reinterpret_cast<unsigned int *>(b->d_ckey);   // 8 KB of free scratch
+    CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * MUSE_U_BINS, st));
+    u_hist_kernel<<<(unsigned)std::min<int64_t>(blocks, (int64_t)b->ctx->sm_count * 8), 256, 0, st>>>(b->d_U, S, d_hist);
+    b->timing.n_launches++;
+    std::vector<unsigned int> hist(MUSE_U_BINS);
+    CU(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned int) * MUSE_U_BINS, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    // count of series with U >= lower edge of bin e (the kernel's own binning: conservative use only)
+    auto lower_edge = [](int e) { return (float)e / MUSE_U_SCALE * 0.99999f; };
+    float pilot_lo = thr_lo;
+    {
+        int64_t acc = 0;
+        int e = MUSE_U_BINS - 1;
+        for (; e > 0; e--) {
+            acc += hist[(size_t)e];
+            if (acc >= K) break;
+        }
+        pilot_lo = std::max(thr_lo, lower_edge(e));
+    }
+    CU(cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), st));
+    survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, pilot_lo, b->d_done, b->d_sidx, b->d_counters + 1);
+    b->timing.n_launches++;
+    unsigned long long npilot = 0;
+    CU(cudaMemcpyAsync(&npilot, b->d_counters + 1, sizeof(npilot), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int32_t *pilot_idx = b->d_sidx;
+    double cut = a.threshold;
+    if (npilot > 0) {
+        int rc = score_exact_all(b, 0, pilot_idx, (int64_t)npilot);
+        if (rc) return rc;
+        b->timing.n_rescored += (int64_t)npilot;
+        // exact scores of the pilot -> cut
+        std::vector<double> sc1;
+        std::vector<int32_t> lg1;
+        rc = gather_to_host(b, pilot_idx, (size_t)npilot, sc1, lg1);
+        if (rc) return rc;
+        std::vector<double> ps;
+        for (size_t i = 0; i < sc1.size(); i++) {
+            const int64_t lg = lg1[i];
+            if (sc1[i] == sc1[i] && (lg < 0 ? -lg : lg) <= a.max_lag && sc1[i] >= a.threshold) ps.push_back(sc1[i]);
+        }
+        if (a.top_n > 0 && (int64_t)ps.size() >= a.top_n) {
+            std::nth_element(ps.begin(), ps.begin() + (a.top_n - 1), ps.end(), std::greater<double>());
+            cut = std::max(cut, ps[(size_t)a.top_n - 1]);
+        }
+    }
+    // ---- everything else that can still reach `cut` ----
+    {
+        float cut_lo = (float)cut;
+        if ((double)cut_lo > cut) cut_lo = nextafterf(cut_lo, -INFINITY);   // round DOWN: never drop a contender
+        if (cut_lo < thr_lo) cut_lo = thr_lo;
+        if (cut_lo < pilot_lo) {
+            // how many would that be?  (histogram estimate, bin granularity)
+            int64_t est = 0;
+            for (int e = MUSE_U_BINS - 1; e >= 0 && lower_edge(e + 1) >= cut_lo; e--) est += hist[(size_t)e];
+            if (est > S / 2 && S > 8192) {   // the bound prunes too little here: score everything exactly
+                *fell_back = true;
+                return score_exact_all(b, 0, nullptr, S);
+            }
+            CU(cudaMemsetAsync(b->d_counters + 2, 0, sizeof(unsigned long long), st));
+            survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, cut_lo, b->d_done, b->d_list, b->d_counters + 2);
+            b->timing.n_launches++;
+            unsigned long long nrest = 0;
+            CU(cudaMemcpyAsync(&nrest, b->d_counters + 2, sizeof(nrest), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (nrest > 0) {
+                int rc = score_exact_all(b, 0, b->d_list, (int64_t)nrest);
+                if (rc) return rc;
+                b->timing.n_rescored += (int64_t)nrest;
+            }
+        }
+    }
     return MUSE_OK;
 }
 
@@ -773,6 +1010,18 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     memset(&b->timing, 0, sizeof(b->timing));
     cudaStream_t st = b->ctx->stream;
     CU(cudaEventRecord(b->ev[0], st));
+    // screening needs: a kernel for this FFT size, an ungrouped unsigned run, a sign filter that
+    // unsigned scores can pass, and a store big enough to be worth two extra round trips
+    const bool can_screen = b->screen_ok && a.n_key_cols == 0 && !a.signed_scores && a.sign_filter != MUSE_SIGN_NEG;
+    bool screen = can_screen && (a.mode == MUSE_MODE_SCREEN || (a.mode == MUSE_MODE_AUTO && b->g->size >= 16384));
+    if (screen) {
+        bool fell_back = false;
+        b->timing.mode = MUSE_MODE_SCREEN;
+        rc = score_screened(b, a, &fell_back);
+        if (rc) return rc;
+        CU(cudaEventRecord(b->ev[2], st));
+        return MUSE_OK;
+    }
     b->timing.mode = MUSE_MODE_EXACT;
     rc = score_exact_all(b, a.signed_scores, nullptr, b->g->size);
     if (rc) return rc;

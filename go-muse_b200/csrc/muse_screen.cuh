@@ -1,0 +1,176 @@
+// muse_screen.cuh -- fp32 screening pass: a rigorous UPPER BOUND on every series' score.
+//
+// For the score of xcorr.go:160-197 / muse_batch.go:74-77,
+//     score = min(1, max_k |cc[k]|),   cc[k] = (1/n) * sum_f C_f * exp(+2*pi*i*f*k/n),
+//     C_f = conj(Y_f) * X_f,
+// the triangle inequality gives  max_k |cc[k]| <= (1/n) * sum_f |Y_f| * |X_f|  =: U.
+// U needs only the FORWARD transform of the series, no inverse, no arg-max.  The kernel
+// computes U in fp32 (forward FFT_M of the half-length packing, split, |Y_f|, dot with the
+// precomputed |X_f| weights) and adds a slack that covers every fp32 rounding in the
+// chain, so that U >= exact fp64 score holds for every series.  Batch.Run then sends only
+// series whose U can still reach the top-N cut-off through the exact fp64 kernel
+// (muse_exact.cuh); its results are therefore identical to scoring everything exactly.
+//
+// Error budget (all in units of the normalised score, |cc| <= 1):
+//   * input: y - pivot is formed in fp64, then rounded to fp32: |err| <= 2^-24 * 2*max|y-mean|
+//     per sample, and max|y-mean| <= sqrt(N-1)*std, so the induced cc error is
+//     <= ||x'||_2 * sqrt(N) * 2^-23 * sqrt(N-1) * ... <= 2^-23 * sqrt(N) ~ 4.5e-6 at N = 1440;
+//   * fp32 FFT (radix-32 x radix-32): relative l2 error of the spectrum <~ 10 * 2^-24 ~ 6e-7,
+//     which moves U by at most ||X||_2*||dY||_2/n <= 6e-7;
+//   * mean, std, magnitude and accumulation roundings: each <= ~1e-6 relative.
+// The sum stays below 2e-5 for N <= 16384; SCREEN_SLACK = 2e-4 leaves a 10x margin and
+// costs nothing (a larger slack only lets a few more series through to the exact kernel).
+// tests/test_gpu_screen.py checks U >= exact on adversarial inputs (offsets of 1e9, spikes,
+// 1e-12 and 1e+12 amplitudes, trends) and records the smallest observed margin.
+#pragma once
+
+#include "muse_score.cuh"
+
+namespace muse {
+
+typedef cx<float> cf;
+
+#define MUSE_SCREEN_SLACK 2e-4f
+
+struct ScreenParams {
+    const double *slab;
+    int64_t ld;
+    int64_t count;
+    int N;
+    const cf *twp;        // per-pass twiddles (fill_pass_twiddles for (LOG2M, LOG2M/2)), fp32
+    const cf *twn;        // exp(-2*pi*i*k/n), k < M, fp32
+    const float *A;       // |X_k|/(2n) * (k == 0 || k == M ? 1 : 2), rounded up, M+1 entries
+    float *out_U;         // [count] upper bound on the score (already clamped to <= 1 + slack)
+};
+
+template <int LOG2M>
+struct ScreenCfg {
+    static_assert(LOG2M % 2 == 0, "screening kernel needs M = P*P");
+    static constexpr int LOG2P = LOG2M / 2;
+    using G = Geo<LOG2M, LOG2P>;
+    static constexpr int T = G::T;                   // == P, <= 32
+    static constexpr int TB = 128;
+    static constexpr int SPB = TB / T;
+    static constexpr int SM_ELEMS = G::MP + 1;
+    static constexpr size_t SMEM = (size_t)SPB * SM_ELEMS * sizeof(cf);
+};
+
+#if defined(__CUDACC__)
+
+template <int T>
+__device__ __forceinline__ float group_sum_f(float x) {
+#pragma unroll
+    for (int off = T / 2; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    return x;
+}
+
+template <int LOG2M, int MINB>
+__global__ void __launch_bounds__(ScreenCfg<LOG2M>::TB, MINB)
+score_screen_kernel(const ScreenParams prm) {
+    using C = ScreenCfg<LOG2M>;
+    using G = typename C::G;
+    constexpr int LOG2P = C::LOG2P, P = G::P, T = C::T, M = G::M, n = 2 * M;
+    static_assert(T <= 32, "one series per (sub-)warp");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int sib = threadIdx.x / T;
+    const int t = threadIdx.x - sib * T;
+    const int64_t pos = (int64_t)blockIdx.x * C::SPB + sib;
+    const bool valid = pos < prm.count;
+    const int64_t row = valid ? pos : prm.count - 1;
+    const double *rowp = prm.slab + row * prm.ld;
+    cf *sm = reinterpret_cast<cf *>(smem_raw) + (size_t)sib * C::SM_ELEMS;
+    const int N = prm.N;
+    const int pad = n - N;
+
+    // ---- load: (y - pivot) in fp64, then fp32 (N even: 16-byte loads) ----
+    const double pivot = __ldg(rowp);
+    const long long pivot_bits = __double_as_longlong(pivot);
+    bool varies = false;     // any sample whose bits differ from row[0]
+    cf v[P];
+    float s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < P; r++) {
+        const int i0 = 2 * (t + r * T) - pad;
+        cf val{0.f, 0.f};
+        if (i0 >= 0) {
+            const cd d = load_pair_stream(rowp + i0);
+            val.x = (float)(d.x - pivot);
+            val.y = (float)(d.y - pivot);
+            varies |= (__double_as_longlong(d.x) != pivot_bits) | (__double_as_longlong(d.y) != pivot_bits);
+        }
+        v[r] = val;
+        s1 += val.x + val.y;
+    }
+    const float mu = group_sum_f<T>(s1) / (float)N;
+    float ss = 0.f;
+#pragma unroll
+    for (int r = 0; r < P; r++) {
+        const int i0 = 2 * (t + r * T) - pad;
+        if (i0 >= 0) {
+            v[r].x -= mu;
+            v[r].y -= mu;
+            ss = fmaf(v[r].x, v[r].x, ss);
+            ss = fmaf(v[r].y, v[r].y, ss);
+        }
+    }
+    ss = group_sum_f<T>(ss);
+
+    // ---- forward FFT_M: radix-P pass through smem, radix-P pass in registers ----
+    fft_pass_compute_store<LOG2M, LOG2P, 0, float, cf>(v, sm, t, prm.twp);
+    __syncwarp();
+    fft_pass_load<LOG2M, LOG2P, 1, float>(v, sm, t);
+    Dft<P, float>::run(v);
+    // v[Perm<P>(j)] = Z[t + P*j]
+
+    // ---- |Y_k| for k = t + P*j; the mirror Z[M-k] sits in lane (P-t)%P, slot P-1-j
+    //      (lane 0: its own slot (P-j)%P) ----
+    const int lane = threadIdx.x & 31;
+    const int partner = (lane - t) + ((P - t) & (P - 1));
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        const cf zk = v[Perm<P>::at(j)];
+        const cf zp = v[Perm<P>::at(P - 1 - j)];
+        cf zm;
+        zm.x = __shfl_sync(0xffffffffu, zp.x, partner);
+        zm.y = __shfl_sync(0xffffffffu, zp.y, partner);
+        if (t == 0) zm = v[Perm<P>::at((P - j) & (P - 1))];
+        const int k = t + P * j;
+        const cf w = prm.twn[k];
+        const cf zmc = cconj(zm);
+        const cf e = cadd(zk, zmc);
+        const cf o = cmul_negi(csub(zk, zmc));
+        const cf wo = cmul(w, o);
+        const cf y = cadd(e, wo);                        // 2*Y_k
+        acc = fmaf(sqrtf(fmaf(y.x, y.x, y.y * y.y)), prm.A[k], acc);
+        if (k == 0) {                                    // Nyquist term 2*Y_M = e - w*o (w = 1)
+            const cf yn = csub(e, wo);
+            acc = fmaf(sqrtf(fmaf(yn.x, yn.x, yn.y * yn.y)), prm.A[M], acc);
+        }
+    }
+    acc = group_sum_f<T>(acc);
+    const bool any_varies = __ballot_sync(0xffffffffu, varies) >> (lane - t) & (T == 32 ? 0xffffffffu : ((1u << T) - 1u));
+
+    if (t == 0 && valid) {
+        const float var = ss / (float)(N - 1);
+        float U;
+        if (!any_varies) {
+            // every sample is bit-identical: the exact kernel finds std == 0 and scores exactly 0
+            // (xcorr.go:165-168), so 0 is a valid bound
+            U = 0.f;
+        } else if (!(var > 0.f) || !(var < 3.0e38f) || !(acc == acc)) {
+            // fp32 may flush a tiny variance to 0 or overflow a huge one: anything degenerate or
+            // non-finite goes to the exact kernel
+            U = 2.f;
+        } else {
+            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
+            if (!(U == U)) U = 2.f;
+        }
+        prm.out_U[pos] = U;
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace muse

@@ -170,10 +170,19 @@ __device__ __forceinline__ bool prefix_match(const SelectState *st, unsigned lon
 __global__ void select_round_kernel(SelectState *st, const unsigned long long *__restrict__ key,
                                     const int32_t *__restrict__ idx, unsigned long long ncand, int r) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool in = false;
+    unsigned d = 0;
     if (i < ncand) {
         const unsigned long long k = key[i];
         const unsigned ni = ~(unsigned)idx[i];
-        if (prefix_match(st, k, ni, r)) atomicAdd(&st->hist[digit_of(k, ni, r)], 1u);
+        in = prefix_match(st, k, ni, r);
+        d = digit_of(k, ni, r);
+    }
+    // scores cluster in a few digits: one atomic per distinct digit per warp, not per lane
+    const unsigned active = __ballot_sync(0xffffffffu, in);
+    if (in) {
+        const unsigned peers = __match_any_sync(active, d);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&st->hist[d], (unsigned)__popc(peers));
     }
     __shared__ bool last;
     __threadfence();
@@ -226,6 +235,25 @@ __global__ void select_gather_kernel(const SelectState *st, const unsigned long 
         out_key[pos] = k;
         out_idx[pos] = idx[i];
     }
+}
+
+// Histogram of the screening bounds U (shared-memory privatised), MUSE_U_BINS bins of width
+// 1/MUSE_U_SCALE; the last bin collects everything above.
+#define MUSE_U_BINS 2048
+#define MUSE_U_SCALE 2000.0f
+__global__ void u_hist_kernel(const float *__restrict__ U, int64_t S, unsigned int *__restrict__ hist) {
+    __shared__ unsigned int h[MUSE_U_BINS];
+    for (int b = threadIdx.x; b < MUSE_U_BINS; b += blockDim.x) h[b] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
+        const float u = U[i];
+        int b = u > 0.f ? (int)(u * MUSE_U_SCALE) : 0;
+        if (b >= MUSE_U_BINS) b = MUSE_U_BINS - 1;
+        atomicAdd(&h[b], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < MUSE_U_BINS; b += blockDim.x)
+        if (h[b]) atomicAdd(&hist[b], h[b]);
 }
 
 }  // namespace muse

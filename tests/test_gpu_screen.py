@@ -1,0 +1,94 @@
+"""The fp32 screening pass: its bound must dominate the exact score on every input, and a
+screened Batch.Run must return exactly what the all-exact run returns.  Needs a B200."""
+import numpy as np
+import pytest
+
+import muse_b200 as mb
+from oracle import c_oracle as co
+from oracle import muse_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return mb.default_context(0)
+
+
+def _adversarial(rng, S, N):
+    """siggen-style rows plus the inputs that stress an fp32 pass."""
+    Y = 0.1 * (rng.random((S, N)) - 0.5)
+    t = np.arange(N)
+    for i in range(S):
+        k = i % 12
+        if k == 0:      # rect pulse near the reference's
+            m = int(rng.integers(N // 2 - N // 8, N // 2 + N // 8))
+            Y[i, m:m + int(rng.integers(3, 20))] += rng.uniform(0.5, 40)
+        elif k == 1:    # huge offset, unit noise
+            Y[i] = 1e9 + rng.standard_normal(N)
+        elif k == 2:    # tiny amplitude
+            Y[i] *= 1e-12
+        elif k == 3:    # huge amplitude
+            Y[i] = 1e12 * rng.standard_normal(N)
+        elif k == 4:    # one spike
+            Y[i, int(rng.integers(0, N))] += 1e6
+        elif k == 5:    # trend
+            Y[i] += 3.0 * t + 1e5
+        elif k == 6:    # exact copy of a shifted reference-like pulse (score ~ 1)
+            Y[i] = 0.0
+            Y[i, N // 2 - 5:N // 2 + 5] = 2.0
+        elif k == 7:    # constant
+            Y[i] = 0.1
+        elif k == 8:    # almost constant: one ulp-level wiggle
+            Y[i] = 5.0
+            Y[i, 7] = np.nextafter(5.0, 6.0)
+        elif k == 9:    # first sample is an outlier (the fp32 pivot)
+            Y[i, 0] = 1e8
+        elif k == 10:   # sinusoid
+            Y[i] = np.sin(2 * np.pi * t / rng.uniform(5, 200)) + 100.0
+        # k == 11: plain noise
+    return Y
+
+
+@pytest.mark.parametrize("N", [1440, 1030, 2048, 480, 300])
+def test_screened_run_equals_exact_run(ctx, N):
+    rng = np.random.default_rng(N)
+    S = 30000
+    Y = _adversarial(rng, S, N)
+    ref = np.zeros(N)
+    ref[N // 2 - 5:N // 2 + 5] = 1.5
+    ref += 0.1 * (rng.random(N) - 0.5)
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    b = mb.DeviceBatch(ctx, store, ref)
+    for max_lag, top_n, thr in ((60, 100, 0.5), (15, 10, 0.0), (N, 2000, 0.9), (5, 50000, 0.2), (60, 0, 0.0)):
+        e = b.run([], max_lag, top_n, thr, mode=mb.MODE_EXACT)
+        assert b.timing().mode == mb.MODE_EXACT
+        s = b.run([], max_lag, top_n, thr, mode=mb.MODE_SCREEN)
+        t = b.timing()
+        assert t.mode == mb.MODE_SCREEN
+        for x, y in zip(e, s):
+            np.testing.assert_array_equal(x, y)      # bit-identical scores, lags and indices
+    # the oracle agrees with both
+    sc, lg, ix = b.run([], 60, 100, 0.5, mode=mb.MODE_SCREEN)
+    wsc, wlg, wix = co.batch_run(ref, Y, None, 60, 100, 0.5)
+    assert np.max(np.abs(sc - wsc), initial=0) <= 1e-9
+    same = ix == wix
+    assert same.mean() > 0.9    # identical rows (k == 6) tie exactly; order among ties may differ from the oracle's
+    assert set(ix[~same]) == set(wix[~same])
+
+
+def test_screening_prunes_on_siggen_data(ctx):
+    # on the benchmark's own data only a few percent may reach the exact kernel
+    N, S, seed = 1440, 200_000, 20261018
+    store = mb.DeviceStore(ctx, N, 2, S)
+    store.append_synthetic(S, seed, 0)
+    ref = mb.synth_reference(seed, N)
+    b = mb.DeviceBatch(ctx, store, ref)
+    e = b.run([], 60, 100, 0.5, mode=mb.MODE_EXACT)
+    s = b.run([], 60, 100, 0.5, mode=mb.MODE_AUTO)
+    t = b.timing()
+    assert t.mode == mb.MODE_SCREEN
+    for x, y in zip(e, s):
+        np.testing.assert_array_equal(x, y)
+    assert 100 <= t.n_rescored <= 0.15 * S
