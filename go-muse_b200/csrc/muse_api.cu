@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 #include <vector>
@@ -846,9 +847,22 @@ static cudaError_t launch_screen_t(const ScreenParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_screen_warp(const ScreenParams &p, cudaStream_t st) {
+    using C = ScreenWarpCfg<10>;
+    auto kern = score_screen_warp_kernel<10, 4>;
+    const size_t wb = C::warp_bytes(p.N);
+    const size_t smem = wb * C::WARPS;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t blocks = (p.count + C::WARPS - 1) / C::WARPS;
+    kern<<<(unsigned)blocks, C::TB, smem, st>>>(p, (unsigned)wb);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_screen(int log2m, const ScreenParams &p, cudaStream_t st) {
+    static const int variant = getenv("MUSE_SCREEN_VARIANT") ? atoi(getenv("MUSE_SCREEN_VARIANT")) : 1;
     switch (log2m) {
-        case 10: return launch_screen_t<10>(p, st);
+        case 10: return variant == 0 ? launch_screen_t<10>(p, st) : launch_screen_warp(p, st);
         case 8: return launch_screen_t<8>(p, st);
     }
     return cudaErrorInvalidValue;

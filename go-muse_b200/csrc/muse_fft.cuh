@@ -20,7 +20,7 @@
 namespace muse {
 
 template <typename F>
-struct cx {
+struct alignas(2 * sizeof(F)) cx {   // naturally aligned: one 64-/128-bit load or store per element
     F x, y;
 };
 
@@ -126,10 +126,12 @@ struct Geo {
     static constexpr int T = M / P;
     static constexpr int LOG2T = LOG2M - LOG2P;
     static constexpr int NPASS = LOG2M == 0 ? 1 : (LOG2M + LOG2P - 1) / LOG2P;
-    // shared-memory index padding: one element per 16 keeps the radix-16 scatter of the
-    // first pass conflict-free for 16-byte (and 8-byte) elements
-    static constexpr int MP = M + (M >> 4);
-    MUSE_HD static constexpr int pad(int i) { return i + (i >> 4); }
+    // shared-memory index padding: one element per P makes the stride of the first pass'
+    // radix-P scatter (thread p writes P*p + j) odd in elements, which is conflict-free for
+    // both 8-byte (half-warp) and 16-byte (quarter-warp) accesses
+    static constexpr int LOG2PAD = LOG2P > 0 ? LOG2P : 4;
+    static constexpr int MP = M + (M >> LOG2PAD);
+    MUSE_HD static constexpr int pad(int i) { return i + (i >> LOG2PAD); }
     MUSE_HD static constexpr int log2r(int pass) {
         return (LOG2M - LOG2P * pass) < LOG2P ? (LOG2M - LOG2P * pass) : LOG2P;
     }

@@ -171,6 +171,162 @@ score_screen_kernel(const ScreenParams prm) {
     }
 }
 
+// ---- one-warp-per-series variant with the row staged in shared memory by one bulk async
+// copy (cp.async.bulk, SASS UBLKCP, completion on an mbarrier).  The whole 11.5 KB row is in
+// flight at once without holding registers, so the DRAM latency is paid once per series
+// instead of once per register-limited batch of loads; with the row in smem the mean is taken
+// in fp64, and the zero padding needs no per-lane predicates: slot Nh = N/2 of the row buffer
+// holds (mean, mean), every out-of-range complex index is clamped to it, and (y - mean)
+// rounds to exactly 0 there.  The |Y_f| bound is invariant under rotation of the padded
+// series, so the zeros may trail (index 0 = first sample) instead of leading.
+// The row buffer is dead once the samples are in registers and is reused as the FFT exchange
+// buffer.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+template <int LOG2M>
+struct ScreenWarpCfg {
+    static_assert(LOG2M == 10, "one warp per series needs M = 32*32");
+    using G = Geo<LOG2M, 5>;
+    static constexpr int WARPS = 4;
+    static constexpr int TB = 32 * WARPS;
+    // per-warp bytes: the row (N doubles) + the (mean, mean) slot, or the padded exchange buffer
+    static size_t warp_bytes(int N) {
+        size_t row = ((size_t)N * 8 + 16 + 127) / 128 * 128;
+        size_t ex = ((size_t)(G::MP + 1) * sizeof(cf) + 127) / 128 * 128;
+        return row > ex ? row : ex;
+    }
+};
+
+template <int LOG2M, int MINB>
+__global__ void __launch_bounds__(ScreenWarpCfg<LOG2M>::TB, MINB)
+score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes) {
+    using C = ScreenWarpCfg<LOG2M>;
+    using G = typename C::G;
+    constexpr int LOG2P = 5, P = 32, M = G::M;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[C::WARPS];
+
+    const int w = threadIdx.x >> 5;
+    const int t = threadIdx.x & 31;
+    const int64_t pos = (int64_t)blockIdx.x * C::WARPS + w;
+    const bool valid = pos < prm.count;
+    const int64_t row = valid ? pos : prm.count - 1;
+    const double *rowp = prm.slab + row * prm.ld;
+    unsigned char *buf = smem_raw + (size_t)w * warp_bytes;
+    const int N = prm.N;
+    const int Nh = N >> 1;
+    const unsigned bar = smem_u32(&bars[w]);
+
+    if (t == 0) {
+        mbar_init(bar, 1);
+        bulk_load(smem_u32(buf), rowp, (unsigned)N * 8u, bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    // ---- mean in fp64 (xcorr.go:85-86) ----
+    const cd *rowc = reinterpret_cast<const cd *>(buf);
+    double s0 = 0.0, s1 = 0.0;
+    for (int j = t; j < Nh; j += 32) {
+        const cd d = rowc[j];
+        s0 += d.x;
+        s1 += d.y;
+    }
+    double sum = s0 + s1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const double mu = sum / (double)N;
+    if (t == 0) reinterpret_cast<cd *>(buf)[Nh] = cd{mu, mu};
+    __syncwarp();
+
+    // ---- centred samples to fp32 registers; out-of-range indices hit the (mean, mean) slot ----
+    cf v[P];
+    float ss = 0.f;
+#pragma unroll
+    for (int r = 0; r < P; r++) {
+        const int j = min(t + r * 32, Nh);
+        const cd d = rowc[j];
+        v[r].x = (float)(d.x - mu);
+        v[r].y = (float)(d.y - mu);
+        ss = fmaf(v[r].x, v[r].x, ss);
+        ss = fmaf(v[r].y, v[r].y, ss);
+    }
+    ss = group_sum_f<32>(ss);
+    __syncwarp();                                   // everyone is done reading the row: reuse it
+
+    cf *sm = reinterpret_cast<cf *>(buf);
+    fft_pass_compute_store<LOG2M, LOG2P, 0, float, cf>(v, sm, t, prm.twp);
+    __syncwarp();
+    fft_pass_load<LOG2M, LOG2P, 1, float>(v, sm, t);
+    Dft<P, float>::run(v);
+
+    const int partner = (P - t) & (P - 1);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        const cf zk = v[Perm<P>::at(j)];
+        const cf zp = v[Perm<P>::at(P - 1 - j)];
+        cf zm;
+        zm.x = __shfl_sync(0xffffffffu, zp.x, partner);
+        zm.y = __shfl_sync(0xffffffffu, zp.y, partner);
+        if (t == 0) zm = v[Perm<P>::at((P - j) & (P - 1))];
+        const int k = t + P * j;
+        const cf wk = prm.twn[k];
+        const cf zmc = cconj(zm);
+        const cf e = cadd(zk, zmc);
+        const cf o = cmul_negi(csub(zk, zmc));
+        const cf wo = cmul(wk, o);
+        const cf y = cadd(e, wo);
+        acc = fmaf(sqrtf(fmaf(y.x, y.x, y.y * y.y)), prm.A[k], acc);
+        if (k == 0) {
+            const cf yn = csub(e, wo);
+            acc = fmaf(sqrtf(fmaf(yn.x, yn.x, yn.y * yn.y)), prm.A[M], acc);
+        }
+    }
+    acc = group_sum_f<32>(acc);
+
+    if (t == 0 && valid) {
+        const float var = ss / (float)(N - 1);
+        float U;
+        if (ss == 0.f) {
+            // every (y - mean) rounded to 0 in fp32: constant series (exact score 0) or a variance
+            // below fp32 range; the exact kernel decides
+            U = 2.f;
+        } else if (!(var > 0.f) || !(var < 3.0e38f) || !(acc == acc)) {
+            U = 2.f;
+        } else {
+            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
+            if (!(U == U)) U = 2.f;
+        }
+        prm.out_U[pos] = U;
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace muse
