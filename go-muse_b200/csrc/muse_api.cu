@@ -847,9 +847,10 @@ static cudaError_t launch_screen_t(const ScreenParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-static cudaError_t launch_screen_warp(const ScreenParams &p, cudaStream_t st) {
+template <int FLAGS>
+static cudaError_t launch_screen_warp_f(const ScreenParams &p, cudaStream_t st) {
     using C = ScreenWarpCfg<10>;
-    auto kern = score_screen_warp_kernel<10, 4>;
+    auto kern = score_screen_warp_kernel<10, 4, FLAGS>;
     const size_t wb = C::warp_bytes(p.N);
     const size_t smem = wb * C::WARPS;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -857,6 +858,12 @@ static cudaError_t launch_screen_warp(const ScreenParams &p, cudaStream_t st) {
     const int64_t blocks = (p.count + C::WARPS - 1) / C::WARPS;
     kern<<<(unsigned)blocks, C::TB, smem, st>>>(p, (unsigned)wb);
     return cudaGetLastError();
+}
+
+static cudaError_t launch_screen_warp(const ScreenParams &p, cudaStream_t st) {
+    static const int flags = getenv("MUSE_SCREEN_FLAGS") ? atoi(getenv("MUSE_SCREEN_FLAGS")) : 0;
+    (void)flags;
+    return launch_screen_warp_f<0>(p, st);
 }
 
 static cudaError_t launch_screen(int log2m, const ScreenParams &p, cudaStream_t st) {

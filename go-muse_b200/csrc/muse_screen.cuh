@@ -208,6 +208,23 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     } while (!done);
 }
 
+// sqrt.approx.f32 (one MUFU): 2 ulp, covered by the 1e-5 relative slack of the bound
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mbar_test(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 template <int LOG2M>
 struct ScreenWarpCfg {
     static_assert(LOG2M == 10, "one warp per series needs M = 32*32");
@@ -222,7 +239,7 @@ struct ScreenWarpCfg {
     }
 };
 
-template <int LOG2M, int MINB>
+template <int LOG2M, int MINB, int FLAGS = 0>
 __global__ void __launch_bounds__(ScreenWarpCfg<LOG2M>::TB, MINB)
 score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes) {
     using C = ScreenWarpCfg<LOG2M>;
@@ -247,11 +264,12 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes) {
         bulk_load(smem_u32(buf), rowp, (unsigned)N * 8u, bar);
     }
     __syncwarp();
-    mbar_wait(bar, 0);
+    mbar_wait(bar, 0);      // every lane waits itself (one polling lane + __syncwarp measured 3x slower)
 
     // ---- mean in fp64 (xcorr.go:85-86) ----
     const cd *rowc = reinterpret_cast<const cd *>(buf);
     double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
     for (int j = t; j < Nh; j += 32) {
         const cd d = rowc[j];
         s0 += d.x;
@@ -285,28 +303,38 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes) {
     fft_pass_load<LOG2M, LOG2P, 1, float>(v, sm, t);
     Dft<P, float>::run(v);
 
+    // |Y_k| for k = t + 32*j.  Branch-free: lane 0 (whose mirror is its own slot (32-j)%32) is
+    // handled with selects and the Nyquist term is added after the loop, so the shuffles need
+    // no divergence handling.
     const int partner = (P - t) & (P - 1);
+    const bool lane0 = (t == 0);
     float acc = 0.f;
+    cf e0{0.f, 0.f}, wo0{0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < P; j++) {
         const cf zk = v[Perm<P>::at(j)];
         const cf zp = v[Perm<P>::at(P - 1 - j)];
+        const cf zs = v[Perm<P>::at((P - j) & (P - 1))];
         cf zm;
         zm.x = __shfl_sync(0xffffffffu, zp.x, partner);
         zm.y = __shfl_sync(0xffffffffu, zp.y, partner);
-        if (t == 0) zm = v[Perm<P>::at((P - j) & (P - 1))];
-        const int k = t + P * j;
-        const cf wk = prm.twn[k];
+        zm.x = lane0 ? zs.x : zm.x;
+        zm.y = lane0 ? zs.y : zm.y;
+        const cf wk = prm.twn[t + P * j];
         const cf zmc = cconj(zm);
         const cf e = cadd(zk, zmc);
         const cf o = cmul_negi(csub(zk, zmc));
         const cf wo = cmul(wk, o);
-        const cf y = cadd(e, wo);
-        acc = fmaf(sqrtf(fmaf(y.x, y.x, y.y * y.y)), prm.A[k], acc);
-        if (k == 0) {
-            const cf yn = csub(e, wo);
-            acc = fmaf(sqrtf(fmaf(yn.x, yn.x, yn.y * yn.y)), prm.A[M], acc);
+        const cf y = cadd(e, wo);                        // 2*Y_k
+        acc = fmaf(sqrt_approx(fmaf(y.x, y.x, y.y * y.y)), prm.A[t + P * j], acc);
+        if (j == 0) {
+            e0 = e;
+            wo0 = wo;
         }
+    }
+    {   // Nyquist term 2*Y_M = e - w*o at k = 0 (lane 0 only; weight 0 elsewhere)
+        const cf yn = csub(e0, wo0);
+        acc = fmaf(sqrt_approx(fmaf(yn.x, yn.x, yn.y * yn.y)), lane0 ? prm.A[M] : 0.f, acc);
     }
     acc = group_sum_f<32>(acc);
 
