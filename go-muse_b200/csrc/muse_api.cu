@@ -82,6 +82,9 @@ struct muse_batch {
     int64_t *d_slot;
     unsigned long long *d_ckey, *d_skey;
     int32_t *d_cidx, *d_sidx;
+    int32_t *d_clag, *d_slag;         // 2*lag + sign of the candidates (muse_select.cuh Cand)
+    unsigned char *h_pin;             // pinned mailbox for the small device->host results
+    size_t h_pin_bytes;
     unsigned long long *d_counters;   // [0] ncand, [1] nselected
     SelectState *d_sel;
     // fp32 screening pass (n = 2048 / 512 ...): tables, bounds, survivor lists
@@ -517,6 +520,8 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
     CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
     CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
     CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
+    b->h_pin_bytes = (size_t)4 << 20;
+    CU(cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault));
     CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
     // twiddle tables, correctly rounded from long double
     std::vector<cd> twn((size_t)(M / 2 + 1));
@@ -552,6 +557,8 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
 static void free_scratch(muse_batch *b) {
     cudaFree(b->d_score); cudaFree(b->d_lag); cudaFree(b->d_slot);
     cudaFree(b->d_ckey); cudaFree(b->d_skey); cudaFree(b->d_cidx); cudaFree(b->d_sidx);
+    cudaFree(b->d_clag); cudaFree(b->d_slag);
+    b->d_clag = b->d_slag = nullptr;
     cudaFree(b->d_U); cudaFree(b->d_list); cudaFree(b->d_done);
     b->d_U = nullptr; b->d_list = nullptr; b->d_done = nullptr;
     b->d_score = nullptr; b->d_lag = nullptr; b->d_slot = nullptr;
@@ -567,6 +574,7 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
     cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
     cudaFree(b->d_flag); cudaFree(b->d_counters); cudaFree(b->d_sel);
     cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f);
+    if (b->h_pin) cudaFreeHost(b->h_pin);
     for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
 }
@@ -585,6 +593,8 @@ static int ensure_scratch(muse_batch *b) {
     CU(cudaMalloc(&b->d_skey, sizeof(unsigned long long) * (size_t)cap));
     CU(cudaMalloc(&b->d_cidx, sizeof(int32_t) * (size_t)cap));
     CU(cudaMalloc(&b->d_sidx, sizeof(int32_t) * (size_t)cap));
+    CU(cudaMalloc(&b->d_clag, sizeof(int32_t) * (size_t)cap));
+    CU(cudaMalloc(&b->d_slag, sizeof(int32_t) * (size_t)cap));
     CU(cudaMalloc(&b->d_U, sizeof(float) * (size_t)cap));
     CU(cudaMalloc(&b->d_list, sizeof(int32_t) * (size_t)cap));
     CU(cudaMalloc(&b->d_done, (size_t)cap));
@@ -600,9 +610,11 @@ static int check_batch(muse_batch *b) {
 }
 
 // All series of the store through the exact kernel -> d_score / d_lag.
-static int score_exact_all(muse_batch *b, int signed_scores, const int32_t *idx, int64_t count) {
+static int score_exact_all(muse_batch *b, int signed_scores, const int32_t *idx, int64_t count,
+                           const unsigned long long *d_count = nullptr) {
     ExactParams p;
     memset(&p, 0, sizeof(p));
+    p.count_ptr = d_count;
     p.slab = b->g->slab;
     p.ld = b->g->ld;
     p.count = count;
@@ -677,8 +689,15 @@ struct RunArgs {
 };
 
 struct Rec {
-    unsigned long long key;
+    unsigned long long key;   // |score| bits
     int32_t idx;
+    int32_t lagsgn;           // 2*lag + (score < 0)
+    double score() const {
+        double a;
+        memcpy(&a, &key, sizeof(a));
+        return (lagsgn & 1) ? -a : a;
+    }
+    int32_t lag() const { return (lagsgn - (lagsgn & 1)) / 2; }
 };
 
 static int setup_group_table(muse_batch *b, const RunArgs &a, KeyCols &kc, GroupTable &gt) {
@@ -747,45 +766,61 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
         group_rep_kernel<<<blocks, 256, 0, st>>>(gt, b->d_score, S, b->d_slot);
         b->timing.n_launches += 2;
     }
-    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
+    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 2, st));
     FilterArgs f{a.max_lag, a.threshold, a.sign_filter, apply_filter};
-    Cand cand{b->d_ckey, b->d_cidx, b->d_counters};
+    Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
     emit_candidates_kernel<<<blocks, 256, 0, st>>>(gt, grouped ? b->d_slot : nullptr, b->d_score, b->d_lag, S, f, cand);
     b->timing.n_launches++;
     CU(cudaGetLastError());
-    unsigned long long ncand = 0;
-    CU(cudaMemcpyAsync(&ncand, b->d_counters, sizeof(ncand), cudaMemcpyDeviceToHost, st));
+    // one round trip: the count and the first CH records together (pinned mailbox)
+    const size_t CH = std::min<size_t>((size_t)S, 32768);
+    unsigned long long *h_n = reinterpret_cast<unsigned long long *>(b->h_pin);
+    unsigned long long *h_key = reinterpret_cast<unsigned long long *>(b->h_pin + 64);
+    int32_t *h_idx = reinterpret_cast<int32_t *>(b->h_pin + 64 + CH * 8);
+    int32_t *h_lag = reinterpret_cast<int32_t *>(b->h_pin + 64 + CH * 12);
+    CU(cudaMemcpyAsync(h_n, b->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_key, b->d_ckey, sizeof(unsigned long long) * CH, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_idx, b->d_cidx, sizeof(int32_t) * CH, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_lag, b->d_clag, sizeof(int32_t) * CH, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    const unsigned long long *src_key = b->d_ckey;
-    const int32_t *src_idx = b->d_cidx;
-    unsigned long long nsel = ncand;
-    if (limit >= 0 && ncand > (unsigned long long)limit && ncand > 4096ull) {
-        // device radix select of the `limit` best by (|score| desc, index asc)
-        if (limit == 0) return MUSE_OK;
-        SelectState init;
-        CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
-        unsigned long long want = (unsigned long long)limit;
-        CU(cudaMemcpyAsync(&b->d_sel->want, &want, sizeof(want), cudaMemcpyHostToDevice, st));
-        (void)init;
-        const unsigned sblocks = (unsigned)((ncand + 1023ull) / 1024ull);
-        for (int r = 0; r < 6; r++) select_round_kernel<<<sblocks, 1024, 0, st>>>(b->d_sel, b->d_ckey, b->d_cidx, ncand, r);
-        select_gather_kernel<<<sblocks, 1024, 0, st>>>(b->d_sel, b->d_ckey, b->d_cidx, ncand, b->d_skey, b->d_sidx, b->d_counters + 1);
-        b->timing.n_launches += 7;
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(&nsel, b->d_counters + 1, sizeof(nsel), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        src_key = b->d_skey;
-        src_idx = b->d_sidx;
-    }
-    if (nsel == 0) return MUSE_OK;
-    std::vector<unsigned long long> hk((size_t)nsel);
-    std::vector<int32_t> hi((size_t)nsel);
-    CU(cudaMemcpyAsync(hk.data(), src_key, sizeof(unsigned long long) * (size_t)nsel, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(hi.data(), src_idx, sizeof(int32_t) * (size_t)nsel, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    recs.resize((size_t)nsel);
-    for (size_t i = 0; i < (size_t)nsel; i++) recs[i] = Rec{hk[i], hi[i]};
+    const unsigned long long ncand = h_n[0];
+    b->timing.n_rescored = (int64_t)(h_n[2] + h_n[3]);     // screened runs: pilot + second round
+    if (ncand == 0) return MUSE_OK;
     auto better = [](const Rec &x, const Rec &y) { return x.key != y.key ? x.key > y.key : x.idx < y.idx; };
+    if (ncand <= CH) {
+        recs.resize((size_t)ncand);
+        for (size_t i = 0; i < (size_t)ncand; i++) recs[i] = Rec{h_key[i], h_idx[i], h_lag[i]};
+    } else {
+        const unsigned long long *src_key = b->d_ckey;
+        const int32_t *src_idx = b->d_cidx, *src_lag = b->d_clag;
+        unsigned long long nsel = ncand;
+        if (limit >= 0 && ncand > (unsigned long long)limit && ncand > 262144ull) {
+            // device radix select of the `limit` best by (|score| desc, index asc)
+            if (limit == 0) return MUSE_OK;
+            CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
+            unsigned long long want = (unsigned long long)limit;
+            CU(cudaMemcpyAsync(&b->d_sel->want, &want, sizeof(want), cudaMemcpyHostToDevice, st));
+            const unsigned sblocks = (unsigned)((ncand + 1023ull) / 1024ull);
+            for (int r = 0; r < 6; r++) select_round_kernel<<<sblocks, 1024, 0, st>>>(b->d_sel, b->d_ckey, b->d_cidx, ncand, r);
+            select_gather_kernel<<<sblocks, 1024, 0, st>>>(b->d_sel, b->d_ckey, b->d_cidx, ncand, b->d_clag, b->d_skey, b->d_sidx,
+                                                           b->d_slag, b->d_counters + 1);
+            b->timing.n_launches += 7;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(&nsel, b->d_counters + 1, sizeof(nsel), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            src_key = b->d_skey;
+            src_idx = b->d_sidx;
+            src_lag = b->d_slag;
+        }
+        std::vector<unsigned long long> hk((size_t)nsel);
+        std::vector<int32_t> hi((size_t)nsel), hl((size_t)nsel);
+        CU(cudaMemcpyAsync(hk.data(), src_key, sizeof(unsigned long long) * (size_t)nsel, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hi.data(), src_idx, sizeof(int32_t) * (size_t)nsel, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hl.data(), src_lag, sizeof(int32_t) * (size_t)nsel, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        recs.resize((size_t)nsel);
+        for (size_t i = 0; i < (size_t)nsel; i++) recs[i] = Rec{hk[i], hi[i], hl[i]};
+    }
     if (limit >= 0 && recs.size() > (size_t)limit) {
         std::nth_element(recs.begin(), recs.begin() + limit, recs.end(), better);
         recs.resize((size_t)limit);
@@ -794,44 +829,14 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
     return MUSE_OK;
 }
 
-__global__ void gather_scores_kernel(const int32_t *__restrict__ idx, unsigned long long n, const double *__restrict__ score,
-                                     const int32_t *__restrict__ lag, double *__restrict__ out_s, int32_t *__restrict__ out_l) {
+__global__ void gather_scores_kernel(const int32_t *__restrict__ idx, const unsigned long long *__restrict__ n,
+                                     const double *__restrict__ score, const int32_t *__restrict__ lag,
+                                     double *__restrict__ out_s, int32_t *__restrict__ out_l) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
+    if (i < *n) {
         out_s[i] = score[idx[i]];
         out_l[i] = lag[idx[i]];
     }
-}
-
-// (score, lag) of the series listed in d_idx (device) -> host vectors, one gather + two copies.
-// Uses d_skey / d_slot as staging (both are free at the call sites).
-static int gather_to_host(muse_batch *b, const int32_t *d_idx, size_t k, std::vector<double> &sc, std::vector<int32_t> &lg) {
-    sc.resize(k);
-    lg.resize(k);
-    if (k == 0) return MUSE_OK;
-    cudaStream_t st = b->ctx->stream;
-    double *ds = reinterpret_cast<double *>(b->d_skey);
-    int32_t *dl = reinterpret_cast<int32_t *>(b->d_slot);
-    gather_scores_kernel<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(d_idx, k, b->d_score, b->d_lag, ds, dl);
-    b->timing.n_launches++;
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(sc.data(), ds, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(lg.data(), dl, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return MUSE_OK;
-}
-
-// Fetch (score, lag) of the selected series from the device score arrays.
-static int fetch_scores(muse_batch *b, const std::vector<Rec> &recs, std::vector<double> &sc, std::vector<int32_t> &lg) {
-    const size_t k = recs.size();
-    sc.resize(k);
-    lg.resize(k);
-    if (k == 0) return MUSE_OK;
-    cudaStream_t st = b->ctx->stream;
-    std::vector<int32_t> hidx(k);
-    for (size_t i = 0; i < k; i++) hidx[i] = recs[i].idx;
-    CU(cudaMemcpyAsync(b->d_sidx, hidx.data(), sizeof(int32_t) * k, cudaMemcpyHostToDevice, st));
-    return gather_to_host(b, b->d_sidx, k, sc, lg);
 }
 
 template <int LOG2M>
@@ -918,11 +923,13 @@ __global__ void mark_done_kernel(const int32_t *__restrict__ idx, unsigned long 
 // still reach the top_n cut-off are re-scored by the exact fp64 kernel; everything else keeps a
 // NaN score, which the selection stage ignores.  The result of the run is identical to
 // score_exact_all + selection:
-//   1. pilot: the K series with the largest U (U >= threshold) are scored exactly; the top_n-th
+//   1. pilot: the ~K series with the largest U (U >= threshold) are scored exactly; the top_n-th
 //      best PASSING exact score among them is a valid lower bound `cut` on the final cut-off
 //      (threshold if fewer than top_n pass);
 //   2. every other series with U >= cut is scored exactly; a series with U < cut has an exact
 //      score < cut and cannot be among the top_n.
+// Two host round trips (histogram of U; exact scores of the pilot); the list lengths stay on the
+// device and the exact kernel is launched over an upper bound taken from the histogram.
 static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
     muse_group *g = b->g;
     const int64_t S = g->size;
@@ -943,53 +950,67 @@ static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
     CU(cudaEventRecord(b->ev[1], st));
     // scores default to NaN (= "cannot be in the result"), nothing exact-scored yet
     CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));
-    CU(cudaMemsetAsync(b->d_lag, 0, sizeof(int32_t) * (size_t)S, st));
     CU(cudaMemsetAsync(b->d_done, 0, (size_t)S, st));
-    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
     const unsigned blocks = (unsigned)((S + 255) / 256);
     const float thr_lo = a.threshold > 0 ? (float)a.threshold * 0.999999f : 0.f;   // never above the fp64 threshold
-    // ---- pilot: the ~K series with the largest bounds (any set works; a good one gives a tight cut) ----
-    const int64_t K = std::min<int64_t>(S, std::max<int64_t>(4 * a.top_n, 4096));
+    // ---- histogram of the bounds ----
     unsigned int *d_hist = reinterpret_cast<unsigned int *>(b->d_ckey);   // 8 KB of free scratch
     CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * MUSE_U_BINS, st));
     u_hist_kernel<<<(unsigned)std::min<int64_t>(blocks, (int64_t)b->ctx->sm_count * 8), 256, 0, st>>>(b->d_U, S, d_hist);
     b->timing.n_launches++;
-    std::vector<unsigned int> hist(MUSE_U_BINS);
-    CU(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned int) * MUSE_U_BINS, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_pin, d_hist, sizeof(unsigned int) * MUSE_U_BINS, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    // count of series with U >= lower edge of bin e (the kernel's own binning: conservative use only)
+    std::vector<unsigned int> hist(MUSE_U_BINS);      // the mailbox is reused below
+    memcpy(hist.data(), b->h_pin, sizeof(unsigned int) * MUSE_U_BINS);
+    // the kernel bins with (int)(u * SCALE); lower_edge() is a value certainly not above the bin's floor
     auto lower_edge = [](int e) { return (float)e / MUSE_U_SCALE * 0.99999f; };
+    // upper bound on #{U >= lo}: every bin from the one just below lo's upwards
+    auto count_ub = [&](float lo) {
+        int e0 = (int)(lo * MUSE_U_SCALE) - 1;
+        if (e0 < 0) e0 = 0;
+        int64_t c = 0;
+        for (int e = e0; e < MUSE_U_BINS; e++) c += hist[e];
+        return c;
+    };
+    // ---- pilot: the ~K series with the largest bounds (any set works; a good one gives a tight cut) ----
+    const int64_t K = std::min<int64_t>(S, std::max<int64_t>(4 * a.top_n, 1024));
     float pilot_lo = thr_lo;
     {
         int64_t acc = 0;
         int e = MUSE_U_BINS - 1;
         for (; e > 0; e--) {
-            acc += hist[(size_t)e];
+            acc += hist[e];
             if (acc >= K) break;
         }
         pilot_lo = std::max(thr_lo, lower_edge(e));
     }
-    CU(cudaMemsetAsync(b->d_counters + 1, 0, sizeof(unsigned long long), st));
-    survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, pilot_lo, b->d_done, b->d_sidx, b->d_counters + 1);
-    b->timing.n_launches++;
-    unsigned long long npilot = 0;
-    CU(cudaMemcpyAsync(&npilot, b->d_counters + 1, sizeof(npilot), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const int32_t *pilot_idx = b->d_sidx;
+    const int64_t pilot_ub = std::min<int64_t>(S, count_ub(pilot_lo));
     double cut = a.threshold;
-    if (npilot > 0) {
-        int rc = score_exact_all(b, 0, pilot_idx, (int64_t)npilot);
+    if (pilot_ub > 0) {
+        survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, pilot_lo, b->d_done, b->d_sidx, b->d_counters + 2);
+        b->timing.n_launches++;
+        int rc = score_exact_all(b, 0, b->d_sidx, pilot_ub, b->d_counters + 2);
         if (rc) return rc;
-        b->timing.n_rescored += (int64_t)npilot;
-        // exact scores of the pilot -> cut
-        std::vector<double> sc1;
-        std::vector<int32_t> lg1;
-        rc = gather_to_host(b, pilot_idx, (size_t)npilot, sc1, lg1);
-        if (rc) return rc;
+        // exact (score, lag) of the pilot -> cut.  Entries past the real count are never read.
+        double *ds = reinterpret_cast<double *>(b->d_skey);
+        int32_t *dl = reinterpret_cast<int32_t *>(b->d_slot);
+        gather_scores_kernel<<<(unsigned)((pilot_ub + 255) / 256), 256, 0, st>>>(b->d_sidx, b->d_counters + 2, b->d_score, b->d_lag, ds, dl);
+        b->timing.n_launches++;
+        const size_t kk = (size_t)pilot_ub;
+        if (64 + kk * 12 > b->h_pin_bytes) return fail(MUSE_ERR_UNSUPPORTED, "pilot of %zu series exceeds the mailbox", kk);
+        unsigned long long *h_n = reinterpret_cast<unsigned long long *>(b->h_pin);
+        double *hs = reinterpret_cast<double *>(b->h_pin + 64);
+        int32_t *hl = reinterpret_cast<int32_t *>(b->h_pin + 64 + kk * 8);
+        CU(cudaMemcpyAsync(h_n, b->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hs, ds, sizeof(double) * kk, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(hl, dl, sizeof(int32_t) * kk, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const size_t npilot = (size_t)std::min<unsigned long long>(h_n[0], kk);
         std::vector<double> ps;
-        for (size_t i = 0; i < sc1.size(); i++) {
-            const int64_t lg = lg1[i];
-            if (sc1[i] == sc1[i] && (lg < 0 ? -lg : lg) <= a.max_lag && sc1[i] >= a.threshold) ps.push_back(sc1[i]);
+        ps.reserve(npilot);
+        for (size_t i = 0; i < npilot; i++) {
+            const int64_t lg = hl[i];
+            if (hs[i] == hs[i] && (lg < 0 ? -lg : lg) <= a.max_lag && hs[i] >= a.threshold) ps.push_back(hs[i]);
         }
         if (a.top_n > 0 && (int64_t)ps.size() >= a.top_n) {
             std::nth_element(ps.begin(), ps.begin() + (a.top_n - 1), ps.end(), std::greater<double>());
@@ -997,29 +1018,20 @@ static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
         }
     }
     // ---- everything else that can still reach `cut` ----
-    {
-        float cut_lo = (float)cut;
-        if ((double)cut_lo > cut) cut_lo = nextafterf(cut_lo, -INFINITY);   // round DOWN: never drop a contender
-        if (cut_lo < thr_lo) cut_lo = thr_lo;
-        if (cut_lo < pilot_lo) {
-            // how many would that be?  (histogram estimate, bin granularity)
-            int64_t est = 0;
-            for (int e = MUSE_U_BINS - 1; e >= 0 && lower_edge(e + 1) >= cut_lo; e--) est += hist[(size_t)e];
-            if (est > S / 2 && S > 8192) {   // the bound prunes too little here: score everything exactly
-                *fell_back = true;
-                return score_exact_all(b, 0, nullptr, S);
-            }
-            CU(cudaMemsetAsync(b->d_counters + 2, 0, sizeof(unsigned long long), st));
-            survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, cut_lo, b->d_done, b->d_list, b->d_counters + 2);
+    float cut_lo = (float)cut;
+    if ((double)cut_lo > cut) cut_lo = nextafterf(cut_lo, -INFINITY);   // round DOWN: never drop a contender
+    if (cut_lo < thr_lo) cut_lo = thr_lo;
+    if (cut_lo < pilot_lo) {
+        const int64_t rest_ub = std::min<int64_t>(S, count_ub(cut_lo));
+        if (rest_ub > S / 2 && S > 8192) {   // the bound prunes too little here: score everything exactly
+            *fell_back = true;
+            return score_exact_all(b, 0, nullptr, S);
+        }
+        if (rest_ub > 0) {
+            survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, cut_lo, b->d_done, b->d_list, b->d_counters + 3);
             b->timing.n_launches++;
-            unsigned long long nrest = 0;
-            CU(cudaMemcpyAsync(&nrest, b->d_counters + 2, sizeof(nrest), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            if (nrest > 0) {
-                int rc = score_exact_all(b, 0, b->d_list, (int64_t)nrest);
-                if (rc) return rc;
-                b->timing.n_rescored += (int64_t)nrest;
-            }
+            int rc = score_exact_all(b, 0, b->d_list, rest_ub, b->d_counters + 3);
+            if (rc) return rc;
         }
     }
     return MUSE_OK;
@@ -1031,6 +1043,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     memset(&b->timing, 0, sizeof(b->timing));
     cudaStream_t st = b->ctx->stream;
     CU(cudaEventRecord(b->ev[0], st));
+    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
     // screening needs: a kernel for this FFT size, an ungrouped unsigned run, a sign filter that
     // unsigned scores can pass, and a store big enough to be worth two extra round trips
     const bool can_screen = b->screen_ok && a.n_key_cols == 0 && !a.signed_scores && a.sign_filter != MUSE_SIGN_NEG;
@@ -1078,13 +1091,9 @@ extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t
     std::vector<Rec> recs;
     rc = run_select(b, a, 1, top_n, recs);
     if (rc) return rc;
-    std::vector<double> sc;
-    std::vector<int32_t> lg;
-    rc = fetch_scores(b, recs, sc, lg);
-    if (rc) return rc;
     for (size_t i = 0; i < recs.size(); i++) {
-        scores[i] = sc[i];
-        lags[i] = lg[i];
+        scores[i] = recs[i].score();
+        lags[i] = recs[i].lag();
         series_idx[i] = b->g->global_offset + recs[i].idx;
     }
     *n_out = (int64_t)recs.size();
@@ -1160,10 +1169,6 @@ extern "C" int muse_batch_run_partial(muse_batch *b, const int32_t *key_cols, in
     rc = run_select(b, a, grouped ? 0 : 1, grouped ? -1 : top_n, recs);
     if (rc) return rc;
     if ((int64_t)recs.size() > capacity) return fail(MUSE_ERR_INVALID_ARG, "partial capacity %lld < %zu records", (long long)capacity, recs.size());
-    std::vector<double> sc;
-    std::vector<int32_t> lg;
-    rc = fetch_scores(b, recs, sc, lg);
-    if (rc) return rc;
     std::vector<uint64_t> keys;
     if (grouped) {
         rc = host_keys(b, a, recs, keys);
@@ -1172,8 +1177,8 @@ extern "C" int muse_batch_run_partial(muse_batch *b, const int32_t *key_cols, in
     for (size_t i = 0; i < recs.size(); i++) {
         out[i].series_idx = b->g->global_offset + recs[i].idx;
         out[i].group_key = grouped ? keys[i] : (uint64_t)out[i].series_idx;
-        out[i].score = sc[i];
-        out[i].lag = lg[i];
+        out[i].score = recs[i].score();
+        out[i].lag = recs[i].lag();
         out[i].flags = 0;
     }
     *n_out = (int64_t)recs.size();

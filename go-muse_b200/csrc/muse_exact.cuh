@@ -16,7 +16,8 @@ enum { MODE_SCORE = 0, MODE_REF = 1, MODE_CC = 2 };
 struct ExactParams {
     const double *slab;      // [rows][ld] fp64
     int64_t ld;              // row stride in doubles (multiple of 16)
-    int64_t count;           // series to process
+    int64_t count;           // series to process (an upper bound when count_ptr is set)
+    const unsigned long long *count_ptr;   // optional: actual count in device memory (no host round trip)
     const int32_t *idx;      // optional gather list (local row numbers), else NULL
     int N;                   // series length
     int signed_scores;
@@ -120,14 +121,16 @@ score_exact_kernel(const ExactParams prm) {
     using G = Geo<LOG2M, LOG2P>;
     using C = ExactCfg<LOG2M, LOG2P>;
     constexpr int T = C::T, M = G::M, n = 2 * M;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red[48];
 
     const int sib = threadIdx.x / T;
     const int t = threadIdx.x - sib * T;
     const int64_t pos = (int64_t)blockIdx.x * C::SPB + sib;
-    const bool valid = pos < prm.count;
-    const int64_t cpos = valid ? pos : prm.count - 1;
+    const int64_t count = prm.count_ptr ? (int64_t)*prm.count_ptr : prm.count;
+    if ((int64_t)blockIdx.x * C::SPB >= count) return;      // whole block beyond the list (uniform)
+    const bool valid = pos < count;
+    const int64_t cpos = valid ? pos : count - 1;
     const int64_t row = prm.idx ? (int64_t)prm.idx[cpos] : cpos;
     const double *rowp = prm.slab + row * prm.ld;
     cd *sm = reinterpret_cast<cd *>(smem_raw) + (size_t)sib * C::SM_ELEMS;

@@ -71,7 +71,7 @@ score_screen_kernel(const ScreenParams prm) {
     using G = typename C::G;
     constexpr int LOG2P = C::LOG2P, P = G::P, T = C::T, M = G::M, n = 2 * M;
     static_assert(T <= 32, "one series per (sub-)warp");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int sib = threadIdx.x / T;
     const int t = threadIdx.x - sib * T;

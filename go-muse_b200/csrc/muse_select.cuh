@@ -111,6 +111,7 @@ __device__ __forceinline__ bool passed(const FilterArgs &f, double sc, int lag) 
 struct Cand {
     unsigned long long *key;   // |score| bits
     int32_t *idx;              // local series index
+    int32_t *lagsgn;           // 2*lag + (score < 0)
     unsigned long long *n;     // counter
 };
 
@@ -139,6 +140,7 @@ __global__ void emit_candidates_kernel(GroupTable gt, const int64_t *__restrict_
         const unsigned long long pos = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
         out.key[pos] = score_bits(sc);
         out.idx[pos] = (int32_t)i;
+        out.lagsgn[pos] = 2 * lag[i] + (sc < 0.0 ? 1 : 0);
     }
 }
 
@@ -223,8 +225,9 @@ __global__ void select_round_kernel(SelectState *st, const unsigned long long *_
 // Gather every candidate whose composite is >= the selected boundary.
 __global__ void select_gather_kernel(const SelectState *st, const unsigned long long *__restrict__ key,
                                      const int32_t *__restrict__ idx, unsigned long long ncand,
+                                     const int32_t *__restrict__ lagsgn,
                                      unsigned long long *__restrict__ out_key, int32_t *__restrict__ out_idx,
-                                     unsigned long long *out_n) {
+                                     int32_t *__restrict__ out_lagsgn, unsigned long long *out_n) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncand) return;
     const unsigned long long k = key[i];
@@ -234,6 +237,7 @@ __global__ void select_gather_kernel(const SelectState *st, const unsigned long 
         const unsigned long long pos = atomicAdd(out_n, 1ull);
         out_key[pos] = k;
         out_idx[pos] = idx[i];
+        out_lagsgn[pos] = lagsgn[i];
     }
 }
 
