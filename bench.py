@@ -197,23 +197,12 @@ def main():
     ref = mb.synth_reference(SEED, N)
     batch = mb.DeviceBatch(ctx, store, ref)
 
-    gather_buf = None
-
     def step():
         if world == 1:
             return batch.run([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)
         parts = batch.run_partial([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)
-        # one small all-gather of fixed-size partial records (top_n per rank, padded)
-        nonlocal gather_buf
-        rec = np.zeros(args.top_n, dtype=mb.PARTIAL_DTYPE)
-        rec["flags"] = 1
-        rec[:len(parts)] = parts
-        t = torch.from_numpy(rec.view(np.uint8)).cuda(non_blocking=True)
-        if gather_buf is None:
-            gather_buf = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(gather_buf, t)
-        allp = gather_buf.cpu().numpy().view(mb.PARTIAL_DTYPE)
-        return mb.merge_partials(allp, args.max_lag, args.top_n, args.threshold, 0)
+        # one small all-gather of fixed-size partial records (top_n per rank), merged on every rank
+        return mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0, fixed_capacity=args.top_n)
 
     def barrier():
         if world > 1:
@@ -267,13 +256,7 @@ def main():
                 r = b2.run([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)   # Run; results land on the host
             else:
                 parts = b2.run_partial([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)
-                rec = np.zeros(args.top_n, dtype=mb.PARTIAL_DTYPE)
-                rec["flags"] = 1
-                rec[:len(parts)] = parts
-                tt = torch.from_numpy(rec.view(np.uint8)).cuda()
-                gb = torch.empty(world * tt.numel(), dtype=torch.uint8, device="cuda")
-                dist.all_gather_into_tensor(gb, tt)
-                r = mb.merge_partials(gb.cpu().numpy().view(mb.PARTIAL_DTYPE), args.max_lag, args.top_n, args.threshold, 0)
+                r = mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0, fixed_capacity=args.top_n)
             b2.close()
             return r
 

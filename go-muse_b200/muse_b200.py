@@ -611,3 +611,40 @@ class Batch:
 
 def NewBatch(ref: Series, comp: Group, results: Results, cc: int) -> Batch:
     return Batch(ref, comp, results, cc)
+
+
+# ----------------------------------------------------------------------------------
+# multi-GPU: one process per GPU, shards merged with one small all-gather
+# ----------------------------------------------------------------------------------
+def allgather_merge(parts: np.ndarray, max_lag: int, top_n: int, threshold: float, sign_filter: int = 0,
+                    fixed_capacity: Optional[int] = None):
+    """All-gather this rank's muse_partial records over torch.distributed (NCCL on GPUs, gloo on
+    CPU) and merge them (muse_merge_partials) -- every rank returns the same global result.
+
+    fixed_capacity: when every rank emits at most that many records (ungrouped runs: top_n) the
+    size exchange is skipped and ONE all-gather is issued; otherwise the counts are gathered first.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    parts = np.ascontiguousarray(parts, dtype=PARTIAL_DTYPE)
+    if fixed_capacity is None:
+        n_local = torch.tensor([parts.size], dtype=torch.int64, device=dev)
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, n_local)
+        counts = counts.cpu().numpy()
+        cap = int(counts.max())
+    else:
+        cap = int(fixed_capacity)
+        counts = None
+    rec = np.zeros(max(cap, 1), dtype=PARTIAL_DTYPE)
+    rec["flags"] = 1                                   # padding records are ignored by the merge
+    rec[:parts.size] = parts
+    t = torch.from_numpy(rec.view(np.uint8)).to(dev)
+    out = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, t)
+    allp = out.cpu().numpy().view(PARTIAL_DTYPE)
+    return merge_partials(allp, max_lag, top_n, threshold, sign_filter)
