@@ -91,6 +91,8 @@ struct muse_batch {
     int screen_ok;
     cf *twp_f, *twn_f;
     float *A_f;
+    float4 *sw_f;          // warp screening kernel: (twn, A[k], A[M-k]) per k < M/2
+    float a_mid;
     float *d_U;
     int32_t *d_list;
     unsigned char *d_done;
@@ -475,6 +477,14 @@ static int rc_screen_tables(muse_batch *b) {
         if ((double)f < a) f = nextafterf(f, INFINITY);   // round up: the bound must not shrink
         A[(size_t)k] = f;
     }
+    if (b->log2m == 10) {   // warp kernel: split twiddle and the two mirror weights in one 16-byte entry
+        std::vector<float4> sw((size_t)M / 2);
+        for (int64_t k = 0; k < M / 2; k++) sw[(size_t)k] = make_float4(twn[(size_t)k].x, twn[(size_t)k].y, A[(size_t)k], A[(size_t)(M - k)]);
+        CU(cudaMalloc(&b->sw_f, sizeof(float4) * sw.size()));
+        CU(cudaMemcpyAsync(b->sw_f, sw.data(), sizeof(float4) * sw.size(), cudaMemcpyHostToDevice, st));
+        b->a_mid = A[(size_t)M / 2];
+        CU(cudaStreamSynchronize(st));
+    }
     CU(cudaMalloc(&b->twp_f, sizeof(cf) * twp.size()));
     CU(cudaMalloc(&b->twn_f, sizeof(cf) * twn.size()));
     CU(cudaMalloc(&b->A_f, sizeof(float) * A.size()));
@@ -573,7 +583,7 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
     cudaFree(b->d_gmax); cudaFree(b->d_hkeys); cudaFree(b->d_gidx);
     cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
     cudaFree(b->d_flag); cudaFree(b->d_counters); cudaFree(b->d_sel);
-    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f);
+    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f); cudaFree(b->sw_f);
     if (b->h_pin) cudaFreeHost(b->h_pin);
     for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
@@ -852,32 +862,55 @@ static cudaError_t launch_screen_t(const ScreenParams &p, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int FLAGS>
-static cudaError_t launch_screen_warp_f(const ScreenParams &p, cudaStream_t st) {
-    using C = ScreenWarpCfg<10>;
-    auto kern = score_screen_warp_kernel<10, 4, FLAGS>;
+template <int NZ>
+static cudaError_t launch_screen_warp_nz(const ScreenParams &p, int sm_count, cudaStream_t st) {
+    using C = ScreenWarpCfg;
+    auto kern = score_screen_warp_kernel<NZ>;
+    const int warps = C::warps(p.N);
     const size_t wb = C::warp_bytes(p.N);
-    const size_t smem = wb * C::WARPS;
+    const size_t smem = wb * (size_t)warps;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int64_t blocks = (p.count + C::WARPS - 1) / C::WARPS;
-    kern<<<(unsigned)blocks, C::TB, smem, st>>>(p, (unsigned)wb);
+    int64_t blocks = (p.count + warps - 1) / warps;      // persistent: one block per SM
+    if (blocks > sm_count) blocks = sm_count;
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(p, (unsigned)wb, (unsigned)C::row_bytes(p.N));
     return cudaGetLastError();
 }
 
-static cudaError_t launch_screen_warp(const ScreenParams &p, cudaStream_t st) {
-    static const int flags = getenv("MUSE_SCREEN_FLAGS") ? atoi(getenv("MUSE_SCREEN_FLAGS")) : 0;
-    (void)flags;
-    return launch_screen_warp_f<0>(p, st);
+// n = 2048: one instantiation per number of non-zero rows of 32 complex slots (N = 1026 .. 2048)
+static cudaError_t launch_screen_warp(const ScreenParams &p, int sm_count, cudaStream_t st) {
+    switch (ScreenWarpCfg::nz(p.N)) {
+#define MUSE_NZ_CASE(z) case z: return launch_screen_warp_nz<z>(p, sm_count, st);
+        MUSE_NZ_CASE(17) MUSE_NZ_CASE(18) MUSE_NZ_CASE(19) MUSE_NZ_CASE(20) MUSE_NZ_CASE(21) MUSE_NZ_CASE(22)
+        MUSE_NZ_CASE(23) MUSE_NZ_CASE(24) MUSE_NZ_CASE(25) MUSE_NZ_CASE(26) MUSE_NZ_CASE(27) MUSE_NZ_CASE(28)
+        MUSE_NZ_CASE(29) MUSE_NZ_CASE(30) MUSE_NZ_CASE(31) MUSE_NZ_CASE(32)
+#undef MUSE_NZ_CASE
+    }
+    return cudaErrorInvalidValue;
 }
 
-static cudaError_t launch_screen(int log2m, const ScreenParams &p, cudaStream_t st) {
-    static const int variant = getenv("MUSE_SCREEN_VARIANT") ? atoi(getenv("MUSE_SCREEN_VARIANT")) : 1;
-    switch (log2m) {
-        case 10: return variant == 0 ? launch_screen_t<10>(p, st) : launch_screen_warp(p, st);
+static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cudaStream_t st) {
+    switch (b->log2m) {
+        case 10: return launch_screen_warp(p, b->ctx->sm_count, st);
         case 8: return launch_screen_t<8>(p, st);
     }
     return cudaErrorInvalidValue;
+}
+
+static ScreenParams screen_params(muse_batch *b) {
+    ScreenParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.slab = b->g->slab;
+    sp.ld = b->g->ld;
+    sp.count = b->g->size;
+    sp.N = (int)b->N;
+    sp.twp = b->twp_f;
+    sp.twn = b->twn_f;
+    sp.A = b->A_f;
+    sp.sw = b->sw_f;
+    sp.a_mid = b->a_mid;
+    sp.out_U = b->d_U;
+    return sp;
 }
 
 // idx list of every series with lo <= U (and not yet exact-scored); marks them done
@@ -935,17 +968,8 @@ static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
     const int64_t S = g->size;
     cudaStream_t st = b->ctx->stream;
     *fell_back = false;
-    ScreenParams sp;
-    memset(&sp, 0, sizeof(sp));
-    sp.slab = g->slab;
-    sp.ld = g->ld;
-    sp.count = S;
-    sp.N = (int)b->N;
-    sp.twp = b->twp_f;
-    sp.twn = b->twn_f;
-    sp.A = b->A_f;
-    sp.out_U = b->d_U;
-    CU(launch_screen(b->log2m, sp, st));
+    ScreenParams sp = screen_params(b);
+    CU(launch_screen(b, sp, st));
     b->timing.n_launches++;
     CU(cudaEventRecord(b->ev[1], st));
     // scores default to NaN (= "cannot be in the result"), nothing exact-scored yet
@@ -1034,6 +1058,24 @@ static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
             if (rc) return rc;
         }
     }
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_screen_bounds(muse_batch *b, float *bounds) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!bounds) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_screen_bounds: NULL output");
+    if (!b->screen_ok) return fail(MUSE_ERR_UNSUPPORTED, "no screening kernel for series length %lld", (long long)b->N);
+    CU(cudaSetDevice(b->ctx->device));
+    rc = ensure_scratch(b);
+    if (rc) return rc;
+    const int64_t S = b->g->size;
+    if (S == 0) return MUSE_OK;
+    cudaStream_t st = b->ctx->stream;
+    ScreenParams sp = screen_params(b);
+    CU(launch_screen(b, sp, st));
+    CU(cudaMemcpyAsync(bounds, b->d_U, sizeof(float) * (size_t)S, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return MUSE_OK;
 }
 

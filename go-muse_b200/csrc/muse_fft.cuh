@@ -33,6 +33,84 @@ template <typename F> MUSE_HD cx<F> cconj(cx<F> a) { return cx<F>{a.x, -a.y}; }
 template <typename F> MUSE_HD cx<F> cmul_negi(cx<F> a) { return cx<F>{a.y, -a.x}; }   // a * (-i)
 template <typename F> MUSE_HD cx<F> cmul_i(cx<F> a) { return cx<F>{-a.y, a.x}; }      // a * (+i)
 
+// ---- fp32 complex arithmetic on packed pairs ------------------------------------------
+// sm_100 has two-wide fp32 instructions (PTX add/sub/mul/fma .f32x2 -> SASS FADD2/FMUL2/
+// FFMA2) whose operands take a free half swap (.LO_HI), per-half negation (.NP) and scalar
+// broadcast (.F32): a complex add is ONE instruction, a complex multiply TWO, and
+// conj / *(+-i) fold into the operand modifiers of the consumer.  The (re, im) pair of a
+// cx<float> is the packed operand; ptxas keeps it in an aligned register pair.  Each half is
+// an IEEE round-to-nearest fp32 operation, so the error analysis of the scalar code holds.
+// Host builds (tests/cpp) use the scalar forms.
+#if defined(__CUDA_ARCH__)
+namespace f32x2 {
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float x, float y) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ cx<float> up(u64 r) {
+    cx<float> v;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+    return v;
+}
+__device__ __forceinline__ cx<float> add(cx<float> a, cx<float> b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)));
+    return up(d);
+}
+__device__ __forceinline__ cx<float> mul(cx<float> a, cx<float> b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)));
+    return up(d);
+}
+__device__ __forceinline__ cx<float> fma(cx<float> a, cx<float> b, cx<float> c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a.x, a.y)), "l"(pk(b.x, b.y)), "l"(pk(c.x, c.y)));
+    return up(d);
+}
+}  // namespace f32x2
+#endif
+
+MUSE_HD cx<float> cadd(cx<float> a, cx<float> b) {
+#if defined(__CUDA_ARCH__)
+    return f32x2::add(a, b);
+#else
+    return cx<float>{a.x + b.x, a.y + b.y};
+#endif
+}
+MUSE_HD cx<float> csub(cx<float> a, cx<float> b) {
+#if defined(__CUDA_ARCH__)
+    return f32x2::add(a, cx<float>{-b.x, -b.y});
+#else
+    return cx<float>{a.x - b.x, a.y - b.y};
+#endif
+}
+// a*b = a * (b.x, b.x) + (-a.y, a.x) * (b.y, b.y): FMUL2 + FFMA2, b's halves broadcast
+MUSE_HD cx<float> cmul(cx<float> a, cx<float> b) {
+#if defined(__CUDA_ARCH__)
+    const cx<float> t = f32x2::mul(a, cx<float>{b.x, b.x});
+    return f32x2::fma(cx<float>{-a.y, a.x}, cx<float>{b.y, b.y}, t);
+#else
+    return cx<float>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+#endif
+}
+// component-wise a*b and a*b + c on the two halves (not complex products)
+MUSE_HD cx<float> pmul(cx<float> a, cx<float> b) {
+#if defined(__CUDA_ARCH__)
+    return f32x2::mul(a, b);
+#else
+    return cx<float>{a.x * b.x, a.y * b.y};
+#endif
+}
+MUSE_HD cx<float> pfma(cx<float> a, cx<float> b, cx<float> c) {
+#if defined(__CUDA_ARCH__)
+    return f32x2::fma(a, b, c);
+#else
+    return cx<float>{a.x * b.x + c.x, a.y * b.y + c.y};
+#endif
+}
+
 // cos(2*pi*k/32), k = 0..8, correctly rounded
 MUSE_HD constexpr double cos32_q(int k) {
     return k == 0 ? 1.0
@@ -60,7 +138,7 @@ MUSE_HD void twiddle_const(cx<F> &v) {
     if (k32 == 16) { v = cx<F>{-v.x, -v.y}; return; }
     if (k32 == 24) { v = cmul_i(v); return; }
     constexpr F c = (F)cos32(k32), s = (F)(-sin32(k32));
-    v = cx<F>{v.x * c - v.y * s, v.x * s + v.y * c};
+    v = cmul(v, cx<F>{c, s});
 }
 
 // ---- in-register forward DFTs (exp(-i)); results land at v[base + Perm<N>(k)] ----
@@ -80,6 +158,27 @@ template <typename F> MUSE_HD void dft4(cx<F> &a, cx<F> &b, cx<F> &c, cx<F> &d) 
     c = csub(t0, t2);
     b = cadd(t1, t3);
     d = csub(t1, t3);
+}
+
+// dft4 whose last 4 - NNZ inputs are known to be zero (pruned first stage of a zero-padded
+// transform): 6 complex additions for NNZ == 3, 4 for NNZ == 2
+template <int NNZ, typename F> MUSE_HD void dft4_lead(cx<F> &a, cx<F> &b, cx<F> &c, cx<F> &d) {
+    static_assert(NNZ >= 2 && NNZ <= 4, "dft4_lead: 2..4 leading non-zero inputs");
+    if constexpr (NNZ == 4) {
+        dft4(a, b, c, d);
+    } else if constexpr (NNZ == 3) {
+        const cx<F> t0 = cadd(a, c), t1 = csub(a, c), t3 = cmul_negi(b), bb = b;
+        a = cadd(t0, bb);
+        c = csub(t0, bb);
+        b = cadd(t1, t3);
+        d = csub(t1, t3);
+    } else {
+        const cx<F> aa = a, bb = b, t3 = cmul_negi(b);
+        a = cadd(aa, bb);
+        c = csub(aa, bb);
+        b = cadd(aa, t3);
+        d = csub(aa, t3);
+    }
 }
 
 template <int N, typename F> struct Dft;
@@ -112,6 +211,24 @@ struct DftComposite {
 template <typename F> struct Dft<8, F> { MUSE_HD static void run(cx<F> *v) { DftComposite<8, 2, 4, F>::run(v); } };
 template <typename F> struct Dft<16, F> { MUSE_HD static void run(cx<F> *v) { DftComposite<16, 4, 4, F>::run(v); } };
 template <typename F> struct Dft<32, F> { MUSE_HD static void run(cx<F> *v) { DftComposite<32, 4, 8, F>::run(v); } };
+
+// 32-point DFT whose inputs v[NZ..31] are zero (NZ >= 16): the radix-4 first stage is pruned.
+template <int NZ, typename F>
+struct Dft32Lead {
+    static_assert(NZ >= 16 && NZ <= 32, "Dft32Lead: 16..32 leading non-zero inputs");
+    using D = DftComposite<32, 4, 8, F>;
+    template <int n2> MUSE_HD static void inner(cx<F> *v) {
+        constexpr int left = NZ - n2;                        // k1 with n2 + 8*k1 < NZ
+        constexpr int cnt = left >= 25 ? 4 : left >= 17 ? 3 : 2;
+        dft4_lead<cnt>(v[n2], v[n2 + 8], v[n2 + 16], v[n2 + 24]);
+        if constexpr (n2 > 0) D::template tw<n2, 1>(v);
+        if constexpr (n2 + 1 < 8) inner<n2 + 1>(v);
+    }
+    MUSE_HD static void run(cx<F> *v) {
+        inner<0>(v);
+        D::template outer<0>(v);
+    }
+};
 
 // ---- Stockham pass geometry ------------------------------------------------------
 // An M = 2^LOG2M point complex FFT done by T = M/P cooperating threads, P = 2^LOG2P

@@ -31,6 +31,10 @@ namespace muse {
 typedef cx<float> cf;
 
 #define MUSE_SCREEN_SLACK 2e-4f
+// warp kernel: sample variance window.  std >= 1e-10: a flushed magnitude (< 1.1e-19) is below
+// 1.1e-9 in units of the score per bin; std <= 1e14: |2Y_k|^2 <= (4*N*std)^2 * N < 3e38.
+#define MUSE_SCREEN_VAR_MIN 1e-20f
+#define MUSE_SCREEN_VAR_MAX 1e28f
 
 struct ScreenParams {
     const double *slab;
@@ -40,6 +44,8 @@ struct ScreenParams {
     const cf *twp;        // per-pass twiddles (fill_pass_twiddles for (LOG2M, LOG2M/2)), fp32
     const cf *twn;        // exp(-2*pi*i*k/n), k < M, fp32
     const float *A;       // |X_k|/(2n) * (k == 0 || k == M ? 1 : 2), rounded up, M+1 entries
+    const float4 *sw;     // warp kernel: (twn[k].x, twn[k].y, A[k], A[M-k]) for k < M/2
+    float a_mid;          // warp kernel: A[M/2]
     float *out_U;         // [count] upper bound on the score (already clamped to <= 1 + slack)
 };
 
@@ -208,10 +214,12 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     } while (!done);
 }
 
-// sqrt.approx.f32 (one MUFU): 2 ulp, covered by the 1e-5 relative slack of the bound
+// sqrt.approx.ftz.f32 (one MUFU): 2 ulp, covered by the 1e-5 relative slack of the bound.  A
+// subnormal |2Y_k|^2 is flushed to 0; the variance window MUSE_SCREEN_VAR_MIN/MAX keeps every
+// bin that matters at the 1e-9 level far away from both ends of the fp32 range.
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -225,133 +233,160 @@ __device__ __forceinline__ void mbar_test(unsigned bar, unsigned parity) {
         : "memory");
 }
 
-template <int LOG2M>
 struct ScreenWarpCfg {
-    static_assert(LOG2M == 10, "one warp per series needs M = 32*32");
-    using G = Geo<LOG2M, 5>;
-    static constexpr int WARPS = 4;
-    static constexpr int TB = 32 * WARPS;
-    // per-warp bytes: the row (N doubles) + the (mean, mean) slot, or the padded exchange buffer
-    static size_t warp_bytes(int N) {
-        size_t row = ((size_t)N * 8 + 16 + 127) / 128 * 128;
-        size_t ex = ((size_t)(G::MP + 1) * sizeof(cf) + 127) / 128 * 128;
-        return row > ex ? row : ex;
+    using G = Geo<10, 5>;                       // M = 1024 = 32 x 32: one warp per series
+    static constexpr int MAX_WARPS = 12;   // 3 warps per scheduler: up to 168 registers per thread
+    static constexpr size_t SMEM_BUDGET = 226 * 1024;
+    static constexpr size_t EX_BYTES = ((size_t)(G::MP + 1) * sizeof(cf) + 127) / 128 * 128;   // padded FFT exchange buffer
+    static size_t row_bytes(int N) { return ((size_t)N * 8 + 127) / 128 * 128; }
+    static size_t warp_bytes(int N) { return row_bytes(N) + EX_BYTES; }
+    static int warps(int N) {
+        const size_t w = SMEM_BUDGET / warp_bytes(N);
+        return (int)(w > MAX_WARPS ? MAX_WARPS : w);
     }
+    // complex slots t + 32*r, r < nz, hold samples; the rest of the padded series is zero
+    static int nz(int N) { return (N / 2 + 31) / 32; }
 };
 
-template <int LOG2M, int MINB, int FLAGS = 0>
-__global__ void __launch_bounds__(ScreenWarpCfg<LOG2M>::TB, MINB)
-score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes) {
-    using C = ScreenWarpCfg<LOG2M>;
+// Persistent kernel, one block per SM, every warp an independent pipeline over its own series
+// (pos = first, first + stride, ...): its row buffer is refilled by the next cp.async.bulk as
+// soon as the 23 x 16 bytes per lane are in registers, so the DRAM latency of row i+1 hides
+// behind the FFT of row i and ~10 rows per SM are in flight at any time.  The FFT exchange
+// goes through a separate per-warp buffer.
+//
+// NZ = ceil(N/64) (17..32 for n = 2048) is a template parameter so that the loads, the
+// conversions and the first radix-4 stage of the zero rows disappear at compile time.  The
+// |Y_f| bound is invariant under rotation of the padded series, so the zeros trail.
+//
+// Split: lane t holds Z[t + 32j] in slot j.  Bins k and M-k share e = Z[k] + conj(Z[M-k]) and
+// w*o, 2Y[k] = e + w*o, 2conj(Y[M-k]) = e - w*o, so each lane walks only j < 16 (k < 512) and
+// gets both magnitudes from one mirror exchange: Z[M-k] sits in lane (32-t)%32, slot 31-j
+// (lane 0: its own slot (32-j)%32; k = 0 pairs with itself and yields the DC and Nyquist
+// terms).  Only k = 512 (lane 0, slot 16, its own mirror) is left over: |2Y[512]| = 2|Z[512]|.
+template <int NZ>
+__global__ void __launch_bounds__(ScreenWarpCfg::MAX_WARPS * 32, 1)
+score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, const unsigned row_bytes) {
+    using C = ScreenWarpCfg;
     using G = typename C::G;
-    constexpr int LOG2P = 5, P = 32, M = G::M;
+    constexpr int P = 32, M = G::M;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[C::WARPS];
+    __shared__ __align__(8) unsigned long long bars[C::MAX_WARPS];
 
     const int w = threadIdx.x >> 5;
     const int t = threadIdx.x & 31;
-    const int64_t pos = (int64_t)blockIdx.x * C::WARPS + w;
-    const bool valid = pos < prm.count;
-    const int64_t row = valid ? pos : prm.count - 1;
-    const double *rowp = prm.slab + row * prm.ld;
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t pos = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
     unsigned char *buf = smem_raw + (size_t)w * warp_bytes;
+    const cd *rowc = reinterpret_cast<const cd *>(buf);
+    cf *sm = reinterpret_cast<cf *>(buf + row_bytes);
     const int N = prm.N;
     const int Nh = N >> 1;
     const unsigned bar = smem_u32(&bars[w]);
+    const int partner = (P - t) & (P - 1);
+    const bool lane0 = (t == 0);
+    const bool last_in = t + (NZ - 1) * 32 < Nh;      // is this lane's slot of the last row a sample?
 
     if (t == 0) {
         mbar_init(bar, 1);
-        bulk_load(smem_u32(buf), rowp, (unsigned)N * 8u, bar);
+        if (pos < prm.count) bulk_load(smem_u32(buf), prm.slab + pos * prm.ld, (unsigned)N * 8u, bar);
     }
     __syncwarp();
-    mbar_wait(bar, 0);      // every lane waits itself (one polling lane + __syncwarp measured 3x slower)
 
-    // ---- mean in fp64 (xcorr.go:85-86) ----
-    const cd *rowc = reinterpret_cast<const cd *>(buf);
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-    for (int j = t; j < Nh; j += 32) {
-        const cd d = rowc[j];
-        s0 += d.x;
-        s1 += d.y;
-    }
-    double sum = s0 + s1;
+    for (unsigned phase = 0; pos < prm.count; phase ^= 1u) {
+        mbar_wait(bar, phase);      // every lane waits itself (one polling lane + __syncwarp measured 3x slower)
+
+        // ---- row -> registers, then hand the buffer back to the copy engine ----
+        cd d[NZ];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    const double mu = sum / (double)N;
-    if (t == 0) reinterpret_cast<cd *>(buf)[Nh] = cd{mu, mu};
-    __syncwarp();
+        for (int r = 0; r < NZ; r++) d[r] = (r < NZ - 1 || last_in) ? rowc[t + r * 32] : cd{0.0, 0.0};
+        __syncwarp();
+        const int64_t next = pos + stride;
+        if (t == 0 && next < prm.count) bulk_load(smem_u32(buf), prm.slab + next * prm.ld, (unsigned)N * 8u, bar);
 
-    // ---- centred samples to fp32 registers; out-of-range indices hit the (mean, mean) slot ----
-    cf v[P];
-    float ss = 0.f;
+        // ---- mean in fp64 (xcorr.go:85-86), centred samples in fp32 ----
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int r = 0; r < P; r++) {
-        const int j = min(t + r * 32, Nh);
-        const cd d = rowc[j];
-        v[r].x = (float)(d.x - mu);
-        v[r].y = (float)(d.y - mu);
-        ss = fmaf(v[r].x, v[r].x, ss);
-        ss = fmaf(v[r].y, v[r].y, ss);
-    }
-    ss = group_sum_f<32>(ss);
-    __syncwarp();                                   // everyone is done reading the row: reuse it
-
-    cf *sm = reinterpret_cast<cf *>(buf);
-    fft_pass_compute_store<LOG2M, LOG2P, 0, float, cf>(v, sm, t, prm.twp);
-    __syncwarp();
-    fft_pass_load<LOG2M, LOG2P, 1, float>(v, sm, t);
-    Dft<P, float>::run(v);
-
-    // |Y_k| for k = t + 32*j.  Branch-free: lane 0 (whose mirror is its own slot (32-j)%32) is
-    // handled with selects and the Nyquist term is added after the loop, so the shuffles need
-    // no divergence handling.
-    const int partner = (P - t) & (P - 1);
-    const bool lane0 = (t == 0);
-    float acc = 0.f;
-    cf e0{0.f, 0.f}, wo0{0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < P; j++) {
-        const cf zk = v[Perm<P>::at(j)];
-        const cf zp = v[Perm<P>::at(P - 1 - j)];
-        const cf zs = v[Perm<P>::at((P - j) & (P - 1))];
-        cf zm;
-        zm.x = __shfl_sync(0xffffffffu, zp.x, partner);
-        zm.y = __shfl_sync(0xffffffffu, zp.y, partner);
-        zm.x = lane0 ? zs.x : zm.x;
-        zm.y = lane0 ? zs.y : zm.y;
-        const cf wk = prm.twn[t + P * j];
-        const cf zmc = cconj(zm);
-        const cf e = cadd(zk, zmc);
-        const cf o = cmul_negi(csub(zk, zmc));
-        const cf wo = cmul(wk, o);
-        const cf y = cadd(e, wo);                        // 2*Y_k
-        acc = fmaf(sqrt_approx(fmaf(y.x, y.x, y.y * y.y)), prm.A[t + P * j], acc);
-        if (j == 0) {
-            e0 = e;
-            wo0 = wo;
+        for (int r = 0; r < NZ; r++) {
+            s0 += d[r].x;
+            s1 += d[r].y;
         }
-    }
-    {   // Nyquist term 2*Y_M = e - w*o at k = 0 (lane 0 only; weight 0 elsewhere)
-        const cf yn = csub(e0, wo0);
-        acc = fmaf(sqrt_approx(fmaf(yn.x, yn.x, yn.y * yn.y)), lane0 ? prm.A[M] : 0.f, acc);
-    }
-    acc = group_sum_f<32>(acc);
-
-    if (t == 0 && valid) {
-        const float var = ss / (float)(N - 1);
-        float U;
-        if (ss == 0.f) {
-            // every (y - mean) rounded to 0 in fp32: constant series (exact score 0) or a variance
-            // below fp32 range; the exact kernel decides
-            U = 2.f;
-        } else if (!(var > 0.f) || !(var < 3.0e38f) || !(acc == acc)) {
-            U = 2.f;
-        } else {
-            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
-            if (!(U == U)) U = 2.f;
+        double sum = s0 + s1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const double mu = sum / (double)N;
+        cf v[P];
+        cf ss2{0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < P; r++) {
+            if (r < NZ) {
+                v[r] = cf{(float)(d[r].x - mu), (float)(d[r].y - mu)};
+                if (r == NZ - 1 && !last_in) v[r] = cf{0.f, 0.f};
+                ss2 = pfma(v[r], v[r], ss2);
+            } else {
+                v[r] = cf{0.f, 0.f};
+            }
         }
-        prm.out_U[pos] = U;
+        const float ss = group_sum_f<32>(ss2.x + ss2.y);
+
+        // ---- forward FFT_1024: pruned radix-32, twiddle, exchange through smem, radix-32 ----
+        Dft32Lead<NZ, float>::run(v);
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            cf val = v[Perm<P>::at(j)];
+            if (j > 0) val = cmul(val, prm.twp[(j - 1) * 32 + t]);          // W_1024^(j*t)
+            sm[G::pad(32 * t + j)] = val;
+        }
+        __syncwarp();
+        fft_pass_load<10, 5, 1, float>(v, sm, t);
+        __syncwarp();                                   // the exchange buffer is free for the next series
+        Dft<P, float>::run(v);                          // v[Perm(j)] = Z[t + 32*j]
+
+        // ---- |2Y_k| and |2Y_(M-k)| for k = t + 32*j, j < 16 ----
+        cf acc2{0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < P / 2; j++) {
+            const cf zk = v[Perm<P>::at(j)];
+            const cf zp = v[Perm<P>::at(P - 1 - j)];
+            const cf zs = v[Perm<P>::at((P - j) & (P - 1))];
+            cf src, zm;
+            src.x = lane0 ? zs.x : zp.x;
+            src.y = lane0 ? zs.y : zp.y;
+            zm.x = __shfl_sync(0xffffffffu, src.x, partner);
+            zm.y = __shfl_sync(0xffffffffu, src.y, partner);
+            const float4 s = prm.sw[t + 32 * j];            // (w_k.x, w_k.y, A[k], A[M-k])
+            const cf zmc = cconj(zm);
+            const cf e = cadd(zk, zmc);
+            const cf o = cmul_negi(csub(zk, zmc));
+            const cf wo = cmul(o, cf{s.x, s.y});
+            const cf y1 = cadd(e, wo);                      // 2*Y_k
+            const cf y2 = csub(e, wo);                      // 2*conj(Y_(M-k))
+            const cf q1 = pmul(y1, y1), q2 = pmul(y2, y2);
+            const cf mag{sqrt_approx(q1.x + q1.y), sqrt_approx(q2.x + q2.y)};
+            acc2 = pfma(mag, cf{s.z, s.w}, acc2);
+        }
+        float acc = acc2.x + acc2.y;
+        {   // k = 512: lane 0, slot 16 (weight 0 on the other lanes)
+            const cf z = v[Perm<P>::at(P / 2)];
+            const cf q = pmul(z, z);
+            acc = fmaf(sqrt_approx(q.x + q.y), lane0 ? 2.f * prm.a_mid : 0.f, acc);
+        }
+        acc = group_sum_f<32>(acc);
+
+        if (t == 0) {
+            const float var = ss / (float)(N - 1);
+            float U;
+            if (!(var >= MUSE_SCREEN_VAR_MIN) || !(var <= MUSE_SCREEN_VAR_MAX) || !(acc == acc)) {
+                // constant series (every y - mean rounds to 0; exact score 0), or a variance outside
+                // the window in which fp32 squares neither flush nor overflow, or NaN/Inf samples:
+                // the exact kernel decides
+                U = 2.f;
+            } else {
+                U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
+                if (!(U == U)) U = 2.f;
+            }
+            prm.out_U[pos] = U;
+        }
+        pos = next;
     }
 }
 

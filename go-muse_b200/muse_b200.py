@@ -118,6 +118,7 @@ ABI = {
                                     C.c_int32, C.c_int32, _dp, _ip64, _ip64, _ip64]),
     "muse_batch_score_all": (C.c_int, [_vp, C.c_int32, _dp, _ip32]),
     "muse_batch_xcorr": (C.c_int, [_vp, C.c_int64, _dp, _ip32]),
+    "muse_batch_screen_bounds": (C.c_int, [_vp, _vp]),
     "muse_batch_run_partial": (C.c_int, [_vp, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                          C.c_int32, _vp, C.c_int64, _ip64]),
     "muse_batch_partial_capacity": (C.c_int64, [_vp, _ip32, C.c_int32, C.c_int64]),
@@ -301,6 +302,13 @@ class DeviceBatch:
         lg = np.zeros(max(S, 1), dtype=np.int32)
         _check(lib().muse_batch_score_all(self.h, int(signed_scores), _d(sc), lg.ctypes.data_as(_ip32)))
         return sc[:S], lg[:S].astype(np.int64)
+
+    def screen_bounds(self) -> np.ndarray:
+        """fp32 upper bound on every series' score (diagnostic; > 1 means undecided)."""
+        S = self.store.size()
+        u = np.zeros(max(S, 1), dtype=np.float32)
+        _check(lib().muse_batch_screen_bounds(self.h, u.ctypes.data_as(_vp)))
+        return u[:S]
 
     def xcorr(self, local_index: int):
         cc = np.zeros(self.fft_len())

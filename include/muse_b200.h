@@ -171,6 +171,11 @@ int  muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t n_key_col
  * muse_batch.go:68-77).  Host outputs of muse_group_size() entries. */
 int  muse_batch_score_all(muse_batch *b, int32_t signed_scores, double *scores, int32_t *lags);
 
+/* Diagnostic: the fp32 screening pass alone.  bounds[i] >= series i's score from
+ * muse_batch_score_all (a value > 1, e.g. 2.0, means "undecided: ask the fp64 kernel").
+ * MUSE_ERR_UNSUPPORTED when the series length has no screening kernel. */
+int  muse_batch_screen_bounds(muse_batch *b, float *bounds);
+
 /* The full cross-correlation vector cc[n] of one series (xcorr.go:160-197's first
  * return value; KAT support).  *std_zero is set when xcorr.go:165-168 applies. */
 int  muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, int32_t *std_zero);

@@ -78,6 +78,32 @@ def test_screened_run_equals_exact_run(ctx, N):
     assert set(ix[~same]) == set(wix[~same])
 
 
+@pytest.mark.parametrize("N", [1440, 1026, 1030, 1088, 1090, 1500, 1984, 2046, 2048, 480, 300])
+def test_bound_dominates_exact_score(ctx, N):
+    """U >= exact fp64 score for every series, on the adversarial inputs and on siggen-style rows;
+    the margin U - score is reported (it must never be negative)."""
+    rng = np.random.default_rng(7 * N)
+    S = 6000
+    Y = _adversarial(rng, S, N)
+    ref = np.zeros(N)
+    ref[N // 2 - 5:N // 2 + 5] = 1.5
+    ref += 0.1 * (rng.random(N) - 0.5)
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    b = mb.DeviceBatch(ctx, store, ref)
+    u = b.screen_bounds().astype(np.float64)
+    sc, _ = b.score_all()
+    assert np.all(np.isfinite(u))
+    margin = u - sc
+    # at least half of the 2e-4 slack is left (bit-identical constant rows may get U == score == 0)
+    worst = int(margin.argmin())
+    assert margin.min() >= 0 and np.all((margin >= 1e-4) | (sc == 0)), (margin.min(), worst, u[worst], sc[worst])
+    decided = u <= 1.5
+    assert decided.mean() > 0.6                     # the bound is not trivially "undecided"
+    # constant / near-constant rows (k == 7, 8) and the 1e-12 amplitude rows are either undecided or bounded
+    assert np.all(u[7::12] >= sc[7::12])
+
+
 def test_screening_prunes_on_siggen_data(ctx):
     # on the benchmark's own data only a few percent may reach the exact kernel
     N, S, seed = 1440, 200_000, 20261018
