@@ -215,7 +215,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    score_ms, launches, n_rescored = [], 0, 0
+    score_ms, launches, n_rescored, n_refined, tail_ms = [], 0, 0, 0, []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
@@ -225,6 +225,8 @@ def main():
         score_ms.append(tm.score_ms)
         launches += tm.n_launches
         n_rescored += tm.n_rescored
+        n_refined += tm.n_refined
+        tail_ms.append(tm.total_ms - tm.score_ms)
     ev1.record(stream)
     barrier()
     clocks = sampler.finish()
@@ -310,7 +312,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(workload(args), mode_used=used_mode,
-                                                rescored_per_step=n_rescored / max(1, args.steps)),
+                                                rescored_per_step=n_rescored / max(1, args.steps),
+                                                refined_per_step=n_refined / max(1, args.steps),
+                                                tail_ms=sum(tail_ms) / max(1, len(tail_ms))),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "top": {"score": float(out[0][0]) if len(out[0]) else None, "n": int(len(out[0]))},
         }

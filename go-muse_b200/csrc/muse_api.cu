@@ -93,6 +93,11 @@ struct muse_batch {
     float *A_f;
     float4 *sw_f;          // warp screening kernel: (twn, A[k], A[M-k]) per k < M/2
     float a_mid;
+    float4 *sx_f;          // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
+    cf x_mid;
+    unsigned *d_cut;       // fused refinement state: [0] cut bits, [2..3] n_refined (u64), [4..] coarse + fine histogram
+    float *d_L;            // lower bounds (diagnostic entry point only)
+    int64_t d_L_cap;
     float *d_U;
     int32_t *d_list;
     unsigned char *d_done;
@@ -102,6 +107,7 @@ struct muse_batch {
     int32_t *d_gidx;
     cudaEvent_t ev[4];
     muse_timing timing;
+    int fused_run;         // this run went through score_fused (d_counters[2] = exact list length, [3] = refined)
 };
 
 struct DeviceGuard {
@@ -483,6 +489,13 @@ static int rc_screen_tables(muse_batch *b) {
         CU(cudaMalloc(&b->sw_f, sizeof(float4) * sw.size()));
         CU(cudaMemcpyAsync(b->sw_f, sw.data(), sizeof(float4) * sw.size(), cudaMemcpyHostToDevice, st));
         b->a_mid = A[(size_t)M / 2];
+        std::vector<float4> sx((size_t)M / 2);
+        for (int64_t k = 0; k < M / 2; k++)
+            sx[(size_t)k] = make_float4((float)X[(size_t)k].x, (float)X[(size_t)k].y, (float)X[(size_t)(M - k)].x, (float)X[(size_t)(M - k)].y);
+        b->x_mid = cf{(float)X[(size_t)M / 2].x, (float)X[(size_t)M / 2].y};
+        CU(cudaMalloc(&b->sx_f, sizeof(float4) * sx.size()));
+        CU(cudaMemcpyAsync(b->sx_f, sx.data(), sizeof(float4) * sx.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaMalloc(&b->d_cut, sizeof(unsigned) * (4 + MUSE_CUT_COARSE + MUSE_CUT_BINS)));
         CU(cudaStreamSynchronize(st));
     }
     CU(cudaMalloc(&b->twp_f, sizeof(cf) * twp.size()));
@@ -583,7 +596,7 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
     cudaFree(b->d_gmax); cudaFree(b->d_hkeys); cudaFree(b->d_gidx);
     cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
     cudaFree(b->d_flag); cudaFree(b->d_counters); cudaFree(b->d_sel);
-    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f); cudaFree(b->sw_f);
+    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f); cudaFree(b->sw_f); cudaFree(b->sx_f); cudaFree(b->d_cut); cudaFree(b->d_L);
     if (b->h_pin) cudaFreeHost(b->h_pin);
     for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
@@ -755,6 +768,11 @@ static int setup_group_table(muse_batch *b, const RunArgs &a, KeyCols &kc, Group
     return MUSE_OK;
 }
 
+// fused screened runs launch the exact kernel over at most this many listed series without knowing
+// the list length on the host; run_fused_overflow finishes a longer list after the fact
+#define MUSE_EXACT_UB 32768
+static int run_fused_overflow(muse_batch *b, int64_t n_exact);
+
 // Produces the selected records on the host (unsorted).  apply_filter == 0 keeps every
 // representative (grouped multi-GPU partials).
 static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t limit, std::vector<Rec> &recs) {
@@ -793,8 +811,23 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
     CU(cudaMemcpyAsync(h_idx, b->d_cidx, sizeof(int32_t) * CH, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_lag, b->d_clag, sizeof(int32_t) * CH, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    const unsigned long long ncand = h_n[0];
-    b->timing.n_rescored = (int64_t)(h_n[2] + h_n[3]);     // screened runs: pilot + second round
+    unsigned long long ncand = h_n[0];
+    if (b->fused_run) {
+        b->timing.n_rescored = (int64_t)h_n[2];
+        b->timing.n_refined = (int64_t)h_n[3];
+        if ((int64_t)h_n[2] > std::min<int64_t>(S, MUSE_EXACT_UB)) {
+            // rare: more exact candidates than the fixed launch covered -> finish them and select again
+            const int64_t n_exact = (int64_t)h_n[2];
+            int rc = run_fused_overflow(b, n_exact);
+            if (rc) return rc;
+            b->fused_run = 0;
+            rc = run_select(b, a, apply_filter, limit, recs);
+            b->timing.n_rescored = n_exact;
+            return rc;
+        }
+    } else {
+        b->timing.n_rescored = (int64_t)(h_n[2] + h_n[3]);     // screened runs: pilot + second round
+    }
     if (ncand == 0) return MUSE_OK;
     auto better = [](const Rec &x, const Rec &y) { return x.key != y.key ? x.key > y.key : x.idx < y.idx; };
     if (ncand <= CH) {
@@ -910,7 +943,39 @@ static ScreenParams screen_params(muse_batch *b) {
     sp.sw = b->sw_f;
     sp.a_mid = b->a_mid;
     sp.out_U = b->d_U;
+    sp.sx = b->sx_f;
+    sp.x_mid = b->x_mid;
+    sp.cut_bits = b->d_cut;
+    sp.n_refined = reinterpret_cast<unsigned long long *>(b->d_cut + 2);
+    sp.cut_hist = b->d_cut + 4;
+    sp.top_n = 1;
     return sp;
+}
+
+// Arms the fused refinement of the warp kernel: running cut-off = cut0 (+inf: bounds only),
+// counters and histogram cleared, lag window in the kernel's rotated cc index.
+__global__ void init_cut_kernel(unsigned *state, float cut0) {
+    for (int i = threadIdx.x; i < 4 + MUSE_CUT_COARSE + MUSE_CUT_BINS; i += blockDim.x) state[i] = (i == 0) ? __float_as_uint(cut0) : 0u;
+}
+
+static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t max_lag, int64_t top_n, double threshold) {
+    if (b->log2m != 10) return MUSE_OK;
+    init_cut_kernel<<<1, 256, 0, b->ctx->stream>>>(b->d_cut, cut0);
+    CU(cudaGetLastError());
+    const int64_t n = b->n, pad = n - b->N;
+    if (max_lag < 0) max_lag = -1;                          // nothing passes |lag| <= max_lag
+    if (2 * max_lag >= n - 1) {                             // every lag is inside
+        sp.win_lo = 0;
+        sp.win_len = (int)n;
+    } else {
+        sp.win_lo = (int)(((pad - max_lag) % n + n) % n);
+        sp.win_len = (int)(2 * max_lag);                    // -2 when max_lag < 0: no index qualifies
+    }
+    sp.top_n = (int)std::min<int64_t>(std::max<int64_t>(top_n, 1), 0x7fffffff);
+    float thr = (float)threshold;
+    if ((double)thr < threshold) thr = nextafterf(thr, INFINITY);    // round UP: a counted lower bound must really reach the threshold
+    sp.thr = thr > 0.f ? thr : 0.f;
+    return MUSE_OK;
 }
 
 // idx list of every series with lo <= U (and not yet exact-scored); marks them done
@@ -928,6 +993,21 @@ __global__ void survivors_kernel(const float *__restrict__ U, int64_t S, float l
         out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
         done[i] = 1;
     }
+}
+
+// idx list of every series whose (refined) bound reaches the final cut-off, read from device memory
+__global__ void survivors_cut_kernel(const float *__restrict__ U, int64_t S, const unsigned *__restrict__ cut_bits,
+                                     int32_t *__restrict__ out, unsigned long long *n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float lo = __uint_as_float(*cut_bits);
+    const bool take = i < S && U[i] >= lo;
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
 }
 
 // candidates for the pilot: (U bits << 32, idx) of every series with U >= lo
@@ -1061,11 +1141,12 @@ static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
     return MUSE_OK;
 }
 
-extern "C" int muse_batch_screen_bounds(muse_batch *b, float *bounds) {
+extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t max_lag, float *upper, float *lower) {
     int rc = check_batch(b);
     if (rc) return rc;
-    if (!bounds) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_screen_bounds: NULL output");
+    if (!upper || (refine && !lower)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_screen_bounds: NULL output");
     if (!b->screen_ok) return fail(MUSE_ERR_UNSUPPORTED, "no screening kernel for series length %lld", (long long)b->N);
+    if (refine && b->log2m != 10) return fail(MUSE_ERR_UNSUPPORTED, "the fused refinement needs an FFT length of 2048");
     CU(cudaSetDevice(b->ctx->device));
     rc = ensure_scratch(b);
     if (rc) return rc;
@@ -1073,16 +1154,63 @@ extern "C" int muse_batch_screen_bounds(muse_batch *b, float *bounds) {
     if (S == 0) return MUSE_OK;
     cudaStream_t st = b->ctx->stream;
     ScreenParams sp = screen_params(b);
+    if (refine) {
+        if (!b->d_L || b->d_L_cap < S) {
+            cudaFree(b->d_L);
+            b->d_L = nullptr;
+            CU(cudaMalloc(&b->d_L, sizeof(float) * (size_t)S));
+            b->d_L_cap = S;
+        }
+        sp.out_L = b->d_L;
+    }
+    // refine: cut-off 0 that never rises (top_n = INT_MAX): every series takes the second stage
+    rc = arm_refinement(b, sp, refine ? 0.f : INFINITY, max_lag, 0x7fffffff, 0.0);
+    if (rc) return rc;
     CU(launch_screen(b, sp, st));
-    CU(cudaMemcpyAsync(bounds, b->d_U, sizeof(float) * (size_t)S, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(upper, b->d_U, sizeof(float) * (size_t)S, cudaMemcpyDeviceToHost, st));
+    if (refine) CU(cudaMemcpyAsync(lower, b->d_L, sizeof(float) * (size_t)S, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MUSE_OK;
+}
+
+// Screened scoring with the fused kernel (n = 2048, ungrouped): ONE pass over the slab gives
+// every series an upper bound that is either the loose spectral one (below the running cut-off:
+// cannot be in the result) or the tight fp32 one; the exact fp64 kernel then scores only the
+// series whose bound reaches the final cut-off.  No host round trip before the final one: the
+// cut-off and the list length stay on the device, the exact kernel is launched over
+// MUSE_EXACT_UB series and skips what the list does not hold.
+static int score_fused(muse_batch *b, const RunArgs &a) {
+    const int64_t S = b->g->size;
+    cudaStream_t st = b->ctx->stream;
+    ScreenParams sp = screen_params(b);
+    const float thr_lo = a.threshold > 0 ? (float)a.threshold * 0.999999f : 0.f;   // never above the fp64 threshold
+    int rc = arm_refinement(b, sp, thr_lo, a.max_lag, a.top_n, a.threshold);
+    if (rc) return rc;
+    CU(launch_screen(b, sp, st));
+    b->timing.n_launches += 2;
+    CU(cudaEventRecord(b->ev[1], st));
+    CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "cannot be in the result"
+    const unsigned blocks = (unsigned)((S + 255) / 256);
+    survivors_cut_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, b->d_cut, b->d_list, b->d_counters + 2);
+    b->timing.n_launches++;
+    rc = score_exact_all(b, 0, b->d_list, std::min<int64_t>(S, MUSE_EXACT_UB), b->d_counters + 2);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(b->d_counters + 3, b->d_cut + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    return MUSE_OK;
+}
+
+// The exact list was longer than the launch bound: score the rest now that its length is known.
+static int run_fused_overflow(muse_batch *b, int64_t n_exact) {
+    const int64_t S = b->g->size;
+    if (n_exact <= std::min<int64_t>(S, MUSE_EXACT_UB)) return MUSE_OK;
+    return score_exact_all(b, 0, b->d_list + MUSE_EXACT_UB, n_exact - MUSE_EXACT_UB);
 }
 
 static int run_scores(muse_batch *b, const RunArgs &a) {
     int rc = ensure_scratch(b);
     if (rc) return rc;
     memset(&b->timing, 0, sizeof(b->timing));
+    b->fused_run = 0;
     cudaStream_t st = b->ctx->stream;
     CU(cudaEventRecord(b->ev[0], st));
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
@@ -1090,6 +1218,14 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     // unsigned scores can pass, and a store big enough to be worth two extra round trips
     const bool can_screen = b->screen_ok && a.n_key_cols == 0 && !a.signed_scores && a.sign_filter != MUSE_SIGN_NEG;
     bool screen = can_screen && (a.mode == MUSE_MODE_SCREEN || (a.mode == MUSE_MODE_AUTO && b->g->size >= 16384));
+    if (screen && b->log2m == 10) {
+        b->timing.mode = MUSE_MODE_SCREEN;
+        b->fused_run = 1;
+        rc = score_fused(b, a);
+        if (rc) return rc;
+        CU(cudaEventRecord(b->ev[2], st));
+        return MUSE_OK;
+    }
     if (screen) {
         bool fell_back = false;
         b->timing.mode = MUSE_MODE_SCREEN;

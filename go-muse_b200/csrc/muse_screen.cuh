@@ -35,6 +35,9 @@ typedef cx<float> cf;
 // 1.1e-9 in units of the score per bin; std <= 1e14: |2Y_k|^2 <= (4*N*std)^2 * N < 3e38.
 #define MUSE_SCREEN_VAR_MIN 1e-20f
 #define MUSE_SCREEN_VAR_MAX 1e28f
+// running cut-off: lower bounds are counted in MUSE_CUT_BINS bins of [0, 1], MUSE_CUT_COARSE groups of 64
+#define MUSE_CUT_BINS 4096
+#define MUSE_CUT_COARSE 64
 
 struct ScreenParams {
     const double *slab;
@@ -46,6 +49,16 @@ struct ScreenParams {
     const float *A;       // |X_k|/(2n) * (k == 0 || k == M ? 1 : 2), rounded up, M+1 entries
     const float4 *sw;     // warp kernel: (twn[k].x, twn[k].y, A[k], A[M-k]) for k < M/2
     float a_mid;          // warp kernel: A[M/2]
+    // ---- fused refinement (warp kernel) ----
+    const float4 *sx;     // (Xt[k].x, Xt[k].y, Xt[M-k].x, Xt[M-k].y) in fp32, k < M/2 (Xt = X/(2n))
+    cf x_mid;             // Xt[M/2]
+    float *out_L;         // [count] certain lower bound on a score that certainly passes the lag filter, else -1
+    unsigned *cut_bits;   // running lower bound on the final top-N cut-off (float bits, only ever raised)
+    unsigned *cut_hist;   // [MUSE_CUT_COARSE] coarse counts, then [MUSE_CUT_BINS] fine counts of lower bounds
+    unsigned long long *n_refined;
+    int top_n;            // series needed above the cut before it may rise
+    int win_lo, win_len;  // lag window in the kernel's rotated cc index: (idx - win_lo) mod n <= win_len
+    float thr;            // threshold rounded up to fp32 (a lower bound must reach it to count)
     float *out_U;         // [count] upper bound on the score (already clamped to <= 1 + slack)
 };
 
@@ -223,6 +236,12 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned r;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
 __device__ __forceinline__ void mbar_test(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -263,6 +282,18 @@ struct ScreenWarpCfg {
 // gets both magnitudes from one mirror exchange: Z[M-k] sits in lane (32-t)%32, slot 31-j
 // (lane 0: its own slot (32-j)%32; k = 0 pairs with itself and yields the DC and Nyquist
 // terms).  Only k = 512 (lane 0, slot 16, its own mirror) is left over: |2Y[512]| = 2|Z[512]|.
+//
+// Fused second stage: U is loose (it ignores every phase), and on the benchmark's data
+// a few percent of the series have U above the top-N cut-off.  A warp whose U reaches the
+// RUNNING cut-off therefore goes on, with the spectrum still in registers: conj(Y)*X in fp32,
+// inverse FFT, max |cc| inside and outside the lag window.  That replaces U by the much
+// tighter u32 = |cc|_max/std + slack (or by -1 when the peak is certainly outside the window:
+// the series fails results.go:46-48), and yields a certain LOWER bound for series that certainly
+// pass the filter.  Lower bounds are counted in a global histogram; the top_n-th largest so far
+// is a valid lower bound on the final cut-off and becomes the new running cut-off (it only ever
+// rises, so a stale read is merely less sharp).  Afterwards only series with out_U >= final cut
+// -- a few hundred -- need the exact fp64 kernel.  The cc index is rotated by pad = n - N against
+// xcorr.go's (zeros trail here, lead there): true index = (idx - pad) mod n.
 template <int NZ>
 __global__ void __launch_bounds__(ScreenWarpCfg::MAX_WARPS * 32, 1)
 score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, const unsigned row_bytes) {
@@ -293,6 +324,11 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
     __syncwarp();
 
     for (unsigned phase = 0; pos < prm.count; phase ^= 1u) {
+        // running cut-off: one lane reads it (so that the whole warp takes the same branch below) at
+        // the top of the iteration; the value is consumed only after U is known, a thousand
+        // instructions later, so the L2 round trip stays off the critical path.  +inf = no refinement
+        unsigned cut_raw = 0u;
+        if (t == 0) cut_raw = ld_relaxed_u32(prm.cut_bits);
         mbar_wait(bar, phase);      // every lane waits itself (one polling lane + __syncwarp measured 3x slower)
 
         // ---- row -> registers, then hand the buffer back to the copy engine ----
@@ -372,19 +408,162 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
         }
         acc = group_sum_f<32>(acc);
 
-        if (t == 0) {
-            const float var = ss / (float)(N - 1);
-            float U;
-            if (!(var >= MUSE_SCREEN_VAR_MIN) || !(var <= MUSE_SCREEN_VAR_MAX) || !(acc == acc)) {
-                // constant series (every y - mean rounds to 0; exact score 0), or a variance outside
-                // the window in which fp32 squares neither flush nor overflow, or NaN/Inf samples:
-                // the exact kernel decides
-                U = 2.f;
-            } else {
-                U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
-                if (!(U == U)) U = 2.f;
+        const float var = ss / (float)(N - 1);
+        float U;
+        if (!(var >= MUSE_SCREEN_VAR_MIN) || !(var <= MUSE_SCREEN_VAR_MAX) || !(acc == acc)) {
+            // constant series (every y - mean rounds to 0; exact score 0), or a variance outside
+            // the window in which fp32 squares neither flush nor overflow, or NaN/Inf samples:
+            // the exact kernel decides
+            U = 2.f;
+        } else {
+            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
+            if (!(U == U)) U = 2.f;
+        }
+        float L = -1.f;
+        const float cut_now = __uint_as_float(__shfl_sync(0xffffffffu, cut_raw, 0));
+        if (U >= cut_now && U < 1.5f) {      // warp-uniform: U comes out of a butterfly reduction
+            // ---- conj(Y)*X on the mirror pairs of the split (pointwise_pair), in place:
+            //      Z'[k] -> own slot j;  Z'[M-k] -> the partner's slot 31-j (lane 0: its own slot 32-j) ----
+#pragma unroll
+            for (int j = 0; j < P / 2; j++) {
+                const cf zk = v[Perm<P>::at(j)];
+                const cf zp = v[Perm<P>::at(P - 1 - j)];
+                const cf zs = v[Perm<P>::at((P - j) & (P - 1))];
+                cf src, zm;
+                src.x = lane0 ? zs.x : zp.x;
+                src.y = lane0 ? zs.y : zp.y;
+                zm.x = __shfl_sync(0xffffffffu, src.x, partner);
+                zm.y = __shfl_sync(0xffffffffu, src.y, partner);
+                const float4 s = prm.sw[t + 32 * j];
+                const float4 x = prm.sx[t + 32 * j];
+                cf ok, om;
+                pointwise_pair(zk, zm, cf{s.x, s.y}, cf{x.x, x.y}, cf{x.z, x.w}, ok, om);
+                cf rcv;
+                rcv.x = __shfl_sync(0xffffffffu, om.x, partner);
+                rcv.y = __shfl_sync(0xffffffffu, om.y, partner);
+                v[Perm<P>::at(j)] = ok;
+                cf &hi = v[Perm<P>::at(P - 1 - j)];
+                hi.x = lane0 ? hi.x : rcv.x;
+                hi.y = lane0 ? hi.y : rcv.y;
+                if (j > 0) {
+                    cf &own = v[Perm<P>::at(P - j)];
+                    own.x = lane0 ? om.x : own.x;
+                    own.y = lane0 ? om.y : own.y;
+                }
             }
+            {   // k = 512 pairs with itself (lane 0, slot 16); w_512 = -i
+                cf &mid = v[Perm<P>::at(P / 2)];
+                cf ok, om;
+                pointwise_pair(mid, mid, cf{0.f, -1.f}, prm.x_mid, prm.x_mid, ok, om);
+                mid.x = lane0 ? ok.x : mid.x;
+                mid.y = lane0 ? ok.y : mid.y;
+            }
+            // ---- inverse FFT_1024 as swap(FFT(swap(.))) (pointwise_pair stores the swapped values) ----
+            cf u[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) u[j] = v[Perm<P>::at(j)];
+            Dft<P, float>::run(u);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                cf val = u[Perm<P>::at(j)];
+                if (j > 0) val = cmul(val, prm.twp[(j - 1) * 32 + t]);
+                sm[G::pad(32 * t + j)] = val;
+            }
+            __syncwarp();
+            fft_pass_load<10, 5, 1, float>(u, sm, t);
+            __syncwarp();
+            Dft<P, float>::run(u);      // u[Perm(j)] = (cc'[2i+1], cc'[2i]), i = t + 32*j; cc' = std * cc rotated by pad
+            // ---- max |cc'| inside and outside the lag window ----
+            float m_in = 0.f, m_out = 0.f;
+            const int base = 2 * t - prm.win_lo;
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const cf r = u[Perm<P>::at(j)];
+                const bool in0 = ((base + 64 * j) & (2 * M - 1)) <= prm.win_len;
+                const bool in1 = ((base + 64 * j + 1) & (2 * M - 1)) <= prm.win_len;
+                const float a0 = fabsf(r.y), a1 = fabsf(r.x);
+                m_in = fmaxf(m_in, in0 ? a0 : 0.f);
+                m_out = fmaxf(m_out, in0 ? 0.f : a0);
+                m_in = fmaxf(m_in, in1 ? a1 : 0.f);
+                m_out = fmaxf(m_out, in1 ? 0.f : a1);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                m_in = fmaxf(m_in, __shfl_xor_sync(0xffffffffu, m_in, off));
+                m_out = fmaxf(m_out, __shfl_xor_sync(0xffffffffu, m_out, off));
+            }
+            const float rstd = rsqrtf(var);
+            const float s_in = m_in * rstd, s_out = m_out * rstd;
+            if (s_in == s_in && s_out == s_out) {
+                // |fp32 cc - exact cc| <= MUSE_SCREEN_SLACK / 2 in score units (error budget above, with the
+                // inverse transform doubling the FFT term); every decision below leaves a full slack
+                const float u32 = fminf(fmaxf(s_in, s_out) * 1.00001f, 1.f) + MUSE_SCREEN_SLACK;
+                if (s_out * 0.99999f - MUSE_SCREEN_SLACK > s_in * 1.00001f + MUSE_SCREEN_SLACK) {
+                    U = -1.f;                   // the peak is certainly outside the window: results.go:46-48 drops it
+                } else {
+                    U = fminf(U, u32);
+                    if (s_in * 0.99999f - MUSE_SCREEN_SLACK > s_out * 1.00001f + MUSE_SCREEN_SLACK)
+                        L = fminf(s_in * 0.99999f, 1.f) - MUSE_SCREEN_SLACK;      // certainly inside
+                }
+            }
+            if (t == 0) atomicAdd(prm.n_refined, 1ull);
+            // ---- a certain pass at or above the running cut-off: count it and try to raise the cut-off ----
+            if (L >= prm.thr && L >= cut_now) {
+                int bin = (int)(L * (float)MUSE_CUT_BINS);
+                bin = bin < 0 ? 0 : (bin >= MUSE_CUT_BINS ? MUSE_CUT_BINS - 1 : bin);
+                unsigned *coarse = prm.cut_hist, *fine = prm.cut_hist + MUSE_CUT_COARSE;
+                if (t == 0) {
+                    atomicAdd(&fine[bin], 1u);
+                    atomicAdd(&coarse[bin >> 6], 1u);
+                }
+                __syncwarp();
+                // all counts only grow, so every value read is a lower bound on the true count and any
+                // cut-off derived from them stays valid; lanes walk the bins from the top down
+                int cbin = -1;
+                unsigned need = (unsigned)prm.top_n;
+                {
+                    const unsigned h = ld_relaxed_u32(&coarse[63 - 2 * t]), l = ld_relaxed_u32(&coarse[62 - 2 * t]);
+                    unsigned incl = h + l;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (t >= off) incl += o;
+                    }
+                    const unsigned excl = incl - (h + l);
+                    const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+                    if (hit) {
+                        const int leader = __ffs(hit) - 1;
+                        const bool upper = excl + h >= need;
+                        const int cb = upper ? 63 - 2 * t : 62 - 2 * t;
+                        const unsigned above = upper ? excl : excl + h;
+                        cbin = __shfl_sync(0xffffffffu, cb, leader);
+                        need -= __shfl_sync(0xffffffffu, above, leader);
+                    }
+                }
+                if (cbin >= 0) {
+                    const unsigned *f = fine + cbin * 64;
+                    const unsigned h = ld_relaxed_u32(&f[63 - 2 * t]), l = ld_relaxed_u32(&f[62 - 2 * t]);
+                    unsigned incl = h + l;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+                        if (t >= off) incl += o;
+                    }
+                    const unsigned excl = incl - (h + l);
+                    const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+                    if (hit) {
+                        const int leader = __ffs(hit) - 1;
+                        if (t == leader) {
+                            const int fb = cbin * 64 + (excl + h >= need ? 63 - 2 * t : 62 - 2 * t);
+                            atomicMax(prm.cut_bits, __float_as_uint((float)fb / (float)MUSE_CUT_BINS));
+                        }
+                    }
+                }
+            }
+        }
+        if (t == 0) {
             prm.out_U[pos] = U;
+            if (prm.out_L) prm.out_L[pos] = L;
         }
         pos = next;
     }

@@ -60,8 +60,8 @@ class Partial(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("score_ms", C.c_float), ("rescore_ms", C.c_float),
-                ("select_ms", C.c_float), ("n_rescored", C.c_int64), ("mode", C.c_int32),
-                ("n_launches", C.c_int32)]
+                ("select_ms", C.c_float), ("n_rescored", C.c_int64), ("n_refined", C.c_int64),
+                ("mode", C.c_int32), ("n_launches", C.c_int32)]
 
 
 PARTIAL_DTYPE = np.dtype([("group_key", "<u8"), ("score", "<f8"), ("series_idx", "<i8"),
@@ -118,7 +118,7 @@ ABI = {
                                     C.c_int32, C.c_int32, _dp, _ip64, _ip64, _ip64]),
     "muse_batch_score_all": (C.c_int, [_vp, C.c_int32, _dp, _ip32]),
     "muse_batch_xcorr": (C.c_int, [_vp, C.c_int64, _dp, _ip32]),
-    "muse_batch_screen_bounds": (C.c_int, [_vp, _vp]),
+    "muse_batch_screen_bounds": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, _vp]),
     "muse_batch_run_partial": (C.c_int, [_vp, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                          C.c_int32, _vp, C.c_int64, _ip64]),
     "muse_batch_partial_capacity": (C.c_int64, [_vp, _ip32, C.c_int32, C.c_int64]),
@@ -303,12 +303,16 @@ class DeviceBatch:
         _check(lib().muse_batch_score_all(self.h, int(signed_scores), _d(sc), lg.ctypes.data_as(_ip32)))
         return sc[:S], lg[:S].astype(np.int64)
 
-    def screen_bounds(self) -> np.ndarray:
-        """fp32 upper bound on every series' score (diagnostic; > 1 means undecided)."""
+    def screen_bounds(self, refine: bool = False, max_lag: int = 0):
+        """fp32 bounds of every series (diagnostic).  refine=False: the spectral upper bound (> 1 means
+        undecided).  refine=True: (upper, lower) of the fused second stage for the lag window max_lag:
+        upper == -1: certainly outside the window; lower >= 0: certainly inside, score >= lower."""
         S = self.store.size()
         u = np.zeros(max(S, 1), dtype=np.float32)
-        _check(lib().muse_batch_screen_bounds(self.h, u.ctypes.data_as(_vp)))
-        return u[:S]
+        lo = np.full(max(S, 1), -1.0, dtype=np.float32)
+        _check(lib().muse_batch_screen_bounds(self.h, int(refine), int(max_lag), u.ctypes.data_as(_vp),
+                                              lo.ctypes.data_as(_vp)))
+        return (u[:S], lo[:S]) if refine else u[:S]
 
     def xcorr(self, local_index: int):
         cc = np.zeros(self.fft_len())

@@ -72,6 +72,7 @@ typedef struct muse_timing {
     float rescore_ms;      /* fp64 re-scoring of screened survivors (0 in exact mode) */
     float select_ms;       /* group max + filter + top-N */
     int64_t n_rescored;    /* series that went through the fp64 kernel after screening */
+    int64_t n_refined;     /* series that took the fused fp32 second stage (inverse transform) */
     int32_t mode;          /* MUSE_MODE_EXACT or MUSE_MODE_SCREEN actually used */
     int32_t n_launches;    /* kernels launched by this run */
 } muse_timing;
@@ -171,10 +172,14 @@ int  muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t n_key_col
  * muse_batch.go:68-77).  Host outputs of muse_group_size() entries. */
 int  muse_batch_score_all(muse_batch *b, int32_t signed_scores, double *scores, int32_t *lags);
 
-/* Diagnostic: the fp32 screening pass alone.  bounds[i] >= series i's score from
+/* Diagnostic: the fp32 screening pass alone.  upper[i] >= series i's score from
  * muse_batch_score_all (a value > 1, e.g. 2.0, means "undecided: ask the fp64 kernel").
- * MUSE_ERR_UNSUPPORTED when the series length has no screening kernel. */
-int  muse_batch_screen_bounds(muse_batch *b, float *bounds);
+ * refine != 0 (FFT length 2048 only) sends EVERY series through the fused second stage
+ * (fp32 inverse transform) for the lag window max_lag: upper[i] = -1 when the peak is
+ * certainly outside the window (the series fails results.go:46-48), else a tight bound;
+ * lower[i] >= 0 is a certain lower bound on the score of a series whose lag is certainly
+ * inside the window, -1 otherwise.  MUSE_ERR_UNSUPPORTED when the shape has no such kernel. */
+int  muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t max_lag, float *upper, float *lower);
 
 /* The full cross-correlation vector cc[n] of one series (xcorr.go:160-197's first
  * return value; KAT support).  *std_zero is set when xcorr.go:165-168 applies. */

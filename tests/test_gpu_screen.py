@@ -104,6 +104,38 @@ def test_bound_dominates_exact_score(ctx, N):
     assert np.all(u[7::12] >= sc[7::12])
 
 
+@pytest.mark.parametrize("N,max_lag", [(1440, 60), (1440, 0), (1440, 5000), (1026, 15), (1500, 300), (2048, 60), (2046, 1)])
+def test_refined_bounds_bracket_exact_score(ctx, N, max_lag):
+    """Fused second stage (fp32 inverse transform) on every series: lower <= exact score <= upper, a series
+    declared outside the lag window really is, one declared inside really is; the fp32 error is reported."""
+    rng = np.random.default_rng(11 * N + max_lag)
+    S = 6000
+    Y = _adversarial(rng, S, N)
+    ref = np.zeros(N)
+    ref[N // 2 - 5:N // 2 + 5] = 1.5
+    ref += 0.1 * (rng.random(N) - 0.5)
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    b = mb.DeviceBatch(ctx, store, ref)
+    up, lo = b.screen_bounds(refine=True, max_lag=max_lag)
+    up = up.astype(np.float64)
+    lo = lo.astype(np.float64)
+    sc, lg = b.score_all()
+    inside = np.abs(lg) <= max_lag
+    out = up == -1.0
+    assert not np.any(out & inside)                  # "certainly outside" is never wrong
+    assert np.all(inside[lo >= 0])                   # "certainly inside" is never wrong
+    dec = ~out
+    assert np.all(up[dec] >= sc[dec] + 0.5e-4)       # upper bound with at least a quarter of the slack left
+    assert np.all(lo[lo >= 0] <= sc[lo >= 0] - 0.5e-4)
+    tight = dec & (up <= 1.5)
+    assert tight.sum() >= dec.sum() - S // 4         # only the tiny / constant / near-constant rows (3 kinds of 12) stay undecided
+    # the refined bound is tight: within ~2 slacks of the exact score almost everywhere it was computed
+    assert np.mean(up[tight] - sc[tight] <= 4.2e-4) > 0.99
+    # most rows are decided one way or the other
+    assert (out | (lo >= 0)).mean() > 0.5
+
+
 def test_screening_prunes_on_siggen_data(ctx):
     # on the benchmark's own data only a few percent may reach the exact kernel
     N, S, seed = 1440, 200_000, 20261018
@@ -117,4 +149,5 @@ def test_screening_prunes_on_siggen_data(ctx):
     assert t.mode == mb.MODE_SCREEN
     for x, y in zip(e, s):
         np.testing.assert_array_equal(x, y)
-    assert 100 <= t.n_rescored <= 0.15 * S
+    assert 100 <= t.n_rescored <= 0.01 * S        # the fused fp32 second stage leaves a few hundred
+    assert t.n_refined <= 0.2 * S
