@@ -65,6 +65,8 @@ struct muse_group {
     int32_t *labels;    // [nkeys][cap]
     int32_t max_id[16];
     int64_t global_offset;
+    unsigned char *row_flags;   // [cap] screening: rows whose offset dwarfs their spread (filled lazily up to flags_upto)
+    int64_t flags_cap, flags_upto;
 };
 
 struct muse_batch {
@@ -229,6 +231,7 @@ extern "C" void muse_group_destroy(muse_group *g) {
     cudaSetDevice(g->ctx->device);
     if (g->slab) cudaFree(g->slab);
     if (g->labels) cudaFree(g->labels);
+    if (g->row_flags) cudaFree(g->row_flags);
     delete g;
 }
 
@@ -387,6 +390,7 @@ extern "C" int muse_group_clear(muse_group *g) {
     CU(cudaSetDevice(g->ctx->device));
     CU(cudaStreamSynchronize(g->ctx->stream));
     g->size = 0;
+    g->flags_upto = 0;
     for (int k = 0; k < 16; k++) g->max_id[k] = -1;
     return MUSE_OK;
 }
@@ -930,6 +934,25 @@ static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cud
     return cudaErrorInvalidValue;
 }
 
+// Per-row offset flags of the store, computed once for rows appended since the last screened run.
+static int refresh_row_flags(muse_group *g) {
+    if (g->flags_cap < g->cap) {
+        if (g->row_flags) cudaFree(g->row_flags);
+        g->row_flags = nullptr;
+        CU(cudaMalloc(&g->row_flags, (size_t)g->cap));
+        g->flags_cap = g->cap;
+        g->flags_upto = 0;
+    }
+    if (g->flags_upto < g->size) {
+        const int64_t count = g->size - g->flags_upto;
+        const unsigned grid = (unsigned)std::min<int64_t>((count + 7) / 8, (int64_t)g->ctx->sm_count * 16);
+        row_offset_flags_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, (int)g->N, g->flags_upto, count, g->row_flags);
+        CU(cudaGetLastError());
+        g->flags_upto = g->size;
+    }
+    return MUSE_OK;
+}
+
 static ScreenParams screen_params(muse_batch *b) {
     ScreenParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -945,6 +968,7 @@ static ScreenParams screen_params(muse_batch *b) {
     sp.out_U = b->d_U;
     sp.sx = b->sx_f;
     sp.x_mid = b->x_mid;
+    sp.row_flags = b->g->row_flags;
     sp.cut_bits = b->d_cut;
     sp.n_refined = reinterpret_cast<unsigned long long *>(b->d_cut + 2);
     sp.cut_hist = b->d_cut + 4;
@@ -960,6 +984,9 @@ __global__ void init_cut_kernel(unsigned *state, float cut0) {
 
 static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t max_lag, int64_t top_n, double threshold) {
     if (b->log2m != 10) return MUSE_OK;
+    int rc = refresh_row_flags(b->g);
+    if (rc) return rc;
+    sp.row_flags = b->g->row_flags;
     init_cut_kernel<<<1, 256, 0, b->ctx->stream>>>(b->d_cut, cut0);
     CU(cudaGetLastError());
     const int64_t n = b->n, pad = n - b->N;

@@ -35,6 +35,13 @@ typedef cx<float> cf;
 // 1.1e-9 in units of the score per bin; std <= 1e14: |2Y_k|^2 <= (4*N*std)^2 * N < 3e38.
 #define MUSE_SCREEN_VAR_MIN 1e-20f
 #define MUSE_SCREEN_VAR_MAX 1e28f
+// |mean| <= 1e8 * std: the fp64 sum of N values of size |mean| is uncertain by at most
+// N * 2^-53 * N * |mean| (sequential worst case), i.e. the mean by 1.6e-13 * |mean| at N = 1440; a
+// shift of the mean by d moves a score by at most d / std, so the limit keeps the disagreement
+// between this kernel's mean and the exact kernel's (summed in another order) below 2e-5, a tenth of
+// the slack.  Rows beyond it are flagged once per store by row_offset_flags_kernel (a register for
+// the mean across the FFT costs this kernel 5 %) and always go to the exact kernel.
+#define MUSE_SCREEN_OFFSET_MAX 1e8
 // running cut-off: lower bounds are counted in MUSE_CUT_BINS bins of [0, 1], MUSE_CUT_COARSE groups of 64
 #define MUSE_CUT_BINS 4096
 #define MUSE_CUT_COARSE 64
@@ -53,6 +60,7 @@ struct ScreenParams {
     const float4 *sx;     // (Xt[k].x, Xt[k].y, Xt[M-k].x, Xt[M-k].y) in fp32, k < M/2 (Xt = X/(2n))
     cf x_mid;             // Xt[M/2]
     float *out_L;         // [count] certain lower bound on a score that certainly passes the lag filter, else -1
+    const unsigned char *row_flags;   // [count] 1: |mean| > MUSE_SCREEN_OFFSET_MAX * std (row_offset_flags_kernel): never bounded here
     unsigned *cut_bits;   // running lower bound on the final top-N cut-off (float bits, only ever raised)
     unsigned *cut_hist;   // [MUSE_CUT_COARSE] coarse counts, then [MUSE_CUT_BINS] fine counts of lower bounds
     unsigned long long *n_refined;
@@ -252,6 +260,35 @@ __device__ __forceinline__ void mbar_test(unsigned bar, unsigned parity) {
         : "memory");
 }
 
+// flags[i] = 1 when row first+i has |mean| > MUSE_SCREEN_OFFSET_MAX * std (std > 0).  One warp per row;
+// sums are taken about the row's first sample so that the one-pass variance does not cancel.
+__global__ void row_offset_flags_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
+                                        unsigned char *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < count; i += nwarp) {
+        const double *row = slab + (first + i) * ld;
+        const double pivot = row[0];
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = lane; k < N; k += 32) {
+            const double x = row[k] - pivot;
+            s1 += x;
+            s2 = fma(x, x, s2);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        }
+        if (lane == 0) {
+            const double mean = pivot + s1 / N;
+            const double var = (s2 - s1 * s1 / N) / (N - 1);
+            flags[first + i] = (var > 0.0 && mean * mean > MUSE_SCREEN_OFFSET_MAX * MUSE_SCREEN_OFFSET_MAX * var) ? 1 : 0;
+        }
+    }
+}
+
 struct ScreenWarpCfg {
     using G = Geo<10, 5>;                       // M = 1024 = 32 x 32: one warp per series
     static constexpr int MAX_WARPS = 12;   // 3 warps per scheduler: up to 168 registers per thread
@@ -305,8 +342,10 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
 
     const int w = threadIdx.x >> 5;
     const int t = threadIdx.x & 31;
-    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
-    int64_t pos = (int64_t)blockIdx.x * (blockDim.x >> 5) + w;
+    // 32-bit series indices (a store holds < 2^31 series): the kernel sits on a register cliff at 168
+    const int count = (int)prm.count;
+    const int stride = (int)(gridDim.x * (blockDim.x >> 5));
+    const int pos0 = (int)(blockIdx.x * (blockDim.x >> 5)) + w;
     unsigned char *buf = smem_raw + (size_t)w * warp_bytes;
     const cd *rowc = reinterpret_cast<const cd *>(buf);
     cf *sm = reinterpret_cast<cf *>(buf + row_bytes);
@@ -319,49 +358,57 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
 
     if (t == 0) {
         mbar_init(bar, 1);
-        if (pos < prm.count) bulk_load(smem_u32(buf), prm.slab + pos * prm.ld, (unsigned)N * 8u, bar);
+        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)N * 8u, bar);
     }
     __syncwarp();
 
-    for (unsigned phase = 0; pos < prm.count; phase ^= 1u) {
+    // mbarrier phase parity = iteration parity; it rides in bit 31 of the loop counter (count < 2^31):
+    // a separate loop-carried register is one too many for the allocator at 168 and gets spilled
+    for (unsigned pp = (unsigned)pos0; (int)(pp & 0x7fffffffu) < count; pp = ((pp & 0x7fffffffu) + (unsigned)stride) | (~pp & 0x80000000u)) {
+        const int pos = (int)(pp & 0x7fffffffu);
+        const unsigned phase = pp >> 31;
         // running cut-off: one lane reads it (so that the whole warp takes the same branch below) at
         // the top of the iteration; the value is consumed only after U is known, a thousand
         // instructions later, so the L2 round trip stays off the critical path.  +inf = no refinement
-        unsigned cut_raw = 0u;
-        if (t == 0) cut_raw = ld_relaxed_u32(prm.cut_bits);
+        unsigned cut_raw = 0u, flag_raw = 0u;
+        if (t == 0) {
+            cut_raw = ld_relaxed_u32(prm.cut_bits);
+            flag_raw = prm.row_flags[pos];      // not combined here: any use of the values would wait for the loads
+        }
         mbar_wait(bar, phase);      // every lane waits itself (one polling lane + __syncwarp measured 3x slower)
 
-        // ---- row -> registers, then hand the buffer back to the copy engine ----
-        cd d[NZ];
-#pragma unroll
-        for (int r = 0; r < NZ; r++) d[r] = (r < NZ - 1 || last_in) ? rowc[t + r * 32] : cd{0.0, 0.0};
-        __syncwarp();
-        const int64_t next = pos + stride;
-        if (t == 0 && next < prm.count) bulk_load(smem_u32(buf), prm.slab + next * prm.ld, (unsigned)N * 8u, bar);
-
-        // ---- mean in fp64 (xcorr.go:85-86), centred samples in fp32 ----
+        // ---- row -> registers; mean in fp64 (xcorr.go:85-86) ----
+        constexpr int KEEP = NZ;       // rows kept in registers across the reduction (a smaller KEEP re-reads the rest; measured slower)
+        cd d[KEEP];
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int r = 0; r < NZ; r++) {
-            s0 += d[r].x;
-            s1 += d[r].y;
+            const cd x = (r < NZ - 1 || last_in) ? rowc[t + r * 32] : cd{0.0, 0.0};
+            if (r < KEEP) d[r] = x;
+            s0 += x.x;
+            s1 += x.y;
         }
         double sum = s0 + s1;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
         const double mu = sum / (double)N;
+
+        // ---- centred samples in fp32, then hand the buffer back to the copy engine ----
         cf v[P];
         cf ss2{0.f, 0.f};
 #pragma unroll
         for (int r = 0; r < P; r++) {
             if (r < NZ) {
-                v[r] = cf{(float)(d[r].x - mu), (float)(d[r].y - mu)};
-                if (r == NZ - 1 && !last_in) v[r] = cf{0.f, 0.f};
+                const cd x = (r == NZ - 1 && !last_in) ? cd{mu, mu} : (r < KEEP ? d[r] : rowc[t + r * 32]);
+                v[r] = cf{(float)(x.x - mu), (float)(x.y - mu)};
                 ss2 = pfma(v[r], v[r], ss2);
             } else {
                 v[r] = cf{0.f, 0.f};
             }
         }
+        __syncwarp();
+        const int next = pos + stride;      // < 2^31: the launcher keeps count + stride below it
+        if (t == 0 && next < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
         const float ss = group_sum_f<32>(ss2.x + ss2.y);
 
         // ---- forward FFT_1024: pruned radix-32, twiddle, exchange through smem, radix-32 ----
@@ -420,7 +467,13 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
             if (!(U == U)) U = 2.f;
         }
         float L = -1.f;
-        const float cut_now = __uint_as_float(__shfl_sync(0xffffffffu, cut_raw, 0));
+        // The two broadcasts must not be scheduled before this point: they would wait for the loads
+        // issued at the top of the iteration (measured: +8 % kernel time).  Their source lane
+        // therefore depends on acc, which exists only now; it is 0 unless acc has one particular
+        // NaN pattern, and then lane 1's zeros merely send the series through the refinement.
+        const int bsrc = (__float_as_uint(acc) == 0x7fc12345u) ? 1 : 0;
+        const float cut_now = __uint_as_float(__shfl_sync(0xffffffffu, cut_raw, bsrc));
+        if (__shfl_sync(0xffffffffu, flag_raw, bsrc)) U = 2.f;   // offset too large against the spread for any fp32 statement: the exact kernel decides
         if (U >= cut_now && U < 1.5f) {      // warp-uniform: U comes out of a butterfly reduction
             // ---- conj(Y)*X on the mirror pairs of the split (pointwise_pair), in place:
             //      Z'[k] -> own slot j;  Z'[M-k] -> the partner's slot 31-j (lane 0: its own slot 32-j) ----
@@ -565,7 +618,6 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
             prm.out_U[pos] = U;
             if (prm.out_L) prm.out_L[pos] = L;
         }
-        pos = next;
     }
 }
 

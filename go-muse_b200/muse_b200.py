@@ -23,7 +23,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libmuse_b200.so")
+# MUSE_B200_LIB: an alternative build of the same library (kernel A/B runs); default = the in-tree build
+LIB_PATH = os.environ.get("MUSE_B200_LIB") or os.path.join(_HERE, "libmuse_b200.so")
 
 MUSE_OK = 0
 MUSE_ERR_INVALID_ARG = 1
