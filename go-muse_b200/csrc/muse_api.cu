@@ -15,7 +15,7 @@
 
 #include "../../include/muse_b200.h"
 #include "muse_exact.cuh"
-#include "muse_screen.cuh"
+#include "muse_screen_block.cuh"
 #include "muse_select.cuh"
 #include "muse_synth.cuh"
 
@@ -463,13 +463,15 @@ static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 
 }
 
 // fp32 tables of the screening kernel; leaves screen_ok = 0 when the shape has no screening kernel
-static int screen_log2m_supported(int log2m) { return log2m == 10 || log2m == 8; }
+static int screen_log2m_supported(int log2m) { return log2m == 8 || (log2m >= 10 && log2m <= 13); }
+// n >= 2048: kernels with the fused fp32 second stage (warp kernel at 2048, block kernel above)
+static int screen_is_fused(int log2m) { return log2m >= 10 && log2m <= 13; }
 
 static int rc_screen_tables(muse_batch *b) {
     b->screen_ok = 0;
     if (!screen_log2m_supported(b->log2m) || (b->N & 1)) return MUSE_OK;
     const int64_t M = b->n / 2;
-    const int log2p = b->log2m / 2;
+    const int log2p = b->log2m == 8 ? 4 : 5;
     cudaStream_t st = b->ctx->stream;
     const long double PI2 = 6.283185307179586476925286766559005768L;
     std::vector<cf> twp((size_t)M + 64), twn((size_t)M);
@@ -487,7 +489,7 @@ static int rc_screen_tables(muse_batch *b) {
         if ((double)f < a) f = nextafterf(f, INFINITY);   // round up: the bound must not shrink
         A[(size_t)k] = f;
     }
-    if (b->log2m == 10) {   // warp kernel: split twiddle and the two mirror weights in one 16-byte entry
+    if (screen_is_fused(b->log2m)) {   // split twiddle and the two mirror weights in one 16-byte entry
         std::vector<float4> sw((size_t)M / 2);
         for (int64_t k = 0; k < M / 2; k++) sw[(size_t)k] = make_float4(twn[(size_t)k].x, twn[(size_t)k].y, A[(size_t)k], A[(size_t)(M - k)]);
         CU(cudaMalloc(&b->sw_f, sizeof(float4) * sw.size()));
@@ -926,8 +928,26 @@ static cudaError_t launch_screen_warp(const ScreenParams &p, int sm_count, cudaS
     return cudaErrorInvalidValue;
 }
 
+template <int LOG2M, int MINB>
+static cudaError_t launch_screen_block(const ScreenParams &p, int sm_count, cudaStream_t st) {
+    using C = ScreenBlockCfg<LOG2M>;
+    auto kern = score_screen_block_kernel<LOG2M, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, C::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t blocks = std::min<int64_t>(p.count, (int64_t)sm_count * per_sm);     // persistent: grid-stride over the series
+    kern<<<(unsigned)blocks, C::T, C::SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cudaStream_t st) {
     switch (b->log2m) {
+        case 13: return launch_screen_block<13, 2>(p, b->ctx->sm_count, st);
+        case 12: return launch_screen_block<12, 4>(p, b->ctx->sm_count, st);
+        case 11: return launch_screen_block<11, 8>(p, b->ctx->sm_count, st);
         case 10: return launch_screen_warp(p, b->ctx->sm_count, st);
         case 8: return launch_screen_t<8>(p, st);
     }
@@ -983,7 +1003,7 @@ __global__ void init_cut_kernel(unsigned *state, float cut0) {
 }
 
 static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t max_lag, int64_t top_n, double threshold) {
-    if (b->log2m != 10) return MUSE_OK;
+    if (!screen_is_fused(b->log2m)) return MUSE_OK;
     int rc = refresh_row_flags(b->g);
     if (rc) return rc;
     sp.row_flags = b->g->row_flags;
@@ -1173,7 +1193,7 @@ extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t m
     if (rc) return rc;
     if (!upper || (refine && !lower)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_screen_bounds: NULL output");
     if (!b->screen_ok) return fail(MUSE_ERR_UNSUPPORTED, "no screening kernel for series length %lld", (long long)b->N);
-    if (refine && b->log2m != 10) return fail(MUSE_ERR_UNSUPPORTED, "the fused refinement needs an FFT length of 2048");
+    if (refine && !screen_is_fused(b->log2m)) return fail(MUSE_ERR_UNSUPPORTED, "the fused refinement needs an FFT length of 2048 .. 16384");
     CU(cudaSetDevice(b->ctx->device));
     rc = ensure_scratch(b);
     if (rc) return rc;
@@ -1245,7 +1265,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     // unsigned scores can pass, and a store big enough to be worth two extra round trips
     const bool can_screen = b->screen_ok && a.n_key_cols == 0 && !a.signed_scores && a.sign_filter != MUSE_SIGN_NEG;
     bool screen = can_screen && (a.mode == MUSE_MODE_SCREEN || (a.mode == MUSE_MODE_AUTO && b->g->size >= 16384));
-    if (screen && b->log2m == 10) {
+    if (screen && screen_is_fused(b->log2m)) {
         b->timing.mode = MUSE_MODE_SCREEN;
         b->fused_run = 1;
         rc = score_fused(b, a);

@@ -260,6 +260,76 @@ __device__ __forceinline__ void mbar_test(unsigned bar, unsigned parity) {
         : "memory");
 }
 
+// Warp-collective: count the certain lower bound L of a series that certainly passes the filter and
+// try to raise the running cut-off to the top_n-th largest lower bound counted so far.  All counts
+// only grow, so every value read is a lower bound on the true count and any cut-off derived from
+// them stays valid; lanes walk the bins from the top down (64 coarse groups, then the 64 fine bins
+// of the group in which the count reaches top_n).
+__device__ __forceinline__ void cut_count_and_raise(const ScreenParams &prm, float L, int t) {
+    int bin = (int)(L * (float)MUSE_CUT_BINS);
+    bin = bin < 0 ? 0 : (bin >= MUSE_CUT_BINS ? MUSE_CUT_BINS - 1 : bin);
+    unsigned *coarse = prm.cut_hist, *fine = prm.cut_hist + MUSE_CUT_COARSE;
+    if (t == 0) {
+        atomicAdd(&fine[bin], 1u);
+        atomicAdd(&coarse[bin >> 6], 1u);
+    }
+    __syncwarp();
+    int cbin = -1;
+    unsigned need = (unsigned)prm.top_n;
+    {
+        const unsigned h = ld_relaxed_u32(&coarse[63 - 2 * t]), l = ld_relaxed_u32(&coarse[62 - 2 * t]);
+        unsigned incl = h + l;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (t >= off) incl += o;
+        }
+        const unsigned excl = incl - (h + l);
+        const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+        if (hit) {
+            const int leader = __ffs(hit) - 1;
+            const bool upper = excl + h >= need;
+            const int cb = upper ? 63 - 2 * t : 62 - 2 * t;
+            const unsigned above = upper ? excl : excl + h;
+            cbin = __shfl_sync(0xffffffffu, cb, leader);
+            need -= __shfl_sync(0xffffffffu, above, leader);
+        }
+    }
+    if (cbin >= 0) {
+        const unsigned *f = fine + cbin * 64;
+        const unsigned h = ld_relaxed_u32(&f[63 - 2 * t]), l = ld_relaxed_u32(&f[62 - 2 * t]);
+        unsigned incl = h + l;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (t >= off) incl += o;
+        }
+        const unsigned excl = incl - (h + l);
+        const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+        if (hit) {
+            const int leader = __ffs(hit) - 1;
+            if (t == leader) {
+                const int fb = cbin * 64 + (excl + h >= need ? 63 - 2 * t : 62 - 2 * t);
+                atomicMax(prm.cut_bits, __float_as_uint((float)fb / (float)MUSE_CUT_BINS));
+            }
+        }
+    }
+}
+
+// Refined decision for one series from the fp32 maxima of |cc| inside / outside the lag window
+// (both already divided by std): returns the new upper bound (-1: certainly outside the window,
+// results.go:46-48 drops the series) and sets L when the peak is certainly inside.
+// |fp32 cc - exact cc| <= MUSE_SCREEN_SLACK / 2 in score units (error budget above, with the inverse
+// transform doubling the FFT term); every decision leaves a full slack.
+__device__ __forceinline__ float refine_decide(float U, float s_in, float s_out, float &L) {
+    if (!(s_in == s_in) || !(s_out == s_out)) return U;
+    const float u32 = fminf(fmaxf(s_in, s_out) * 1.00001f, 1.f) + MUSE_SCREEN_SLACK;
+    if (s_out * 0.99999f - MUSE_SCREEN_SLACK > s_in * 1.00001f + MUSE_SCREEN_SLACK) return -1.f;
+    if (s_in * 0.99999f - MUSE_SCREEN_SLACK > s_out * 1.00001f + MUSE_SCREEN_SLACK)
+        L = fminf(s_in * 0.99999f, 1.f) - MUSE_SCREEN_SLACK;      // certainly inside
+    return fminf(U, u32);
+}
+
 // flags[i] = 1 when row first+i has |mean| > MUSE_SCREEN_OFFSET_MAX * std (std > 0).  One warp per row;
 // sums are taken about the row's first sample so that the one-pass variance does not cancel.
 __global__ void row_offset_flags_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
@@ -547,72 +617,10 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
             }
             const float rstd = rsqrtf(var);
             const float s_in = m_in * rstd, s_out = m_out * rstd;
-            if (s_in == s_in && s_out == s_out) {
-                // |fp32 cc - exact cc| <= MUSE_SCREEN_SLACK / 2 in score units (error budget above, with the
-                // inverse transform doubling the FFT term); every decision below leaves a full slack
-                const float u32 = fminf(fmaxf(s_in, s_out) * 1.00001f, 1.f) + MUSE_SCREEN_SLACK;
-                if (s_out * 0.99999f - MUSE_SCREEN_SLACK > s_in * 1.00001f + MUSE_SCREEN_SLACK) {
-                    U = -1.f;                   // the peak is certainly outside the window: results.go:46-48 drops it
-                } else {
-                    U = fminf(U, u32);
-                    if (s_in * 0.99999f - MUSE_SCREEN_SLACK > s_out * 1.00001f + MUSE_SCREEN_SLACK)
-                        L = fminf(s_in * 0.99999f, 1.f) - MUSE_SCREEN_SLACK;      // certainly inside
-                }
-            }
+            U = refine_decide(U, s_in, s_out, L);
             if (t == 0) atomicAdd(prm.n_refined, 1ull);
             // ---- a certain pass at or above the running cut-off: count it and try to raise the cut-off ----
-            if (L >= prm.thr && L >= cut_now) {
-                int bin = (int)(L * (float)MUSE_CUT_BINS);
-                bin = bin < 0 ? 0 : (bin >= MUSE_CUT_BINS ? MUSE_CUT_BINS - 1 : bin);
-                unsigned *coarse = prm.cut_hist, *fine = prm.cut_hist + MUSE_CUT_COARSE;
-                if (t == 0) {
-                    atomicAdd(&fine[bin], 1u);
-                    atomicAdd(&coarse[bin >> 6], 1u);
-                }
-                __syncwarp();
-                // all counts only grow, so every value read is a lower bound on the true count and any
-                // cut-off derived from them stays valid; lanes walk the bins from the top down
-                int cbin = -1;
-                unsigned need = (unsigned)prm.top_n;
-                {
-                    const unsigned h = ld_relaxed_u32(&coarse[63 - 2 * t]), l = ld_relaxed_u32(&coarse[62 - 2 * t]);
-                    unsigned incl = h + l;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
-                        if (t >= off) incl += o;
-                    }
-                    const unsigned excl = incl - (h + l);
-                    const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
-                    if (hit) {
-                        const int leader = __ffs(hit) - 1;
-                        const bool upper = excl + h >= need;
-                        const int cb = upper ? 63 - 2 * t : 62 - 2 * t;
-                        const unsigned above = upper ? excl : excl + h;
-                        cbin = __shfl_sync(0xffffffffu, cb, leader);
-                        need -= __shfl_sync(0xffffffffu, above, leader);
-                    }
-                }
-                if (cbin >= 0) {
-                    const unsigned *f = fine + cbin * 64;
-                    const unsigned h = ld_relaxed_u32(&f[63 - 2 * t]), l = ld_relaxed_u32(&f[62 - 2 * t]);
-                    unsigned incl = h + l;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
-                        if (t >= off) incl += o;
-                    }
-                    const unsigned excl = incl - (h + l);
-                    const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
-                    if (hit) {
-                        const int leader = __ffs(hit) - 1;
-                        if (t == leader) {
-                            const int fb = cbin * 64 + (excl + h >= need ? 63 - 2 * t : 62 - 2 * t);
-                            atomicMax(prm.cut_bits, __float_as_uint((float)fb / (float)MUSE_CUT_BINS));
-                        }
-                    }
-                }
-            }
+            if (L >= prm.thr && L >= cut_now) cut_count_and_raise(prm, L, t);
         }
         if (t == 0) {
             prm.out_U[pos] = U;

@@ -1,0 +1,281 @@
+// muse_screen_block.cuh -- the fp32 screening + fused refinement pass for FFT lengths above 2048
+// (n = 4096, 8192, 16384: series of 2050 .. 16384 samples, e.g. one week at one sample per minute).
+//
+// Same mathematics and the same contract as score_screen_warp_kernel (muse_screen.cuh): a rigorous
+// upper bound U = (1/n) sum_f |Y_f||X_f| / std + slack for every series; a series whose U reaches the
+// running top-N cut-off goes on to conj(Y)*X, the inverse transform and the maxima of |cc| inside and
+// outside the lag window, which tighten the bound and feed the cut-off histogram.
+//
+// What differs is the shape: one series is M = n/2 complex points = 32 per thread on T = M/32
+// threads (T = 256 at n = 16384), one series per block, so the Stockham passes (radix 32, 32, and
+// 8 / 4 / 2) exchange through shared memory with block barriers, and the mirror pairs of the real
+// split are read from shared memory instead of being shuffled.
+//   * loads: each thread reads its 16-byte pairs straight from the slab (consecutive threads,
+//     consecutive addresses); the NEXT row of the block is pulled into L2 by one
+//     cp.async.bulk.prefetch.L2 at the top of the iteration, so the DRAM latency is paid under the
+//     previous series' FFT and the loads themselves hit L2;
+//   * centring: the whole row does not fit in registers as fp64 next to the fp32 FFT data, so the
+//     samples are converted as (y - pivot), pivot = the fp64 mean of the first 2T samples (one block
+//     reduction), and the fp64 mean of (y - pivot) is subtracted in fp32.  The rounding is then
+//     relative to |y - pivot| <= |y - mean| + |mean - pivot|, and |mean - pivot| <= std*sqrt(N/(2T)) = 4.5 std,
+//     which costs a factor below 6 on the 6e-8 input term of the error budget in muse_screen.cuh.
+#pragma once
+
+#include "muse_screen.cuh"
+
+namespace muse {
+
+template <int LOG2M>
+struct ScreenBlockCfg {
+    static_assert(LOG2M >= 11 && LOG2M <= 13, "block kernel: n = 4096 .. 16384");
+    using G = Geo<LOG2M, 5>;
+    static constexpr int T = G::T;                   // threads per series == block size (64, 128, 256)
+    static constexpr int NWARP = T / 32;
+    static constexpr size_t SMEM = (size_t)(G::MP + 1) * sizeof(cf);
+    static constexpr int LAST = G::NPASS - 1;        // NPASS == 3
+    static constexpr int LR_LAST = G::log2r(LAST);   // 1, 2, 3
+    static constexpr int R_LAST = 1 << LR_LAST;
+    static constexpr int NB_LAST = 32 / R_LAST;
+    static constexpr int LS_LAST = 10;
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void l2_prefetch(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Block-wide sums / maxima: every thread returns the same value (same order of operations).
+template <int NWARP>
+__device__ __forceinline__ double block_sum_d(double x, double *red, int tid) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    if ((tid & 31) == 0) red[tid >> 5] = x;
+    __syncthreads();
+    double s = red[0];
+#pragma unroll
+    for (int w = 1; w < NWARP; w++) s += red[w];
+    __syncthreads();
+    return s;
+}
+template <int NWARP>
+__device__ __forceinline__ float2 block_sum_f2(float a, float b, float2 *red, int tid) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = make_float2(a, b);
+    __syncthreads();
+    float2 s = red[0];
+#pragma unroll
+    for (int w = 1; w < NWARP; w++) {
+        s.x += red[w].x;
+        s.y += red[w].y;
+    }
+    __syncthreads();
+    return s;
+}
+template <int NWARP>
+__device__ __forceinline__ float2 block_max_f2(float a, float b, float2 *red, int tid) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, off));
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = make_float2(a, b);
+    __syncthreads();
+    float2 s = red[0];
+#pragma unroll
+    for (int w = 1; w < NWARP; w++) {
+        s.x = fmaxf(s.x, red[w].x);
+        s.y = fmaxf(s.y, red[w].y);
+    }
+    __syncthreads();
+    return s;
+}
+
+// Forward FFT_M of the 32 points per thread in v (input j of thread t = element t + T*j); on return
+// v[c*R_LAST + Perm<R_LAST>(j)] = Z[(t + c*T) + (j << 10)].  Ends WITHOUT a barrier after the last
+// pass' loads: the caller synchronises before it writes the exchange buffer again.
+template <int LOG2M>
+__device__ __forceinline__ void block_fft(cf *v, cf *sm, int t, const cf *twp) {
+    using C = ScreenBlockCfg<LOG2M>;
+    fft_pass_compute_store<LOG2M, 5, 0, float, cf>(v, sm, t, twp);
+    __syncthreads();
+    fft_pass_load<LOG2M, 5, 1, float>(v, sm, t);
+    __syncthreads();
+    fft_pass_compute_store<LOG2M, 5, 1, float, cf>(v, sm, t, twp);
+    __syncthreads();
+    fft_pass_load<LOG2M, 5, 2, float>(v, sm, t);
+#pragma unroll
+    for (int c = 0; c < C::NB_LAST; c++) Dft<C::R_LAST, float>::run(v + c * C::R_LAST);
+}
+
+template <int LOG2M, int MINB>
+__global__ void __launch_bounds__(ScreenBlockCfg<LOG2M>::T, MINB)
+score_screen_block_kernel(const ScreenParams prm) {
+    using C = ScreenBlockCfg<LOG2M>;
+    using G = typename C::G;
+    constexpr int P = 32, M = G::M, T = C::T, NW = C::NWARP;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double red_d[NW];
+    __shared__ float2 red_f[NW];
+    __shared__ unsigned bc_word[2];                  // running cut-off and row flag, broadcast by thread 0
+    cf *sm = reinterpret_cast<cf *>(smem_raw);
+
+    const int t = threadIdx.x;
+    const int N = prm.N;
+    const int Nh = N >> 1;
+    const int nz = (Nh + T - 1) / T;                 // rows of T complex slots that hold samples
+    const int count = (int)prm.count;
+    const unsigned row_bytes = (unsigned)N * 8u;
+
+    for (int pos = blockIdx.x; pos < count; pos += gridDim.x) {
+        const double *rowp = prm.slab + (int64_t)pos * prm.ld;
+        unsigned cut_raw = 0u, flag_raw = 0u;
+        if (t == 0) {
+            if (pos + (int)gridDim.x < count) l2_prefetch(prm.slab + (int64_t)(pos + (int)gridDim.x) * prm.ld, row_bytes);
+            cut_raw = ld_relaxed_u32(prm.cut_bits);
+            flag_raw = prm.row_flags[pos];
+        }
+
+        // ---- pivot = mean of the first 2T samples (fp64) ----
+        const cd first = load_pair_stream(rowp + 2 * t);           // Nh > M/2 >= T: always a sample
+        const double pivot = block_sum_d<NW>(first.x + first.y, red_d, t) / (double)(2 * T);
+
+        // ---- (y - pivot) -> fp32 registers, fp64 sum of (y - pivot) ----
+        cf v[P];
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < P; r++) {
+            v[r] = cf{0.f, 0.f};
+            if (r < nz) {
+                const int j = t + r * T;
+                if (j < Nh) {
+                    const cd x = r == 0 ? first : load_pair_stream(rowp + 2 * j);
+                    const double dx = x.x - pivot, dy = x.y - pivot;
+                    s0 += dx;
+                    s1 += dy;
+                    v[r] = cf{(float)dx, (float)dy};
+                }
+            }
+        }
+        const double dmean = block_sum_d<NW>(s0 + s1, red_d, t) / (double)N;   // mean - pivot
+        const float mf = (float)dmean;
+        cf ss2{0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < P; r++) {
+            if (r < nz && t + r * T < Nh) {
+                v[r] = cf{v[r].x - mf, v[r].y - mf};
+                ss2 = pfma(v[r], v[r], ss2);
+            }
+        }
+
+        // ---- forward FFT_M ----
+        block_fft<LOG2M>(v, sm, t, prm.twp);
+        __syncthreads();                                           // last pass' loads are done
+#pragma unroll
+        for (int c = 0; c < C::NB_LAST; c++)
+#pragma unroll
+            for (int j = 0; j < C::R_LAST; j++)
+                sm[G::pad((t + c * T) + (j << C::LS_LAST))] = v[c * C::R_LAST + Perm<C::R_LAST>::at(j)];
+        __syncthreads();
+
+        // ---- |2Y_k| and |2Y_(M-k)| for k = t + T*i < M/2 (k = 0 pairs with itself: DC and Nyquist) ----
+        cf acc2{0.f, 0.f};
+#pragma unroll 4
+        for (int i = 0; i < P / 2; i++) {
+            const int k = t + T * i;
+            const cf zk = sm[G::pad(k)];
+            const cf zm = sm[G::pad((M - k) & (M - 1))];
+            const float4 s = prm.sw[k];                            // (w_k.x, w_k.y, A[k], A[M-k])
+            const cf zmc = cconj(zm);
+            const cf e = cadd(zk, zmc);
+            const cf o = cmul_negi(csub(zk, zmc));
+            const cf wo = cmul(o, cf{s.x, s.y});
+            const cf y1 = cadd(e, wo);                             // 2*Y_k
+            const cf y2 = csub(e, wo);                             // 2*conj(Y_(M-k))
+            const cf q1 = pmul(y1, y1), q2 = pmul(y2, y2);
+            const cf mag{sqrt_approx(q1.x + q1.y), sqrt_approx(q2.x + q2.y)};
+            acc2 = pfma(mag, cf{s.z, s.w}, acc2);
+        }
+        float acc = acc2.x + acc2.y;
+        if (t == 0) {                                              // k = M/2, its own mirror: |2Y| = 2|Z|
+            const cf z = sm[G::pad(M / 2)];
+            const cf q = pmul(z, z);
+            acc = fmaf(sqrt_approx(q.x + q.y), 2.f * prm.a_mid, acc);
+            bc_word[0] = cut_raw;
+            bc_word[1] = flag_raw;
+        }
+        const float2 sums = block_sum_f2<NW>(acc, ss2.x + ss2.y, red_f, t);   // barrier inside: bc_word is visible
+        acc = sums.x;
+        const float var = sums.y / (float)(N - 1);
+        const float cut_now = __uint_as_float(bc_word[0]);
+        float U;
+        if (!(var >= MUSE_SCREEN_VAR_MIN) || !(var <= MUSE_SCREEN_VAR_MAX) || !(acc == acc) || bc_word[1]) {
+            U = 2.f;                                               // see score_screen_warp_kernel
+        } else {
+            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
+            if (!(U == U)) U = 2.f;
+        }
+        float L = -1.f;
+        if (U >= cut_now && U < 1.5f) {                            // block-uniform
+            // ---- conj(Y)*X on the mirror pairs, in place in shared memory (each pair has one owner) ----
+#pragma unroll 2
+            for (int i = 0; i < P / 2; i++) {
+                const int k = t + T * i;
+                const int m = (M - k) & (M - 1);
+                const cf zk = sm[G::pad(k)];
+                const cf zm = sm[G::pad(m)];
+                const float4 s = prm.sw[k];
+                const float4 x = prm.sx[k];
+                cf ok, om;
+                pointwise_pair(zk, zm, cf{s.x, s.y}, cf{x.x, x.y}, cf{x.z, x.w}, ok, om);
+                sm[G::pad(m)] = om;
+                sm[G::pad(k)] = ok;                                // k == m (k = 0): ok wins, as pointwise_phase
+            }
+            if (t == 0) {                                          // k = M/2; w = exp(-i*pi/2) = -i
+                const cf mid = sm[G::pad(M / 2)];
+                cf ok, om;
+                pointwise_pair(mid, mid, cf{0.f, -1.f}, prm.x_mid, prm.x_mid, ok, om);
+                sm[G::pad(M / 2)] = ok;
+            }
+            __syncthreads();
+            // ---- inverse FFT_M as swap(FFT(swap(.))) ----
+#pragma unroll
+            for (int j = 0; j < P; j++) v[j] = sm[G::pad(t + T * j)];
+            __syncthreads();
+            block_fft<LOG2M>(v, sm, t, prm.twp);
+            // v[c*R + Perm(j)] = (cc'[2k+1], cc'[2k]), k = (t + c*T) + (j << 10); cc' = std * cc rotated by pad
+            float m_in = 0.f, m_out = 0.f;
+            const int base = 2 * t - prm.win_lo;
+#pragma unroll
+            for (int c = 0; c < C::NB_LAST; c++)
+#pragma unroll
+                for (int j = 0; j < C::R_LAST; j++) {
+                    const cf r = v[c * C::R_LAST + Perm<C::R_LAST>::at(j)];
+                    const int off = 2 * (c * T + (j << C::LS_LAST));
+                    const bool in0 = ((base + off) & (2 * M - 1)) <= prm.win_len;
+                    const bool in1 = ((base + off + 1) & (2 * M - 1)) <= prm.win_len;
+                    const float a0 = fabsf(r.y), a1 = fabsf(r.x);
+                    m_in = fmaxf(m_in, fmaxf(in0 ? a0 : 0.f, in1 ? a1 : 0.f));
+                    m_out = fmaxf(m_out, fmaxf(in0 ? 0.f : a0, in1 ? 0.f : a1));
+                }
+            const float2 mx = block_max_f2<NW>(m_in, m_out, red_f, t);
+            const float rstd = rsqrtf(var);
+            U = refine_decide(U, mx.x * rstd, mx.y * rstd, L);
+            if (t == 0) atomicAdd(prm.n_refined, 1ull);
+            if (t < 32 && L >= prm.thr && L >= cut_now) cut_count_and_raise(prm, L, t);
+        }
+        if (t == 0) {
+            prm.out_U[pos] = U;
+            if (prm.out_L) prm.out_L[pos] = L;
+        }
+        __syncthreads();                                           // the exchange buffer and bc_word are free again
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace muse

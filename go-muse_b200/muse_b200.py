@@ -626,6 +626,44 @@ def NewBatch(ref: Series, comp: Group, results: Results, cc: int) -> Batch:
     return Batch(ref, comp, results, cc)
 
 
+class Muse:
+    """muse.go:12-92: one reference, Run(compGraphs) scores ONE group of series with SIGNED scores
+    (clamped to [-1, 1], muse.go:72-76), keeps the one with the largest |score| (strictly greater,
+    first always taken, muse.go:86) and pushes it through Results.Update."""
+
+    def __init__(self, ref: Series, results: Results, ctx: Optional[Context] = None):
+        if ref.Length() < 1:                                                # muse.go:24-26
+            raise MuseError(MUSE_ERR_INVALID_ARG, "Reference series length must be greater than zero")
+        self.Results = results
+        self.refN = ref.Length()
+        self._ctx = ctx or default_context()
+        self._ref = np.array(ref.Values(), dtype=np.float64, copy=True)
+        self._store = DeviceStore(self._ctx, self.refN, 0, 1)
+        self._batch = DeviceBatch(self._ctx, self._store, self._ref)        # MuseError "Invalid input query" on std == 0
+        self.n = self._batch.fft_len()
+
+    def Run(self, compGraphs: Sequence[Series]):
+        if len(compGraphs) == 0:                                            # muse.go:48-51
+            return None
+        for s in compGraphs:                                                # muse.go:70-72
+            if s.Length() != self.refN:
+                return MuseError(MUSE_ERR_LENGTH_MISMATCH,
+                                 "Encountered a comparison graph with differing length than the reference, %r" % s.Labels())
+        self._store.clear()
+        self._store.append(np.stack([np.asarray(s.Values(), dtype=np.float64) for s in compGraphs]))
+        sc, lg = self._batch.score_all(signed_scores=True)
+        best = 0
+        for i in range(1, len(sc)):                                         # muse.go:86: strictly greater |score|
+            if abs(sc[i]) > abs(sc[best]):
+                best = i
+        self.Results.Update(Score(compGraphs[best].Labels(), int(lg[best]), float(sc[best])))
+        return None
+
+
+def New(ref: Series, results: Results) -> Muse:
+    return Muse(ref, results)
+
+
 # ----------------------------------------------------------------------------------
 # multi-GPU: one process per GPU, shards merged with one small all-gather
 # ----------------------------------------------------------------------------------

@@ -58,6 +58,41 @@ def test_reference_batch_errors(kats):
     assert e.value.code == mb.MUSE_ERR_STDDEV_ZERO and "Invalid input query" in str(e.value)
 
 
+def test_reference_muse_run_kats(kats):
+    # muse_test.go:41-142: the signed Muse.Run path with all three sign filters, one series per Run
+    k = kats["muse_run_simple"]
+    for key, sf in (("expected_any", mb.SignFilter_ANY), ("expected_pos", mb.SignFilter_POS),
+                    ("expected_neg", mb.SignFilter_NEG)):
+        ref = mb.NewSeries(k["ref"]["y"], mb.NewLabels(k["ref"]["labels"]))
+        m = mb.New(ref, mb.NewResults(k["results"]["max_lag"], k["results"]["top_n"], k["results"]["threshold"], sf))
+        for s in _mk(k["comp"]):
+            assert m.Run([s]) is None
+        scores, _ = m.Results.Fetch()
+        _compare_scores(scores, k[key], k["score_tol"])
+    # one Run over the whole list keeps only the member with the largest |score| (muse.go:86)
+    ref = mb.NewSeries(k["ref"]["y"], mb.NewLabels(k["ref"]["labels"]))
+    m = mb.New(ref, mb.NewResults(k["results"]["max_lag"], k["results"]["top_n"], k["results"]["threshold"], mb.SignFilter_ANY))
+    assert m.Run(_mk(k["comp"])) is None
+    scores, _ = m.Results.Fetch()
+    om = mo.Muse(mo.Series(k["ref"]["y"], mo.Labels(k["ref"]["labels"])),
+                 mo.Results(k["results"]["max_lag"], k["results"]["top_n"], k["results"]["threshold"], mo.SIGN_FILTER_ANY))
+    om.Run([mo.Series(e["y"], mo.Labels(e["labels"])) for e in k["comp"]])
+    want, _ = om.Results.Fetch()
+    assert len(scores) == len(want)
+    for g, w in zip(scores, want):
+        assert abs(g.PercentScore - w.PercentScore) <= 1e-9 and g.Lag == w.Lag and g.Labels.labels == w.Labels.labels
+    # TestRunNoInput (muse_test.go) and the length check (muse.go:70-72)
+    m = mb.New(ref, mb.NewResults(10, 20, 0, 0))
+    assert m.Run([]) is None
+    scores, mean = m.Results.Fetch()
+    assert scores == [] and mean != mean
+    err = m.Run([mb.NewSeries([1.0, 2.0, 3.0], mb.NewLabels({"a": "b"}))])
+    assert isinstance(err, mb.MuseError) and "differing length" in str(err)
+    with pytest.raises(mb.MuseError) as e:
+        mb.New(mb.NewSeries([3.0, 3.0, 3.0, 3.0]), mb.NewResults(1, 1, 0, 0))
+    assert e.value.code == mb.MUSE_ERR_STDDEV_ZERO
+
+
 def test_example_structure(kats):
     # example_test.go:9-94 shape (C1): Run(nil) / ["graph"] / ["host"] on one Batch, Results reused
     rng = np.random.default_rng(5)
