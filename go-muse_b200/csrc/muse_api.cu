@@ -109,7 +109,7 @@ struct muse_batch {
     int32_t *d_gidx;
     cudaEvent_t ev[4];
     muse_timing timing;
-    int fused_run;         // this run went through score_fused (d_counters[2] = exact list length, [3] = refined)
+    int fused_run;         // 1: score_fused, 2: score_fused_grouped (d_counters[2] = exact list length, [3] = refined)
 };
 
 struct DeviceGuard {
@@ -821,7 +821,7 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
     if (b->fused_run) {
         b->timing.n_rescored = (int64_t)h_n[2];
         b->timing.n_refined = (int64_t)h_n[3];
-        if ((int64_t)h_n[2] > std::min<int64_t>(S, MUSE_EXACT_UB)) {
+        if (b->fused_run == 1 && (int64_t)h_n[2] > std::min<int64_t>(S, MUSE_EXACT_UB)) {
             // rare: more exact candidates than the fixed launch covered -> finish them and select again
             const int64_t n_exact = (int64_t)h_n[2];
             int rc = run_fused_overflow(b, n_exact);
@@ -952,6 +952,17 @@ static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cud
         case 8: return launch_screen_t<8>(p, st);
     }
     return cudaErrorInvalidValue;
+}
+
+static int ensure_lower(muse_batch *b) {
+    const int64_t S = b->g->size;
+    if (!b->d_L || b->d_L_cap < S) {
+        cudaFree(b->d_L);
+        b->d_L = nullptr;
+        CU(cudaMalloc(&b->d_L, sizeof(float) * (size_t)S));
+        b->d_L_cap = S;
+    }
+    return MUSE_OK;
 }
 
 // Per-row offset flags of the store, computed once for rows appended since the last screened run.
@@ -1202,12 +1213,8 @@ extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t m
     cudaStream_t st = b->ctx->stream;
     ScreenParams sp = screen_params(b);
     if (refine) {
-        if (!b->d_L || b->d_L_cap < S) {
-            cudaFree(b->d_L);
-            b->d_L = nullptr;
-            CU(cudaMalloc(&b->d_L, sizeof(float) * (size_t)S));
-            b->d_L_cap = S;
-        }
+        rc = ensure_lower(b);
+        if (rc) return rc;
         sp.out_L = b->d_L;
     }
     // refine: cut-off 0 that never rises (top_n = INT_MAX): every series takes the second stage
@@ -1246,6 +1253,46 @@ static int score_fused(muse_batch *b, const RunArgs &a) {
     return MUSE_OK;
 }
 
+// Grouped runs on the fused kernels: every series takes the fp32 second stage (bounds on the score
+// itself, window ignored), a group's best LOWER bound prunes its members, and only the members whose
+// upper bound reaches it -- the representative and whatever ties it within the fp32 slack -- are
+// scored in fp64.  The group max / representative / filter / top-N then run on those exact scores
+// exactly as in an all-exact run (every other member is provably below its group's representative).
+static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
+    const int64_t S = b->g->size;
+    cudaStream_t st = b->ctx->stream;
+    ScreenParams sp = screen_params(b);
+    int rc = ensure_lower(b);
+    if (rc) return rc;
+    sp.out_L = b->d_L;
+    sp.grouped = 1;
+    rc = arm_refinement(b, sp, 0.f, 0, 0x7fffffff, 0.0);         // cut-off 0 that never rises: refine everything
+    if (rc) return rc;
+    CU(launch_screen(b, sp, st));
+    b->timing.n_launches += 2;
+    CU(cudaEventRecord(b->ev[1], st));
+    CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "not its group's representative"
+    GroupTable gt;
+    memset(&gt, 0, sizeof(gt));
+    KeyCols kc;
+    memset(&kc, 0, sizeof(kc));
+    rc = setup_group_table(b, a, kc, gt);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((S + 255) / 256);
+    group_lower_bound_kernel<<<blocks, 256, 0, st>>>(gt, kc, b->d_L, S, b->d_slot);
+    group_contenders_kernel<<<blocks, 256, 0, st>>>(gt, b->d_U, S, b->d_slot, b->d_list, b->d_counters + 2);
+    b->timing.n_launches += 2;
+    CU(cudaGetLastError());
+    unsigned long long *h_n = reinterpret_cast<unsigned long long *>(b->h_pin);
+    CU(cudaMemcpyAsync(h_n, b->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));                                 // one small round trip: the list length sizes the launch
+    const int64_t n_exact = (int64_t)h_n[0];
+    rc = score_exact_all(b, 0, b->d_list, n_exact);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(b->d_counters + 3, b->d_cut + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    return MUSE_OK;
+}
+
 // The exact list was longer than the launch bound: score the rest now that its length is known.
 static int run_fused_overflow(muse_batch *b, int64_t n_exact) {
     const int64_t S = b->g->size;
@@ -1263,8 +1310,19 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
     // screening needs: a kernel for this FFT size, an ungrouped unsigned run, a sign filter that
     // unsigned scores can pass, and a store big enough to be worth two extra round trips
-    const bool can_screen = b->screen_ok && a.n_key_cols == 0 && !a.signed_scores && a.sign_filter != MUSE_SIGN_NEG;
+    // grouped runs are screened only by the fused kernels (the bound of a member says nothing about the
+    // lag of its group's representative; the fused second stage bounds every member's score tightly)
+    const bool can_screen = b->screen_ok && (a.n_key_cols == 0 || screen_is_fused(b->log2m)) && !a.signed_scores &&
+                            a.sign_filter != MUSE_SIGN_NEG;
     bool screen = can_screen && (a.mode == MUSE_MODE_SCREEN || (a.mode == MUSE_MODE_AUTO && b->g->size >= 16384));
+    if (screen && a.n_key_cols > 0) {
+        b->timing.mode = MUSE_MODE_SCREEN;
+        b->fused_run = 2;          // statistics as a fused run; its exact list is already complete
+        rc = score_fused_grouped(b, a);
+        if (rc) return rc;
+        CU(cudaEventRecord(b->ev[2], st));
+        return MUSE_OK;
+    }
     if (screen && screen_is_fused(b->log2m)) {
         b->timing.mode = MUSE_MODE_SCREEN;
         b->fused_run = 1;

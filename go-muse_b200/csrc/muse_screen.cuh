@@ -67,6 +67,7 @@ struct ScreenParams {
     int top_n;            // series needed above the cut before it may rise
     int win_lo, win_len;  // lag window in the kernel's rotated cc index: (idx - win_lo) mod n <= win_len
     float thr;            // threshold rounded up to fp32 (a lower bound must reach it to count)
+    int grouped;          // grouped run: every series is refined, bounds ignore the window, no cut-off
     float *out_U;         // [count] upper bound on the score (already clamped to <= 1 + slack)
 };
 
@@ -321,9 +322,15 @@ __device__ __forceinline__ void cut_count_and_raise(const ScreenParams &prm, flo
 // results.go:46-48 drops the series) and sets L when the peak is certainly inside.
 // |fp32 cc - exact cc| <= MUSE_SCREEN_SLACK / 2 in score units (error budget above, with the inverse
 // transform doubling the FFT term); every decision leaves a full slack.
-__device__ __forceinline__ float refine_decide(float U, float s_in, float s_out, float &L) {
+// grouped != 0: the window is not this series' business (its group's representative is decided by
+// the scores alone, muse_batch.go:87-89): upper and lower bound on the score itself.
+__device__ __forceinline__ float refine_decide(float U, float s_in, float s_out, float &L, int grouped) {
     if (!(s_in == s_in) || !(s_out == s_out)) return U;
     const float u32 = fminf(fmaxf(s_in, s_out) * 1.00001f, 1.f) + MUSE_SCREEN_SLACK;
+    if (grouped) {
+        L = fmaxf(fminf(fmaxf(s_in, s_out) * 0.99999f, 1.f) - MUSE_SCREEN_SLACK, 0.f);
+        return fminf(U, u32);
+    }
     if (s_out * 0.99999f - MUSE_SCREEN_SLACK > s_in * 1.00001f + MUSE_SCREEN_SLACK) return -1.f;
     if (s_in * 0.99999f - MUSE_SCREEN_SLACK > s_out * 1.00001f + MUSE_SCREEN_SLACK)
         L = fminf(s_in * 0.99999f, 1.f) - MUSE_SCREEN_SLACK;      // certainly inside
@@ -617,7 +624,7 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
             }
             const float rstd = rsqrtf(var);
             const float s_in = m_in * rstd, s_out = m_out * rstd;
-            U = refine_decide(U, s_in, s_out, L);
+            U = refine_decide(U, s_in, s_out, L, prm.grouped);
             if (t == 0) atomicAdd(prm.n_refined, 1ull);
             // ---- a certain pass at or above the running cut-off: count it and try to raise the cut-off ----
             if (L >= prm.thr && L >= cut_now) cut_count_and_raise(prm, L, t);

@@ -264,7 +264,7 @@ score_screen_block_kernel(const ScreenParams prm) {
                 }
             const float2 mx = block_max_f2<NW>(m_in, m_out, red_f, t);
             const float rstd = rsqrtf(var);
-            U = refine_decide(U, mx.x * rstd, mx.y * rstd, L);
+            U = refine_decide(U, mx.x * rstd, mx.y * rstd, L, prm.grouped);
             if (t == 0) atomicAdd(prm.n_refined, 1ull);
             if (t < 32 && L >= prm.thr && L >= cut_now) cut_count_and_raise(prm, L, t);
         }

@@ -82,6 +82,34 @@ __global__ void group_max_kernel(GroupTable gt, KeyCols kc, const double *__rest
     if (sc == sc) atomicMax(&gt.gmax[s], score_bits(sc));
 }
 
+// Grouped screening: slot per series + atomicMax of the fp32 LOWER bounds of the members' scores
+// (float bits in the low word of gmax; non-negative floats order like their bit patterns).
+__global__ void group_lower_bound_kernel(GroupTable gt, KeyCols kc, const float *__restrict__ lower, int64_t S,
+                                         int64_t *__restrict__ slot_of) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const int64_t s = table_slot(gt, kc, i);
+    slot_of[i] = s;
+    const float lo = lower[i];
+    if (lo >= 0.f) atomicMax(&gt.gmax[s], (unsigned long long)__float_as_uint(lo));
+}
+
+// ... and the members that can still be their group's representative: upper bound >= the group's
+// best lower bound (the true representative always qualifies, and so does every member that ties it)
+__global__ void group_contenders_kernel(GroupTable gt, const float *__restrict__ upper, int64_t S,
+                                        const int64_t *__restrict__ slot_of, int32_t *__restrict__ out,
+                                        unsigned long long *n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = i < S && upper[i] >= __uint_as_float((unsigned)gt.gmax[slot_of[i]]);
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
+}
+
 // pass 2: lowest series index among the members that hold the group max
 __global__ void group_rep_kernel(GroupTable gt, const double *__restrict__ score, int64_t S,
                                  const int64_t *__restrict__ slot_of) {

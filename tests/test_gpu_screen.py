@@ -138,6 +138,40 @@ def test_refined_bounds_bracket_exact_score(ctx, N, max_lag):
     assert (out | (lo >= 0)).mean() > 0.5
 
 
+@pytest.mark.parametrize("N", [1440, 2500, 10080])
+def test_grouped_screened_run_equals_exact_run(ctx, N):
+    """Grouped runs on the fused kernels: every member refined, a group's best lower bound prunes its members,
+    only the contenders are scored in fp64 -- the result must be the all-exact run's, bit for bit."""
+    rng = np.random.default_rng(3 * N)
+    S = 12000 if N <= 2048 else 4000
+    Y = _adversarial(rng, S, N)
+    ref = np.zeros(N)
+    ref[N // 2 - 5:N // 2 + 5] = 1.5
+    ref += 0.1 * (rng.random(N) - 0.5)
+    graph = (np.arange(S) // 40).astype(np.int32)
+    host = (np.arange(S) % 40).astype(np.int32)
+    colo = rng.integers(0, 3, S).astype(np.int32)
+    rnd = rng.integers(0, 1_500_000, S).astype(np.int32)      # hash-table path with singleton groups
+    store = mb.DeviceStore(ctx, N, 4, S)
+    store.append(Y, np.stack([graph, host, colo, rnd], axis=1))
+    b = mb.DeviceBatch(ctx, store, ref)
+    for cols in ([0], [1], [0, 2], [2], [3, 0]):
+        for max_lag, top_n, thr in ((60, 100, 0.5), (15, 10, 0.0), (N, 2000, 0.2)):
+            e = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_EXACT)
+            s = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_SCREEN)
+            t = b.timing()
+            assert t.mode == mb.MODE_SCREEN
+            for x, y in zip(e, s):
+                np.testing.assert_array_equal(x, y)
+    # the point of it: far fewer fp64 scorings than series
+    b.run([0], 60, 100, 0.5, mode=mb.MODE_SCREEN)
+    assert b.timing().n_rescored < 0.6 * S
+    # sharded partials (F2: unfiltered group representatives) also come out of the screened path unchanged
+    pe = b.run_partial([0, 2], 60, 100, 0.5, mode=mb.MODE_EXACT)
+    ps = b.run_partial([0, 2], 60, 100, 0.5, mode=mb.MODE_SCREEN)
+    np.testing.assert_array_equal(np.sort(pe, order=["group_key"]), np.sort(ps, order=["group_key"]))
+
+
 def test_fused_run_with_more_exact_candidates_than_the_launch_bound(ctx):
     """top_n above the store size: the cut-off never rises, every series reaches the exact kernel, and the
     list is longer than the fixed launch bound of the fused path (the overflow branch of run_select)."""
