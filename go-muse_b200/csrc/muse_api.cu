@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -48,11 +49,42 @@ extern "C" const char *muse_version(void) { return "muse_b200 0.1 (sm_100a)"; }
 // ------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------
+// Everything a batch needs per run whose size follows the store (not the reference): kept in a small
+// per-context pool across muse_batch_create / muse_batch_destroy, because cudaMalloc / cudaFree /
+// cudaHostAlloc of these cost milliseconds to seconds (measured: a NewBatch + Run + destroy cycle per
+// request spent 3 s in cudaFree/cudaFreeHost once in four) while the run itself takes 2.7 ms.
+struct RunScratch {
+    int64_t scratch_cap;
+    double *d_score;
+    int32_t *d_lag;
+    int64_t *d_slot;
+    unsigned long long *d_ckey, *d_skey;
+    int32_t *d_cidx, *d_sidx;
+    int32_t *d_clag, *d_slag;         // 2*lag + sign of the candidates (muse_select.cuh Cand)
+    float *d_U;
+    int32_t *d_list;
+    unsigned char *d_done;
+    float *d_L;                       // lower bounds (grouped screened runs, diagnostic entry point)
+    int64_t d_L_cap;
+    unsigned char *h_pin;             // pinned mailbox for the small device->host results
+    size_t h_pin_bytes;
+    unsigned long long *d_counters;   // [0] ncand, [1] nselected, [2] exact list length, [3] refined
+    SelectState *d_sel;
+    int32_t *d_flag;
+    unsigned *d_cut;                  // fused refinement state: [0] cut bits, [2..3] n_refined (u64), [4..] coarse + fine histogram
+    // group table
+    int64_t table_cap;
+    unsigned long long *d_gmax, *d_hkeys;
+    int32_t *d_gidx;
+};
+
 struct muse_ctx {
     int device;
     int sm_count;
     cudaStream_t stream;       // the stream in use
     cudaStream_t own_stream;   // created with the context
+    std::mutex mu;
+    std::vector<RunScratch> pool;   // scratch sets of destroyed batches, reused by the next muse_batch_create
 };
 
 struct muse_group {
@@ -69,44 +101,21 @@ struct muse_group {
     int64_t flags_cap, flags_upto;
 };
 
-struct muse_batch {
+struct muse_batch : RunScratch {
     muse_ctx *ctx;
     muse_group *g;
     int64_t N, n;
     int log2m;
     double *d_ref;      // padded copy of the reference row
     cd *Xt, *twM, *twn;
-    int32_t *d_flag;
-    // per-run scratch (sized to the group on demand)
-    int64_t scratch_cap;
-    double *d_score;
-    int32_t *d_lag;
-    int64_t *d_slot;
-    unsigned long long *d_ckey, *d_skey;
-    int32_t *d_cidx, *d_sidx;
-    int32_t *d_clag, *d_slag;         // 2*lag + sign of the candidates (muse_select.cuh Cand)
-    unsigned char *h_pin;             // pinned mailbox for the small device->host results
-    size_t h_pin_bytes;
-    unsigned long long *d_counters;   // [0] ncand, [1] nselected
-    SelectState *d_sel;
-    // fp32 screening pass (n = 2048 / 512 ...): tables, bounds, survivor lists
+    // fp32 screening pass (n = 512, 2048 .. 16384): tables
     int screen_ok;
     cf *twp_f, *twn_f;
     float *A_f;
-    float4 *sw_f;          // warp screening kernel: (twn, A[k], A[M-k]) per k < M/2
+    float4 *sw_f;          // fused kernels: (twn, A[k], A[M-k]) per k < M/2
     float a_mid;
     float4 *sx_f;          // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
     cf x_mid;
-    unsigned *d_cut;       // fused refinement state: [0] cut bits, [2..3] n_refined (u64), [4..] coarse + fine histogram
-    float *d_L;            // lower bounds (diagnostic entry point only)
-    int64_t d_L_cap;
-    float *d_U;
-    int32_t *d_list;
-    unsigned char *d_done;
-    // group table
-    int64_t table_cap;
-    unsigned long long *d_gmax, *d_hkeys;
-    int32_t *d_gidx;
     cudaEvent_t ev[4];
     muse_timing timing;
     int fused_run;         // 1: score_fused, 2: score_fused_grouped (d_counters[2] = exact list length, [3] = refined)
@@ -143,9 +152,21 @@ extern "C" int muse_ctx_create(int device, muse_ctx **out) {
     return MUSE_OK;
 }
 
+static void scratch_free(RunScratch &r) {
+    cudaFree(r.d_score); cudaFree(r.d_lag); cudaFree(r.d_slot);
+    cudaFree(r.d_ckey); cudaFree(r.d_skey); cudaFree(r.d_cidx); cudaFree(r.d_sidx);
+    cudaFree(r.d_clag); cudaFree(r.d_slag);
+    cudaFree(r.d_U); cudaFree(r.d_list); cudaFree(r.d_done); cudaFree(r.d_L);
+    cudaFree(r.d_gmax); cudaFree(r.d_hkeys); cudaFree(r.d_gidx);
+    cudaFree(r.d_flag); cudaFree(r.d_counters); cudaFree(r.d_sel); cudaFree(r.d_cut);
+    if (r.h_pin) cudaFreeHost(r.h_pin);
+    memset(&r, 0, sizeof(r));
+}
+
 extern "C" void muse_ctx_destroy(muse_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (RunScratch &r : c->pool) scratch_free(r);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -249,9 +270,14 @@ extern "C" int muse_group_append(muse_group *g, const double *rows, int64_t n_se
     int rc = group_reserve(g, g->size + n_series);
     if (rc != MUSE_OK) return rc;
     cudaStream_t st = g->ctx->stream;
-    CU(cudaMemcpy2DAsync(g->slab + (size_t)g->size * g->ld, sizeof(double) * (size_t)g->ld, rows,
-                         sizeof(double) * (size_t)g->N, sizeof(double) * (size_t)g->N, (size_t)n_series,
-                         cudaMemcpyHostToDevice, st));
+    if (g->ld == g->N) {   // rows are already at the slab's pitch: one flat copy (a pitched copy of 10^6 rows is not always at DMA rate)
+        CU(cudaMemcpyAsync(g->slab + (size_t)g->size * g->ld, rows, sizeof(double) * (size_t)g->N * (size_t)n_series,
+                           cudaMemcpyHostToDevice, st));
+    } else {
+        CU(cudaMemcpy2DAsync(g->slab + (size_t)g->size * g->ld, sizeof(double) * (size_t)g->ld, rows,
+                             sizeof(double) * (size_t)g->N, sizeof(double) * (size_t)g->N, (size_t)n_series,
+                             cudaMemcpyHostToDevice, st));
+    }
     if (g->nkeys > 0) {
         // host [n_series][nkeys] -> device SoA [nkeys][cap]
         std::vector<int32_t> col((size_t)n_series);
@@ -364,6 +390,38 @@ extern "C" int muse_group_append_synthetic(muse_group *g, int64_t n_series, uint
     if (g->nkeys >= 2) g->max_id[1] = std::max<int32_t>(g->max_id[1], (int32_t)std::min<int64_t>(999, first_index + n_series - 1));
     for (int k = 2; k < g->nkeys; k++) g->max_id[k] = std::max(g->max_id[k], 0);
     g->size += n_series;
+    return MUSE_OK;
+}
+
+// label id of key k for global series index i: (i / div[k]) % mod[k]
+__global__ void synth_labels_kernel(int32_t *labels, int64_t cap, int nkeys, int64_t row0, int64_t n_series, int64_t first_index,
+                                    const int64_t d0, const int64_t m0, const int64_t d1, const int64_t m1, const int64_t d2,
+                                    const int64_t m2, const int64_t d3, const int64_t m3) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_series) return;
+    const int64_t gi = first_index + r;
+    const int64_t d[4] = {d0, d1, d2, d3}, m[4] = {m0, m1, m2, m3};
+    for (int k = 0; k < nkeys && k < 4; k++) labels[(size_t)k * cap + row0 + r] = (int32_t)((gi / d[k]) % m[k]);
+}
+
+extern "C" int muse_group_set_synthetic_labels(muse_group *g, const int64_t *div, const int64_t *mod) {
+    if (!g || !div || !mod) return fail(MUSE_ERR_INVALID_ARG, "muse_group_set_synthetic_labels: NULL argument");
+    if (g->nkeys > 4) return fail(MUSE_ERR_UNSUPPORTED, "synthetic labels for at most 4 keys");
+    if (g->size == 0 || g->nkeys == 0) return MUSE_OK;
+    int64_t d[4] = {1, 1, 1, 1}, m[4] = {1, 1, 1, 1};
+    for (int k = 0; k < g->nkeys; k++) {
+        if (div[k] < 1 || mod[k] < 1 || mod[k] > 0x7fffffffLL) return fail(MUSE_ERR_INVALID_ARG, "label divisor / modulus out of range");
+        d[k] = div[k];
+        m[k] = mod[k];
+    }
+    CU(cudaSetDevice(g->ctx->device));
+    synth_labels_kernel<<<(unsigned)((g->size + 255) / 256), 256, 0, g->ctx->stream>>>(g->labels, g->cap, g->nkeys, 0, g->size,
+                                                                                       g->global_offset, d[0], m[0], d[1], m[1],
+                                                                                       d[2], m[2], d[3], m[3]);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(g->ctx->stream));
+    for (int k = 0; k < g->nkeys; k++)      // an upper bound is all the group table needs
+        g->max_id[k] = (int32_t)std::min<int64_t>(m[k] - 1, (g->global_offset + g->size - 1) / d[k]);
     return MUSE_OK;
 }
 
@@ -501,7 +559,6 @@ static int rc_screen_tables(muse_batch *b) {
         b->x_mid = cf{(float)X[(size_t)M / 2].x, (float)X[(size_t)M / 2].y};
         CU(cudaMalloc(&b->sx_f, sizeof(float4) * sx.size()));
         CU(cudaMemcpyAsync(b->sx_f, sx.data(), sizeof(float4) * sx.size(), cudaMemcpyHostToDevice, st));
-        CU(cudaMalloc(&b->d_cut, sizeof(unsigned) * (4 + MUSE_CUT_COARSE + MUSE_CUT_BINS)));
         CU(cudaStreamSynchronize(st));
     }
     CU(cudaMalloc(&b->twp_f, sizeof(cf) * twp.size()));
@@ -546,11 +603,24 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
     });
     CU(cudaMalloc(&b->twM, sizeof(cd) * twM.size()));
     CU(cudaMalloc(&b->twn, sizeof(cd) * (size_t)(M / 2 + 1)));
-    CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
-    CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
-    CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
-    b->h_pin_bytes = (size_t)4 << 20;
-    CU(cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault));
+    {   // scratch of an earlier batch on this context, if there is one (the largest fits most stores)
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!ctx->pool.empty()) {
+            size_t best = 0;
+            for (size_t i = 1; i < ctx->pool.size(); i++)
+                if (ctx->pool[i].scratch_cap > ctx->pool[best].scratch_cap) best = i;
+            static_cast<RunScratch &>(*b) = ctx->pool[best];
+            ctx->pool.erase(ctx->pool.begin() + (long)best);
+        }
+    }
+    if (!b->d_flag) CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
+    if (!b->d_counters) CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
+    if (!b->d_sel) CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
+    if (!b->d_cut) CU(cudaMalloc(&b->d_cut, sizeof(unsigned) * (4 + MUSE_CUT_COARSE + MUSE_CUT_BINS)));
+    if (!b->h_pin) {
+        b->h_pin_bytes = (size_t)4 << 20;
+        CU(cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault));
+    }
     CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
     // twiddle tables, correctly rounded from long double
     std::vector<cd> twn((size_t)(M / 2 + 1));
@@ -598,12 +668,17 @@ static void free_scratch(muse_batch *b) {
 extern "C" void muse_batch_destroy(muse_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    free_scratch(b);
-    cudaFree(b->d_gmax); cudaFree(b->d_hkeys); cudaFree(b->d_gidx);
+    cudaStreamSynchronize(b->ctx->stream);
+    {   // the store-sized scratch goes back to the context (at most 4 sets are kept)
+        std::lock_guard<std::mutex> lk(b->ctx->mu);
+        if (b->ctx->pool.size() < 4) {
+            b->ctx->pool.push_back(static_cast<RunScratch &>(*b));
+            memset(static_cast<RunScratch *>(b), 0, sizeof(RunScratch));
+        }
+    }
+    scratch_free(*b);
     cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
-    cudaFree(b->d_flag); cudaFree(b->d_counters); cudaFree(b->d_sel);
-    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f); cudaFree(b->sw_f); cudaFree(b->sx_f); cudaFree(b->d_cut); cudaFree(b->d_L);
-    if (b->h_pin) cudaFreeHost(b->h_pin);
+    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f); cudaFree(b->sw_f); cudaFree(b->sx_f);
     for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
 }

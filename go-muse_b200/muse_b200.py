@@ -102,6 +102,7 @@ ABI = {
     "muse_group_append": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp]),
     "muse_group_append_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp]),
     "muse_group_append_synthetic": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int64]),
+    "muse_group_set_synthetic_labels": (C.c_int, [_vp, _ip64, _ip64]),
     "muse_synth_row": (None, [C.c_uint64, C.c_int64, C.c_int64, _dp]),
     "muse_synth_reference": (None, [C.c_uint64, C.c_int64, _dp]),
     "muse_group_size": (C.c_int64, [_vp]),
@@ -222,6 +223,13 @@ class DeviceStore:
 
     def append_synthetic(self, n_series: int, seed: int, first_index: int):
         _check(lib().muse_group_append_synthetic(self.h, n_series, seed, first_index))
+
+    def set_synthetic_labels(self, div: Sequence[int], mod: Sequence[int]):
+        """label id of key k for global series index i = (i / div[k]) % mod[k] (call after set_global_offset)."""
+        d = np.asarray(list(div), dtype=np.int64)
+        m = np.asarray(list(mod), dtype=np.int64)
+        assert d.size >= self.n_label_keys and m.size >= self.n_label_keys
+        _check(lib().muse_group_set_synthetic_labels(self.h, d.ctypes.data_as(_ip64), m.ctypes.data_as(_ip64)))
 
     def set_global_offset(self, off: int):
         _check(lib().muse_group_set_global_offset(self.h, off))

@@ -120,6 +120,10 @@ int  muse_group_append_device(muse_group *g, const double *d_rows, int64_t n_ser
  * Label ids: key 0 = i / 1000 ("graph"), key 1 = i % 1000 ("host") when the group has
  * >= 2 label keys. */
 int  muse_group_append_synthetic(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index);
+/* Replace the label ids of every series in the store by the synthetic scheme
+ * id(key k, global index i) = (i / div[k]) % mod[k], i = global offset + local index (benchmarks:
+ * SURVEY section 8d config C4 = {graph: i/10000 % 1000, host: i/100 % 100, colo: i % 100}). */
+int  muse_group_set_synthetic_labels(muse_group *g, const int64_t *div, const int64_t *mod);
 void muse_synth_row(uint64_t seed, int64_t index, int64_t series_len, double *out_row);
 void muse_synth_reference(uint64_t seed, int64_t series_len, double *out_row);
 
