@@ -222,12 +222,13 @@ def main():
     def step():
         if world == 1:
             return batch.run(cols, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
-        parts = batch.run_partial(cols, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
         if grouped:
             # every group representative of the shard, unfiltered (F2); sizes differ per rank
+            parts = batch.run_partial(cols, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
             return mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0)
-        # one small all-gather of fixed-size partial records (top_n per rank), merged on every rank
-        return mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0, fixed_capacity=args.top_n)
+        # the shard's top_n stay on the device, ONE small NCCL all-gather of fixed-size records on the
+        # library's stream, one copy to the host, merge on every rank
+        return mb.allgather_merge_device(batch, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
 
     def barrier():
         if world > 1:
@@ -282,8 +283,7 @@ def main():
             if world == 1:
                 r = b2.run([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)   # Run; results land on the host
             else:
-                parts = b2.run_partial([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)
-                r = mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0, fixed_capacity=args.top_n)
+                r = mb.allgather_merge_device(b2, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
             b2.close()
             return r
 

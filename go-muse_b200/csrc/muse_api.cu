@@ -118,6 +118,7 @@ struct muse_batch : RunScratch {
     cf x_mid;
     cudaEvent_t ev[4];
     muse_timing timing;
+    int timing_pending;    // the last run was queued without a final synchronisation (muse_batch_run_partial_device)
     int fused_run;         // 1: score_fused, 2: score_fused_grouped (d_counters[2] = exact list length, [3] = refined)
 };
 
@@ -1380,6 +1381,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     if (rc) return rc;
     memset(&b->timing, 0, sizeof(b->timing));
     b->fused_run = 0;
+    b->timing_pending = 0;
     cudaStream_t st = b->ctx->stream;
     CU(cudaEventRecord(b->ev[0], st));
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
@@ -1433,6 +1435,8 @@ static int finish_timing(muse_batch *b) {
     return MUSE_OK;
 }
 
+static int queue_topn_records(muse_batch *b, const RunArgs &a, muse_partial *d_out, int64_t capacity);
+
 extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n,
                                  double threshold, int32_t sign_filter, int32_t mode, int32_t signed_scores, double *scores,
                                  int64_t *lags, int64_t *series_idx, int64_t *n_out) {
@@ -1444,6 +1448,51 @@ extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t
     CU(cudaSetDevice(b->ctx->device));
     RunArgs a{key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, signed_scores};
     *n_out = 0;
+    if (n_key_cols == 0 && top_n > 0 && top_n <= 65536 && b->g->size > 0) {
+        // ungrouped: filter and top-N on the device, ONE copy of top_n records to the host
+        rc = ensure_scratch(b);
+        if (rc) return rc;
+        if (top_n * 4 <= b->scratch_cap) {
+            muse_partial *d_rec = reinterpret_cast<muse_partial *>(b->d_skey);      // free scratch in this path
+            rc = queue_topn_records(b, a, d_rec, top_n);
+            if (rc) return rc;
+            cudaStream_t st = b->ctx->stream;
+            const muse_partial *h_rec = reinterpret_cast<const muse_partial *>(b->h_pin + 64);
+            CU(cudaMemcpyAsync(b->h_pin + 64, d_rec, sizeof(muse_partial) * (size_t)top_n, cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(b->ev[3], st));
+            CU(cudaStreamSynchronize(st));
+            if (h_rec[0].flags != 2) {
+                int64_t k = 0;
+                for (; k < top_n && h_rec[k].flags == 0; k++) {
+                    scores[k] = h_rec[k].score;
+                    lags[k] = h_rec[k].lag;
+                    series_idx[k] = h_rec[k].series_idx;
+                }
+                *n_out = k;
+                muse_timing t;
+                return muse_batch_last_timing(b, &t);      // settles timing_pending (events are complete)
+            }
+            // the candidate list was too long for the device-side select (or the fused path's exact launch
+            // did not cover its list): the host path below finishes from the scores already on the device
+            b->timing_pending = 0;
+            const unsigned long long *h_n = reinterpret_cast<const unsigned long long *>(b->h_pin);
+            if (b->fused_run == 1) {
+                rc = run_fused_overflow(b, (int64_t)h_n[2]);
+                if (rc) return rc;
+                b->fused_run = 0;
+            }
+            std::vector<Rec> recs2;
+            rc = run_select(b, a, 1, top_n, recs2);
+            if (rc) return rc;
+            for (size_t i = 0; i < recs2.size(); i++) {
+                scores[i] = recs2[i].score();
+                lags[i] = recs2[i].lag();
+                series_idx[i] = b->g->global_offset + recs2[i].idx;
+            }
+            *n_out = (int64_t)recs2.size();
+            return finish_timing(b);
+        }
+    }
     rc = run_scores(b, a);
     if (rc) return rc;
     std::vector<Rec> recs;
@@ -1473,6 +1522,55 @@ extern "C" int64_t muse_batch_partial_capacity(muse_batch *b, const int32_t *key
     if (!b) return 0;
     if (n_key_cols <= 0) return std::min<int64_t>(std::max<int64_t>(top_n, 0), b->g->size);
     return b->g->size;   // at most one representative per series
+}
+
+// Ungrouped shard partials without a host round trip: scores, filter and the shard's top_n stay on
+// the device; `d_out` (DEVICE memory, `capacity` >= top_n records) is complete when the work queued
+// on the context's stream has run.  Nothing is synchronised here, so a collective enqueued on the
+// same stream (ncclAllGather of the records) follows directly.
+// Queues (no synchronisation): scores, filter, device-side top_n of an UNGROUPED run as muse_partial
+// records in device memory, the counters into the pinned mailbox, and the end-of-run event.
+static int queue_topn_records(muse_batch *b, const RunArgs &a, muse_partial *d_out, int64_t capacity) {
+    static_assert(sizeof(PartialRec) == sizeof(muse_partial), "PartialRec mirrors muse_partial");
+    const int64_t top_n = a.top_n;
+    int rc = run_scores(b, a);
+    if (rc) return rc;
+    const int64_t S = b->g->size;
+    cudaStream_t st = b->ctx->stream;
+    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 2, st));
+    if (S > 0) {
+        FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
+        Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
+        GroupTable gt;
+        memset(&gt, 0, sizeof(gt));
+        emit_candidates_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(gt, nullptr, b->d_score, b->d_lag, S, f, cand);
+        b->timing.n_launches++;
+    }
+    // the grid covers MUSE_PARTIAL_RANK_CAP candidates; blocks past the real count (device side) leave at once
+    const long long exact_bound = b->fused_run == 1 ? (long long)std::min<int64_t>(S, MUSE_EXACT_UB) : -1;
+    const unsigned pblocks = (unsigned)std::min<int64_t>((std::max<int64_t>(S, 1) + 7) / 8, (int64_t)b->ctx->sm_count * 8);   // 8 warps per block, one warp per candidate
+    partial_topn_kernel<<<pblocks, 256, 0, st>>>(b->d_ckey, b->d_cidx, b->d_clag, b->d_counters, (long long)top_n,
+                                                 (long long)b->g->global_offset, exact_bound, reinterpret_cast<PartialRec *>(d_out),
+                                                 (long long)capacity);
+    b->timing.n_launches++;
+    CU(cudaGetLastError());
+    // statistics and the end-of-run event are picked up by muse_batch_last_timing
+    CU(cudaMemcpyAsync(b->h_pin, b->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(b->ev[3], st));
+    b->timing_pending = 1;
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_run_partial_device(muse_batch *b, int64_t max_lag, int64_t top_n, double threshold, int32_t sign_filter,
+                                             int32_t mode, muse_partial *d_out, int64_t capacity) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!d_out || capacity < 1) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_partial_device: no output records");
+    if (top_n < 0) top_n = 0;
+    if (top_n > capacity) return fail(MUSE_ERR_INVALID_ARG, "partial capacity %lld < top_n %lld", (long long)capacity, (long long)top_n);
+    CU(cudaSetDevice(b->ctx->device));
+    RunArgs a{nullptr, 0, max_lag, top_n, threshold, sign_filter, mode, 0};
+    return queue_topn_records(b, a, d_out, capacity);
 }
 
 static int host_keys(muse_batch *b, const RunArgs &a, const std::vector<Rec> &recs, std::vector<uint64_t> &keys) {
@@ -1587,8 +1685,25 @@ extern "C" int muse_merge_partials(const muse_partial *parts, int64_t n_parts, i
     return MUSE_OK;
 }
 
-extern "C" int muse_batch_last_timing(const muse_batch *b, muse_timing *out) {
-    if (!b || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_last_timing: NULL argument");
+extern "C" int muse_batch_last_timing(const muse_batch *cb, muse_timing *out) {
+    if (!cb || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_last_timing: NULL argument");
+    muse_batch *b = const_cast<muse_batch *>(cb);
+    if (b->timing_pending) {     // a device-side run (muse_batch_run_partial_device): finish its bookkeeping now
+        CU(cudaSetDevice(b->ctx->device));
+        CU(cudaEventSynchronize(b->ev[3]));
+        cudaEventElapsedTime(&b->timing.total_ms, b->ev[0], b->ev[3]);
+        cudaEventElapsedTime(&b->timing.score_ms, b->ev[0], b->ev[1]);
+        cudaEventElapsedTime(&b->timing.rescore_ms, b->ev[1], b->ev[2]);
+        cudaEventElapsedTime(&b->timing.select_ms, b->ev[2], b->ev[3]);
+        const unsigned long long *h_n = reinterpret_cast<const unsigned long long *>(b->h_pin);
+        if (b->fused_run) {
+            b->timing.n_rescored = (int64_t)h_n[2];
+            b->timing.n_refined = (int64_t)h_n[3];
+        } else {
+            b->timing.n_rescored = (int64_t)(h_n[2] + h_n[3]);
+        }
+        b->timing_pending = 0;
+    }
     *out = b->timing;
     return MUSE_OK;
 }

@@ -172,6 +172,58 @@ __global__ void emit_candidates_kernel(GroupTable gt, const int64_t *__restrict_
     }
 }
 
+// ---- device-side top-N of a short candidate list, written as muse_partial records ------
+// Rank by counting: candidate i's position in the (|score| desc, index asc) order is the number of
+// candidates that come before it; those with a position < top_n write their own muse_partial
+// record to that slot.  n^2 comparisons spread over the whole GPU (n ~ 4.5 k at C3: ~10 us; a
+// one-block bitonic sort of the same list took 180 us).  Slots min(n, top_n) .. capacity-1 are
+// padded with flags = 1 (ignored by the merge).  A multi-GPU step can then all-gather the records
+// straight from device memory: no host round trip between the scores and the collective.
+// flags = 2 in record 0 tells the caller that the list was too long for this kernel (or that the
+// fused path's exact launch did not cover its list): it then takes the host path.
+#define MUSE_PARTIAL_RANK_CAP 32768
+struct PartialRec {           // == muse_partial (include/muse_b200.h)
+    unsigned long long group_key;
+    double score;
+    long long series_idx;
+    int lag;
+    int flags;
+};
+
+__global__ void __launch_bounds__(256)
+partial_topn_kernel(const unsigned long long *__restrict__ ckey, const int32_t *__restrict__ cidx,
+                    const int32_t *__restrict__ clag, const unsigned long long *__restrict__ counters, long long top_n,
+                    long long global_offset, long long exact_list_bound, PartialRec *__restrict__ out, long long capacity) {
+    const unsigned long long n = counters[0];
+    const bool overflow = n > MUSE_PARTIAL_RANK_CAP || (exact_list_bound >= 0 && counters[2] > (unsigned long long)exact_list_bound);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long take = overflow ? 0 : ((long long)n < top_n ? (long long)n : top_n);
+    // padding (and the overflow signal) by the first threads of the grid
+    for (long long r = take + gtid; r < capacity; r += (long long)gridDim.x * blockDim.x)
+        out[r] = PartialRec{0ull, 0.0, 0ll, 0, (overflow && r == 0) ? 2 : 1};
+    if (overflow) return;
+    // one warp per candidate; its lanes stride over the list (54 KB at C3: L1/L2 resident)
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long i = (unsigned long long)gtid >> 5; i < n; i += nwarps) {
+        const unsigned long long k = ckey[i];
+        const unsigned ix = (unsigned)cidx[i];
+        unsigned before = 0;
+        for (unsigned long long j = lane; j < n; j += 32) {
+            const unsigned long long kj = ckey[j];
+            before += (kj > k || (kj == k && (unsigned)cidx[j] < ix)) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
+        if (lane == 0 && (long long)before < top_n) {
+            const int ls = clag[i];
+            const double a = __longlong_as_double((long long)k);
+            const long long gi = global_offset + (long long)ix;
+            out[before] = PartialRec{(unsigned long long)gi, (ls & 1) ? -a : a, gi, (ls - (ls & 1)) / 2, 0};
+        }
+    }
+}
+
 // ---- radix select of the top_n candidates by (key desc, idx asc) ---------------------
 // 96-bit composite (key, ~idx) examined 16 bits at a time, most significant first.
 // State lives on the device; round r narrows [prefix] and the remaining rank.

@@ -123,6 +123,7 @@ ABI = {
     "muse_batch_screen_bounds": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, _vp]),
     "muse_batch_run_partial": (C.c_int, [_vp, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                          C.c_int32, _vp, C.c_int64, _ip64]),
+    "muse_batch_run_partial_device": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32, _vp, C.c_int64]),
     "muse_batch_partial_capacity": (C.c_int64, [_vp, _ip32, C.c_int32, C.c_int64]),
     "muse_merge_partials": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                       _dp, _ip64, _ip64, _ip64]),
@@ -339,6 +340,13 @@ class DeviceBatch:
         _check(lib().muse_batch_run_partial(self.h, kcp, kc.size, max_lag, top_n, threshold, sign_filter, mode,
                                             out.ctypes.data_as(_vp), cap, C.byref(n_out)))
         return out[:int(n_out.value)]
+
+    def run_partial_device(self, max_lag: int, top_n: int, threshold: float, sign_filter: int, mode: int,
+                           d_out_ptr: int, capacity: int):
+        """Ungrouped shard partials written to DEVICE memory at d_out_ptr (capacity records of 32 bytes) by work
+        queued on the context's stream; nothing is synchronised (see muse_batch_run_partial_device)."""
+        _check(lib().muse_batch_run_partial_device(self.h, max_lag, top_n, threshold, sign_filter, mode,
+                                                   _vp(d_out_ptr), capacity))
 
     def timing(self) -> Timing:
         t = Timing()
@@ -706,4 +714,37 @@ def allgather_merge(parts: np.ndarray, max_lag: int, top_n: int, threshold: floa
     out = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(out, t)
     allp = out.cpu().numpy().view(PARTIAL_DTYPE)
+    return merge_partials(allp, max_lag, top_n, threshold, sign_filter)
+
+
+_gather_buffers: Dict[Tuple[int, int, int], tuple] = {}
+
+
+def allgather_merge_device(batch: DeviceBatch, max_lag: int, top_n: int, threshold: float, sign_filter: int = 0,
+                           mode: int = MODE_AUTO):
+    """One multi-GPU step of an UNGROUPED run with the partials kept on the device: the shard's top_n
+    records are written by the library on the context's stream (which must be torch's current stream:
+    Context.set_stream), all-gathered by NCCL on that same stream, copied to the host once and merged
+    (muse_merge_partials).  Falls back to the host path when the device-side select reports an overflow."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    dev = torch.cuda.current_device()
+    cap = max(1, int(top_n))
+    key = (dev, world, cap)
+    if key not in _gather_buffers:
+        t = torch.empty(cap * PARTIAL_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        out = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
+        host = torch.empty(world * t.numel(), dtype=torch.uint8, pin_memory=True)
+        _gather_buffers[key] = (t, out, host)
+    t, out, host = _gather_buffers[key]
+    batch.run_partial_device(max_lag, top_n, threshold, sign_filter, mode, t.data_ptr(), cap)
+    dist.all_gather_into_tensor(out, t)
+    host.copy_(out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    allp = host.numpy().view(PARTIAL_DTYPE)
+    if np.any(allp["flags"] == 2):      # some shard's candidate list did not fit the device-side select
+        parts = batch.run_partial([], max_lag, top_n, threshold, sign_filter, mode=mode)
+        return allgather_merge(parts, max_lag, top_n, threshold, sign_filter, fixed_capacity=top_n)
     return merge_partials(allp, max_lag, top_n, threshold, sign_filter)

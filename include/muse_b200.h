@@ -198,6 +198,14 @@ int  muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, int32_t *s
 int  muse_batch_run_partial(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
                             int64_t max_lag, int64_t top_n, double threshold, int32_t sign_filter,
                             int32_t mode, muse_partial *out, int64_t capacity, int64_t *n_out);
+/* Ungrouped shard partials WITHOUT a host round trip: the shard's filtered top_n are written to
+ * d_out in DEVICE memory (capacity >= top_n records; the rest padded with flags = 1) by work queued
+ * on the context's stream; the call does not synchronise, so an all-gather of the records enqueued
+ * on the same stream (muse_ctx_set_stream) follows directly and muse_merge_partials runs on the
+ * gathered host copy.  flags == 2 in record 0: the candidate list was too long for the device-side
+ * select -- call muse_batch_run_partial instead.  Timings: muse_batch_last_timing. */
+int  muse_batch_run_partial_device(muse_batch *b, int64_t max_lag, int64_t top_n, double threshold,
+                                   int32_t sign_filter, int32_t mode, muse_partial *d_out, int64_t capacity);
 /* Upper bound on the records run_partial can emit for these arguments. */
 int64_t muse_batch_partial_capacity(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
                                     int64_t top_n);

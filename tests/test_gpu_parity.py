@@ -315,6 +315,35 @@ def test_sharded_partials_merge_equals_single_store(ctx):
             np.testing.assert_array_equal(sc, wsc)
 
 
+def test_device_side_partials_equal_host_partials(ctx):
+    # muse_batch_run_partial_device: the shard's filtered top_n written to device memory == run_partial's records
+    import torch
+    rng = np.random.default_rng(29)
+    for S, N in ((3000, 256), (40_000, 1440)):
+        ref, Y = _siggen(rng, S, N)
+        Y[5] = Y[4]                                  # an exact tie: lowest index first
+        st = mb.DeviceStore(ctx, N, 0, S)
+        st.append(Y)
+        st.set_global_offset(1_000_000)
+        b = mb.DeviceBatch(ctx, st, ref)
+        for max_lag, top_n, thr in ((20, 10, 0.0), (128, 100, 0.3), (N, 500, 0.0)):
+            want = b.run_partial([], max_lag, top_n, thr)
+            t = torch.zeros(top_n * 32, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            b.run_partial_device(max_lag, top_n, thr, 0, mb.MODE_AUTO, t.data_ptr(), top_n)
+            ctx.synchronize()
+            got = t.cpu().numpy().view(mb.PARTIAL_DTYPE)
+            if np.any(got["flags"] == 2):            # more than 32768 passing candidates: the documented overflow signal
+                assert thr == 0.0 and max_lag == N
+                continue
+            k = len(want)
+            np.testing.assert_array_equal(got[:k], want)
+            assert np.all(got["flags"][k:] == 1)
+            tm = b.timing()
+            assert tm.total_ms > 0 and tm.n_launches >= 2
+        b.close()
+
+
 def test_c_oracle_agrees_at_larger_size(ctx):
     # the fast C oracle as checker at a size the numpy form would take long on
     rng = np.random.default_rng(23)
