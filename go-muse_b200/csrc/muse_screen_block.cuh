@@ -41,6 +41,14 @@ struct ScreenBlockCfg {
 
 #if defined(__CUDACC__)
 
+// 16-byte table entry that must not displace the per-pass twiddles from L1: the split tables (64 KB
+// each at n = 16384) are read once per series per thread, the twiddles 62 times
+__device__ __forceinline__ float4 load_f4_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ void l2_prefetch(const void *p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -98,16 +106,46 @@ __device__ __forceinline__ float2 block_max_f2(float a, float b, float2 *red, in
 // Forward FFT_M of the 32 points per thread in v (input j of thread t = element t + T*j); on return
 // v[c*R_LAST + Perm<R_LAST>(j)] = Z[(t + c*T) + (j << 10)].  Ends WITHOUT a barrier after the last
 // pass' loads: the caller synchronises before it writes the exchange buffer again.
+//
+// Same passes as fft_pass_compute_store / fft_pass_load of muse_fft.cuh for Geo<LOG2M, 5>, with the
+// padded shared-memory indices written out as (per-thread base) + (compile-time offset): T is a
+// multiple of 32, so pad(t + T*x) = pad(t) + (T + T/32)*x and pad(q + 1024*p + 32*j) = q + 1056*p + 33*j.
+// (The generic index arithmetic was 20 % of the kernel's instructions.)
 template <int LOG2M>
 __device__ __forceinline__ void block_fft(cf *v, cf *sm, int t, const cf *twp) {
     using C = ScreenBlockCfg<LOG2M>;
-    fft_pass_compute_store<LOG2M, 5, 0, float, cf>(v, sm, t, twp);
+    using G = typename C::G;
+    constexpr int T = C::T, TP = T + T / 32;              // pad(t + T*x) = pad(t) + TP*x
+    const int pt = t + (t >> 5);                            // pad(t)
+    // pass 0: radix 32 over elements t + T*j, twiddle W_M^(j*t), scatter to 32*t + j
+    Dft<32, float>::run(v);
+    {
+        cf *dst = sm + 33 * t;
+        const cf *tw = twp + t;                             // row j-1, column t of the pass-0 table (T columns)
+        dst[0] = v[Perm<32>::at(0)];
+#pragma unroll
+        for (int j = 1; j < 32; j++) dst[j] = cmul(v[Perm<32>::at(j)], tw[(j - 1) * T]);
+    }
     __syncthreads();
-    fft_pass_load<LOG2M, 5, 1, float>(v, sm, t);
+    // pass 1: butterfly b = t: p = t >> 5, q = t & 31; inputs t + T*j; twiddle W_T^(j*p); scatter to q + 1024*p + 32*j
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = sm[pt + TP * j];
     __syncthreads();
-    fft_pass_compute_store<LOG2M, 5, 1, float, cf>(v, sm, t, twp);
+    Dft<32, float>::run(v);
+    {
+        const int p = t >> 5, q = t & 31;
+        cf *dst = sm + q + 1056 * p;
+        const cf *tw = twp + G::tw_off(1) + p;              // row j-1, column p of the pass-1 table (T/32 columns)
+        dst[0] = v[Perm<32>::at(0)];
+#pragma unroll
+        for (int j = 1; j < 32; j++) dst[33 * j] = cmul(v[Perm<32>::at(j)], tw[(j - 1) * (T / 32)]);
+    }
     __syncthreads();
-    fft_pass_load<LOG2M, 5, 2, float>(v, sm, t);
+    // last pass: NB_LAST butterflies of radix R_LAST per thread, b = t + c*T, inputs b + (j << 10); no twiddles
+#pragma unroll
+    for (int c = 0; c < C::NB_LAST; c++)
+#pragma unroll
+        for (int j = 0; j < C::R_LAST; j++) v[c * C::R_LAST + j] = sm[pt + TP * c + 1056 * j];
 #pragma unroll
     for (int c = 0; c < C::NB_LAST; c++) Dft<C::R_LAST, float>::run(v + c * C::R_LAST);
 }
@@ -125,6 +163,9 @@ score_screen_block_kernel(const ScreenParams prm) {
     cf *sm = reinterpret_cast<cf *>(smem_raw);
 
     const int t = threadIdx.x;
+    constexpr int TP = T + T / 32;                      // pad(t + T*x) = pad(t) + TP*x (T is a multiple of 32)
+    const int pt = t + (t >> 5);                        // pad(t)
+    const int pm = M + M / 32 - t - ((t + 31) >> 5);    // pad(M - t) for t >= 1 (t = 0 pairs bin 0 with itself)
     const int N = prm.N;
     const int Nh = N >> 1;
     const int nz = (Nh + T - 1) / T;                 // rows of T complex slots that hold samples
@@ -140,25 +181,31 @@ score_screen_block_kernel(const ScreenParams prm) {
             flag_raw = prm.row_flags[pos];
         }
 
-        // ---- pivot = mean of the first 2T samples (fp64) ----
-        const cd first = load_pair_stream(rowp + 2 * t);           // Nh > M/2 >= T: always a sample
-        const double pivot = block_sum_d<NW>(first.x + first.y, red_d, t) / (double)(2 * T);
-
-        // ---- (y - pivot) -> fp32 registers, fp64 sum of (y - pivot) ----
+        // ---- (y - pivot) -> fp32 registers, fp64 sum of (y - pivot); pivot = fp64 mean of the first 2T
+        //      samples.  Loads go out in batches of 8 rows (8 x 16 bytes in flight per thread) ahead of
+        //      their use; the first batch is issued before the pivot's block reduction ----
         cf v[P];
-        double s0 = 0.0, s1 = 0.0;
+        double s0 = 0.0, s1 = 0.0, pivot = 0.0;
 #pragma unroll
-        for (int r = 0; r < P; r++) {
-            v[r] = cf{0.f, 0.f};
-            if (r < nz) {
-                const int j = t + r * T;
+        for (int b0 = 0; b0 < P; b0 += 8) {
+            cd x[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int j = t + (b0 + q) * T;
+                x[q] = j < Nh ? load_pair_stream(rowp + 2 * j) : cd{0.0, 0.0};
+            }
+            if (b0 == 0) pivot = block_sum_d<NW>(x[0].x + x[0].y, red_d, t) / (double)(2 * T);   // Nh > M/2 >= T: row 0 is all samples
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int j = t + (b0 + q) * T;
+                cf val{0.f, 0.f};
                 if (j < Nh) {
-                    const cd x = r == 0 ? first : load_pair_stream(rowp + 2 * j);
-                    const double dx = x.x - pivot, dy = x.y - pivot;
+                    const double dx = x[q].x - pivot, dy = x[q].y - pivot;
                     s0 += dx;
                     s1 += dy;
-                    v[r] = cf{(float)dx, (float)dy};
+                    val = cf{(float)dx, (float)dy};
                 }
+                v[b0 + q] = val;
             }
         }
         const double dmean = block_sum_d<NW>(s0 + s1, red_d, t) / (double)N;   // mean - pivot
@@ -179,17 +226,21 @@ score_screen_block_kernel(const ScreenParams prm) {
         for (int c = 0; c < C::NB_LAST; c++)
 #pragma unroll
             for (int j = 0; j < C::R_LAST; j++)
-                sm[G::pad((t + c * T) + (j << C::LS_LAST))] = v[c * C::R_LAST + Perm<C::R_LAST>::at(j)];
+                sm[pt + TP * c + 1056 * j] = v[c * C::R_LAST + Perm<C::R_LAST>::at(j)];      // pad((t + c*T) + (j << 10))
         __syncthreads();
 
         // ---- |2Y_k| and |2Y_(M-k)| for k = t + T*i < M/2 (k = 0 pairs with itself: DC and Nyquist) ----
+        // (the 16 table entries are fetched up front: consumed one by one in a rolled loop, each multiply
+        //  waited for its own L2 round trip -- 9 % of all stall samples)
+        float4 swr[P / 2];
+#pragma unroll
+        for (int i = 0; i < P / 2; i++) swr[i] = load_f4_stream(prm.sw + t + T * i);    // (w_k.x, w_k.y, A[k], A[M-k])
         cf acc2{0.f, 0.f};
-#pragma unroll 4
+#pragma unroll
         for (int i = 0; i < P / 2; i++) {
-            const int k = t + T * i;
-            const cf zk = sm[G::pad(k)];
-            const cf zm = sm[G::pad((M - k) & (M - 1))];
-            const float4 s = prm.sw[k];                            // (w_k.x, w_k.y, A[k], A[M-k])
+            const cf zk = sm[pt + TP * i];                             // pad(k)
+            const cf zm = sm[(i == 0 && t == 0) ? 0 : pm - TP * i];    // pad(M - k)
+            const float4 s = swr[i];
             const cf zmc = cconj(zm);
             const cf e = cadd(zk, zmc);
             const cf o = cmul_negi(csub(zk, zmc));
@@ -222,18 +273,21 @@ score_screen_block_kernel(const ScreenParams prm) {
         float L = -1.f;
         if (U >= cut_now && U < 1.5f) {                            // block-uniform
             // ---- conj(Y)*X on the mirror pairs, in place in shared memory (each pair has one owner) ----
-#pragma unroll 2
+            float4 sxr[P / 2];
+#pragma unroll
+            for (int i = 0; i < P / 2; i++) sxr[i] = load_f4_stream(prm.sx + t + T * i);
+#pragma unroll
             for (int i = 0; i < P / 2; i++) {
-                const int k = t + T * i;
-                const int m = (M - k) & (M - 1);
-                const cf zk = sm[G::pad(k)];
-                const cf zm = sm[G::pad(m)];
-                const float4 s = prm.sw[k];
-                const float4 x = prm.sx[k];
+                const int ik = pt + TP * i;                            // pad(k), k = t + T*i
+                const int im = (i == 0 && t == 0) ? 0 : pm - TP * i;   // pad(M - k)
+                const cf zk = sm[ik];
+                const cf zm = sm[im];
+                const float4 s = swr[i];
+                const float4 x = sxr[i];
                 cf ok, om;
                 pointwise_pair(zk, zm, cf{s.x, s.y}, cf{x.x, x.y}, cf{x.z, x.w}, ok, om);
-                sm[G::pad(m)] = om;
-                sm[G::pad(k)] = ok;                                // k == m (k = 0): ok wins, as pointwise_phase
+                sm[im] = om;
+                sm[ik] = ok;                                           // k == M - k (k = 0): ok wins, as pointwise_phase
             }
             if (t == 0) {                                          // k = M/2; w = exp(-i*pi/2) = -i
                 const cf mid = sm[G::pad(M / 2)];
@@ -244,7 +298,7 @@ score_screen_block_kernel(const ScreenParams prm) {
             __syncthreads();
             // ---- inverse FFT_M as swap(FFT(swap(.))) ----
 #pragma unroll
-            for (int j = 0; j < P; j++) v[j] = sm[G::pad(t + T * j)];
+            for (int j = 0; j < P; j++) v[j] = sm[pt + TP * j];
             __syncthreads();
             block_fft<LOG2M>(v, sm, t, prm.twp);
             // v[c*R + Perm(j)] = (cc'[2k+1], cc'[2k]), k = (t + c*T) + (j << 10); cc' = std * cc rotated by pad
