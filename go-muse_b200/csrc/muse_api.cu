@@ -63,7 +63,6 @@ struct RunScratch {
     int32_t *d_clag, *d_slag;         // 2*lag + sign of the candidates (muse_select.cuh Cand)
     float *d_U;
     int32_t *d_list;
-    unsigned char *d_done;
     float *d_L;                       // lower bounds (grouped screened runs, diagnostic entry point)
     int64_t d_L_cap;
     unsigned char *h_pin;             // pinned mailbox for the small device->host results
@@ -110,8 +109,7 @@ struct muse_batch : RunScratch {
     cd *Xt, *twM, *twn;
     // fp32 screening pass (n = 512, 2048 .. 16384): tables
     int screen_ok;
-    cf *twp_f, *twn_f;
-    float *A_f;
+    cf *twp_f;
     float4 *sw_f;          // fused kernels: (twn, A[k], A[M-k]) per k < M/2
     float a_mid;
     float4 *sx_f;          // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
@@ -157,7 +155,7 @@ static void scratch_free(RunScratch &r) {
     cudaFree(r.d_score); cudaFree(r.d_lag); cudaFree(r.d_slot);
     cudaFree(r.d_ckey); cudaFree(r.d_skey); cudaFree(r.d_cidx); cudaFree(r.d_sidx);
     cudaFree(r.d_clag); cudaFree(r.d_slag);
-    cudaFree(r.d_U); cudaFree(r.d_list); cudaFree(r.d_done); cudaFree(r.d_L);
+    cudaFree(r.d_U); cudaFree(r.d_list); cudaFree(r.d_L);
     cudaFree(r.d_gmax); cudaFree(r.d_hkeys); cudaFree(r.d_gidx);
     cudaFree(r.d_flag); cudaFree(r.d_counters); cudaFree(r.d_sel); cudaFree(r.d_cut);
     if (r.h_pin) cudaFreeHost(r.h_pin);
@@ -522,52 +520,48 @@ static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 
 }
 
 // fp32 tables of the screening kernel; leaves screen_ok = 0 when the shape has no screening kernel
-static int screen_log2m_supported(int log2m) { return log2m == 8 || (log2m >= 10 && log2m <= 13); }
-// n >= 2048: kernels with the fused fp32 second stage (warp kernel at 2048, block kernel above)
-static int screen_is_fused(int log2m) { return log2m >= 10 && log2m <= 13; }
+// n = 512 .. 16384: kernels with the fused fp32 second stage (warp kernel at 2048, block kernel elsewhere)
+static int screen_is_fused(int log2m) { return log2m >= 8 && log2m <= 13; }
+static int screen_log2m_supported(int log2m) { return screen_is_fused(log2m); }
+static int screen_log2p(int log2m) { return log2m >= 10 ? 5 : (log2m == 9 ? 4 : 3); }
 
 static int rc_screen_tables(muse_batch *b) {
     b->screen_ok = 0;
     if (!screen_log2m_supported(b->log2m) || (b->N & 1)) return MUSE_OK;
     const int64_t M = b->n / 2;
-    const int log2p = b->log2m == 8 ? 4 : 5;
+    const int log2p = screen_log2p(b->log2m);
     cudaStream_t st = b->ctx->stream;
     const long double PI2 = 6.283185307179586476925286766559005768L;
-    std::vector<cf> twp((size_t)M + 64), twn((size_t)M);
+    std::vector<cf> twp((size_t)M + 64);
     fill_pass_twiddles(b->log2m, log2p, twp.data(), [&](long long num, long long den) {
         return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
     });
-    for (int64_t k = 0; k < M; k++) twn[(size_t)k] = cf{(float)cosl(-PI2 * k / b->n), (float)sinl(-PI2 * k / b->n)};
     std::vector<cd> X((size_t)M + 1);
     CU(cudaMemcpyAsync(X.data(), b->Xt, sizeof(cd) * (size_t)(M + 1), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    // weights of the bound: A[k] = |Xt[k]| * (1 at DC and Nyquist, else 2), rounded UP (the bound must not shrink)
     std::vector<float> A((size_t)M + 1);
     for (int64_t k = 0; k <= M; k++) {
         const double a = hypot(X[(size_t)k].x, X[(size_t)k].y) * ((k == 0 || k == M) ? 1.0 : 2.0);
         float f = (float)a;
-        if ((double)f < a) f = nextafterf(f, INFINITY);   // round up: the bound must not shrink
+        if ((double)f < a) f = nextafterf(f, INFINITY);
         A[(size_t)k] = f;
     }
-    if (screen_is_fused(b->log2m)) {   // split twiddle and the two mirror weights in one 16-byte entry
-        std::vector<float4> sw((size_t)M / 2);
-        for (int64_t k = 0; k < M / 2; k++) sw[(size_t)k] = make_float4(twn[(size_t)k].x, twn[(size_t)k].y, A[(size_t)k], A[(size_t)(M - k)]);
-        CU(cudaMalloc(&b->sw_f, sizeof(float4) * sw.size()));
-        CU(cudaMemcpyAsync(b->sw_f, sw.data(), sizeof(float4) * sw.size(), cudaMemcpyHostToDevice, st));
-        b->a_mid = A[(size_t)M / 2];
-        std::vector<float4> sx((size_t)M / 2);
-        for (int64_t k = 0; k < M / 2; k++)
-            sx[(size_t)k] = make_float4((float)X[(size_t)k].x, (float)X[(size_t)k].y, (float)X[(size_t)(M - k)].x, (float)X[(size_t)(M - k)].y);
-        b->x_mid = cf{(float)X[(size_t)M / 2].x, (float)X[(size_t)M / 2].y};
-        CU(cudaMalloc(&b->sx_f, sizeof(float4) * sx.size()));
-        CU(cudaMemcpyAsync(b->sx_f, sx.data(), sizeof(float4) * sx.size(), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));
+    // one 16-byte entry per mirror pair (k, M-k), k < M/2: the split twiddle exp(-2*pi*i*k/n) with the two
+    // weights, and the two reference coefficients of the second stage
+    std::vector<float4> sw((size_t)M / 2), sx((size_t)M / 2);
+    for (int64_t k = 0; k < M / 2; k++) {
+        sw[(size_t)k] = make_float4((float)cosl(-PI2 * k / b->n), (float)sinl(-PI2 * k / b->n), A[(size_t)k], A[(size_t)(M - k)]);
+        sx[(size_t)k] = make_float4((float)X[(size_t)k].x, (float)X[(size_t)k].y, (float)X[(size_t)(M - k)].x, (float)X[(size_t)(M - k)].y);
     }
+    b->a_mid = A[(size_t)M / 2];
+    b->x_mid = cf{(float)X[(size_t)M / 2].x, (float)X[(size_t)M / 2].y};
+    CU(cudaMalloc(&b->sw_f, sizeof(float4) * sw.size()));
+    CU(cudaMalloc(&b->sx_f, sizeof(float4) * sx.size()));
     CU(cudaMalloc(&b->twp_f, sizeof(cf) * twp.size()));
-    CU(cudaMalloc(&b->twn_f, sizeof(cf) * twn.size()));
-    CU(cudaMalloc(&b->A_f, sizeof(float) * A.size()));
+    CU(cudaMemcpyAsync(b->sw_f, sw.data(), sizeof(float4) * sw.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->sx_f, sx.data(), sizeof(float4) * sx.size(), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b->twp_f, twp.data(), sizeof(cf) * twp.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->twn_f, twn.data(), sizeof(cf) * twn.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->A_f, A.data(), sizeof(float) * A.size(), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));
     b->screen_ok = 1;
     return MUSE_OK;
@@ -659,8 +653,8 @@ static void free_scratch(muse_batch *b) {
     cudaFree(b->d_ckey); cudaFree(b->d_skey); cudaFree(b->d_cidx); cudaFree(b->d_sidx);
     cudaFree(b->d_clag); cudaFree(b->d_slag);
     b->d_clag = b->d_slag = nullptr;
-    cudaFree(b->d_U); cudaFree(b->d_list); cudaFree(b->d_done);
-    b->d_U = nullptr; b->d_list = nullptr; b->d_done = nullptr;
+    cudaFree(b->d_U); cudaFree(b->d_list);
+    b->d_U = nullptr; b->d_list = nullptr;
     b->d_score = nullptr; b->d_lag = nullptr; b->d_slot = nullptr;
     b->d_ckey = b->d_skey = nullptr; b->d_cidx = b->d_sidx = nullptr;
     b->scratch_cap = 0;
@@ -679,7 +673,7 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
     }
     scratch_free(*b);
     cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
-    cudaFree(b->twp_f); cudaFree(b->twn_f); cudaFree(b->A_f); cudaFree(b->sw_f); cudaFree(b->sx_f);
+    cudaFree(b->twp_f); cudaFree(b->sw_f); cudaFree(b->sx_f);
     for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
 }
@@ -702,7 +696,6 @@ static int ensure_scratch(muse_batch *b) {
     CU(cudaMalloc(&b->d_slag, sizeof(int32_t) * (size_t)cap));
     CU(cudaMalloc(&b->d_U, sizeof(float) * (size_t)cap));
     CU(cudaMalloc(&b->d_list, sizeof(int32_t) * (size_t)cap));
-    CU(cudaMalloc(&b->d_done, (size_t)cap));
     b->scratch_cap = cap;
     return MUSE_OK;
 }
@@ -954,29 +947,6 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
     return MUSE_OK;
 }
 
-__global__ void gather_scores_kernel(const int32_t *__restrict__ idx, const unsigned long long *__restrict__ n,
-                                     const double *__restrict__ score, const int32_t *__restrict__ lag,
-                                     double *__restrict__ out_s, int32_t *__restrict__ out_l) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < *n) {
-        out_s[i] = score[idx[i]];
-        out_l[i] = lag[idx[i]];
-    }
-}
-
-template <int LOG2M>
-static cudaError_t launch_screen_t(const ScreenParams &p, cudaStream_t st) {
-    using C = ScreenCfg<LOG2M>;
-    auto kern = score_screen_kernel<LOG2M, 4>;
-    if (C::SMEM > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return e;
-    }
-    const int64_t blocks = (p.count + C::SPB - 1) / C::SPB;
-    kern<<<(unsigned)blocks, C::TB, C::SMEM, st>>>(p);
-    return cudaGetLastError();
-}
-
 template <int NZ>
 static cudaError_t launch_screen_warp_nz(const ScreenParams &p, int sm_count, cudaStream_t st) {
     using C = ScreenWarpCfg;
@@ -1025,7 +995,8 @@ static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cud
         case 12: return launch_screen_block<12, 4>(p, b->ctx->sm_count, st);
         case 11: return launch_screen_block<11, 8>(p, b->ctx->sm_count, st);
         case 10: return launch_screen_warp(p, b->ctx->sm_count, st);
-        case 8: return launch_screen_t<8>(p, st);
+        case 9: return launch_screen_block<9, 16>(p, b->ctx->sm_count, st);
+        case 8: return launch_screen_block<8, 16>(p, b->ctx->sm_count, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -1068,8 +1039,6 @@ static ScreenParams screen_params(muse_batch *b) {
     sp.count = b->g->size;
     sp.N = (int)b->N;
     sp.twp = b->twp_f;
-    sp.twn = b->twn_f;
-    sp.A = b->A_f;
     sp.sw = b->sw_f;
     sp.a_mid = b->a_mid;
     sp.out_U = b->d_U;
@@ -1112,23 +1081,6 @@ static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t m
     return MUSE_OK;
 }
 
-// idx list of every series with lo <= U (and not yet exact-scored); marks them done
-__global__ void survivors_kernel(const float *__restrict__ U, int64_t S, float lo, unsigned char *done,
-                                 int32_t *__restrict__ out, unsigned long long *n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool take = i < S && !done[i] && U[i] >= lo;
-    const unsigned mask = __ballot_sync(0xffffffffu, take);
-    if (mask == 0u) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(n, (unsigned long long)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (take) {
-        out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
-        done[i] = 1;
-    }
-}
-
 // idx list of every series whose (refined) bound reaches the final cut-off, read from device memory
 __global__ void survivors_cut_kernel(const float *__restrict__ U, int64_t S, const unsigned *__restrict__ cut_bits,
                                      int32_t *__restrict__ out, unsigned long long *n) {
@@ -1142,137 +1094,6 @@ __global__ void survivors_cut_kernel(const float *__restrict__ U, int64_t S, con
     if (lane == leader) base = atomicAdd(n, (unsigned long long)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (take) out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
-}
-
-// candidates for the pilot: (U bits << 32, idx) of every series with U >= lo
-__global__ void pilot_candidates_kernel(const float *__restrict__ U, int64_t S, float lo, Cand out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool take = i < S && U[i] >= lo;
-    const unsigned mask = __ballot_sync(0xffffffffu, take);
-    if (mask == 0u) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(out.n, (unsigned long long)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (take) {
-        const unsigned long long pos = base + __popc(mask & ((1u << lane) - 1u));
-        out.key[pos] = ((unsigned long long)__float_as_uint(U[i])) << 32;   // U >= 0: bits order like values
-        out.idx[pos] = (int32_t)i;
-    }
-}
-
-__global__ void mark_done_kernel(const int32_t *__restrict__ idx, unsigned long long n, unsigned char *done) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) done[idx[i]] = 1;
-}
-
-// Screened scoring (ungrouped runs).  Every series gets the fp32 upper bound U; series that can
-// still reach the top_n cut-off are re-scored by the exact fp64 kernel; everything else keeps a
-// NaN score, which the selection stage ignores.  The result of the run is identical to
-// score_exact_all + selection:
-//   1. pilot: the ~K series with the largest U (U >= threshold) are scored exactly; the top_n-th
-//      best PASSING exact score among them is a valid lower bound `cut` on the final cut-off
-//      (threshold if fewer than top_n pass);
-//   2. every other series with U >= cut is scored exactly; a series with U < cut has an exact
-//      score < cut and cannot be among the top_n.
-// Two host round trips (histogram of U; exact scores of the pilot); the list lengths stay on the
-// device and the exact kernel is launched over an upper bound taken from the histogram.
-static int score_screened(muse_batch *b, const RunArgs &a, bool *fell_back) {
-    muse_group *g = b->g;
-    const int64_t S = g->size;
-    cudaStream_t st = b->ctx->stream;
-    *fell_back = false;
-    ScreenParams sp = screen_params(b);
-    CU(launch_screen(b, sp, st));
-    b->timing.n_launches++;
-    CU(cudaEventRecord(b->ev[1], st));
-    // scores default to NaN (= "cannot be in the result"), nothing exact-scored yet
-    CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));
-    CU(cudaMemsetAsync(b->d_done, 0, (size_t)S, st));
-    const unsigned blocks = (unsigned)((S + 255) / 256);
-    const float thr_lo = a.threshold > 0 ? (float)a.threshold * 0.999999f : 0.f;   // never above the fp64 threshold
-    // ---- histogram of the bounds ----
-    unsigned int *d_hist = reinterpret_cast<unsigned int *>(b->d_ckey);   // 8 KB of free scratch
-    CU(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * MUSE_U_BINS, st));
-    u_hist_kernel<<<(unsigned)std::min<int64_t>(blocks, (int64_t)b->ctx->sm_count * 8), 256, 0, st>>>(b->d_U, S, d_hist);
-    b->timing.n_launches++;
-    CU(cudaMemcpyAsync(b->h_pin, d_hist, sizeof(unsigned int) * MUSE_U_BINS, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    std::vector<unsigned int> hist(MUSE_U_BINS);      // the mailbox is reused below
-    memcpy(hist.data(), b->h_pin, sizeof(unsigned int) * MUSE_U_BINS);
-    // the kernel bins with (int)(u * SCALE); lower_edge() is a value certainly not above the bin's floor
-    auto lower_edge = [](int e) { return (float)e / MUSE_U_SCALE * 0.99999f; };
-    // upper bound on #{U >= lo}: every bin from the one just below lo's upwards
-    auto count_ub = [&](float lo) {
-        int e0 = (int)(lo * MUSE_U_SCALE) - 1;
-        if (e0 < 0) e0 = 0;
-        int64_t c = 0;
-        for (int e = e0; e < MUSE_U_BINS; e++) c += hist[e];
-        return c;
-    };
-    // ---- pilot: the ~K series with the largest bounds (any set works; a good one gives a tight cut) ----
-    const int64_t K = std::min<int64_t>(S, std::max<int64_t>(4 * a.top_n, 1024));
-    float pilot_lo = thr_lo;
-    {
-        int64_t acc = 0;
-        int e = MUSE_U_BINS - 1;
-        for (; e > 0; e--) {
-            acc += hist[e];
-            if (acc >= K) break;
-        }
-        pilot_lo = std::max(thr_lo, lower_edge(e));
-    }
-    const int64_t pilot_ub = std::min<int64_t>(S, count_ub(pilot_lo));
-    double cut = a.threshold;
-    if (pilot_ub > 0) {
-        survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, pilot_lo, b->d_done, b->d_sidx, b->d_counters + 2);
-        b->timing.n_launches++;
-        int rc = score_exact_all(b, 0, b->d_sidx, pilot_ub, b->d_counters + 2);
-        if (rc) return rc;
-        // exact (score, lag) of the pilot -> cut.  Entries past the real count are never read.
-        double *ds = reinterpret_cast<double *>(b->d_skey);
-        int32_t *dl = reinterpret_cast<int32_t *>(b->d_slot);
-        gather_scores_kernel<<<(unsigned)((pilot_ub + 255) / 256), 256, 0, st>>>(b->d_sidx, b->d_counters + 2, b->d_score, b->d_lag, ds, dl);
-        b->timing.n_launches++;
-        const size_t kk = (size_t)pilot_ub;
-        if (64 + kk * 12 > b->h_pin_bytes) return fail(MUSE_ERR_UNSUPPORTED, "pilot of %zu series exceeds the mailbox", kk);
-        unsigned long long *h_n = reinterpret_cast<unsigned long long *>(b->h_pin);
-        double *hs = reinterpret_cast<double *>(b->h_pin + 64);
-        int32_t *hl = reinterpret_cast<int32_t *>(b->h_pin + 64 + kk * 8);
-        CU(cudaMemcpyAsync(h_n, b->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(hs, ds, sizeof(double) * kk, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(hl, dl, sizeof(int32_t) * kk, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        const size_t npilot = (size_t)std::min<unsigned long long>(h_n[0], kk);
-        std::vector<double> ps;
-        ps.reserve(npilot);
-        for (size_t i = 0; i < npilot; i++) {
-            const int64_t lg = hl[i];
-            if (hs[i] == hs[i] && (lg < 0 ? -lg : lg) <= a.max_lag && hs[i] >= a.threshold) ps.push_back(hs[i]);
-        }
-        if (a.top_n > 0 && (int64_t)ps.size() >= a.top_n) {
-            std::nth_element(ps.begin(), ps.begin() + (a.top_n - 1), ps.end(), std::greater<double>());
-            cut = std::max(cut, ps[(size_t)a.top_n - 1]);
-        }
-    }
-    // ---- everything else that can still reach `cut` ----
-    float cut_lo = (float)cut;
-    if ((double)cut_lo > cut) cut_lo = nextafterf(cut_lo, -INFINITY);   // round DOWN: never drop a contender
-    if (cut_lo < thr_lo) cut_lo = thr_lo;
-    if (cut_lo < pilot_lo) {
-        const int64_t rest_ub = std::min<int64_t>(S, count_ub(cut_lo));
-        if (rest_ub > S / 2 && S > 8192) {   // the bound prunes too little here: score everything exactly
-            *fell_back = true;
-            return score_exact_all(b, 0, nullptr, S);
-        }
-        if (rest_ub > 0) {
-            survivors_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, cut_lo, b->d_done, b->d_list, b->d_counters + 3);
-            b->timing.n_launches++;
-            int rc = score_exact_all(b, 0, b->d_list, rest_ub, b->d_counters + 3);
-            if (rc) return rc;
-        }
-    }
-    return MUSE_OK;
 }
 
 extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t max_lag, float *upper, float *lower) {
@@ -1400,18 +1221,10 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
         CU(cudaEventRecord(b->ev[2], st));
         return MUSE_OK;
     }
-    if (screen && screen_is_fused(b->log2m)) {
+    if (screen) {
         b->timing.mode = MUSE_MODE_SCREEN;
         b->fused_run = 1;
         rc = score_fused(b, a);
-        if (rc) return rc;
-        CU(cudaEventRecord(b->ev[2], st));
-        return MUSE_OK;
-    }
-    if (screen) {
-        bool fell_back = false;
-        b->timing.mode = MUSE_MODE_SCREEN;
-        rc = score_screened(b, a, &fell_back);
         if (rc) return rc;
         CU(cudaEventRecord(b->ev[2], st));
         return MUSE_OK;

@@ -51,12 +51,10 @@ struct ScreenParams {
     int64_t ld;
     int64_t count;
     int N;
-    const cf *twp;        // per-pass twiddles (fill_pass_twiddles for (LOG2M, LOG2M/2)), fp32
-    const cf *twn;        // exp(-2*pi*i*k/n), k < M, fp32
-    const float *A;       // |X_k|/(2n) * (k == 0 || k == M ? 1 : 2), rounded up, M+1 entries
-    const float4 *sw;     // warp kernel: (twn[k].x, twn[k].y, A[k], A[M-k]) for k < M/2
-    float a_mid;          // warp kernel: A[M/2]
-    // ---- fused refinement (warp kernel) ----
+    const cf *twp;        // per-pass twiddles (fill_pass_twiddles), fp32
+    const float4 *sw;     // (w_k.x, w_k.y, A[k], A[M-k]) for k < M/2: split twiddle exp(-2*pi*i*k/n), weights |X|/(2n)*(1|2) rounded up
+    float a_mid;          // A[M/2]
+    // ---- fused second stage ----
     const float4 *sx;     // (Xt[k].x, Xt[k].y, Xt[M-k].x, Xt[M-k].y) in fp32, k < M/2 (Xt = X/(2n))
     cf x_mid;             // Xt[M/2]
     float *out_L;         // [count] certain lower bound on a score that certainly passes the lag filter, else -1
@@ -71,18 +69,6 @@ struct ScreenParams {
     float *out_U;         // [count] upper bound on the score (already clamped to <= 1 + slack)
 };
 
-template <int LOG2M>
-struct ScreenCfg {
-    static_assert(LOG2M % 2 == 0, "screening kernel needs M = P*P");
-    static constexpr int LOG2P = LOG2M / 2;
-    using G = Geo<LOG2M, LOG2P>;
-    static constexpr int T = G::T;                   // == P, <= 32
-    static constexpr int TB = 128;
-    static constexpr int SPB = TB / T;
-    static constexpr int SM_ELEMS = G::MP + 1;
-    static constexpr size_t SMEM = (size_t)SPB * SM_ELEMS * sizeof(cf);
-};
-
 #if defined(__CUDACC__)
 
 template <int T>
@@ -92,123 +78,7 @@ __device__ __forceinline__ float group_sum_f(float x) {
     return x;
 }
 
-template <int LOG2M, int MINB>
-__global__ void __launch_bounds__(ScreenCfg<LOG2M>::TB, MINB)
-score_screen_kernel(const ScreenParams prm) {
-    using C = ScreenCfg<LOG2M>;
-    using G = typename C::G;
-    constexpr int LOG2P = C::LOG2P, P = G::P, T = C::T, M = G::M, n = 2 * M;
-    static_assert(T <= 32, "one series per (sub-)warp");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-
-    const int sib = threadIdx.x / T;
-    const int t = threadIdx.x - sib * T;
-    const int64_t pos = (int64_t)blockIdx.x * C::SPB + sib;
-    const bool valid = pos < prm.count;
-    const int64_t row = valid ? pos : prm.count - 1;
-    const double *rowp = prm.slab + row * prm.ld;
-    cf *sm = reinterpret_cast<cf *>(smem_raw) + (size_t)sib * C::SM_ELEMS;
-    const int N = prm.N;
-    const int pad = n - N;
-
-    // ---- load: (y - pivot) in fp64, then fp32 (N even: 16-byte loads) ----
-    const double pivot = __ldg(rowp);
-    const long long pivot_bits = __double_as_longlong(pivot);
-    bool varies = false;     // any sample whose bits differ from row[0]
-    cf v[P];
-    float s1 = 0.f;
-#pragma unroll
-    for (int r = 0; r < P; r++) {
-        const int i0 = 2 * (t + r * T) - pad;
-        cf val{0.f, 0.f};
-        if (i0 >= 0) {
-            const cd d = load_pair_stream(rowp + i0);
-            val.x = (float)(d.x - pivot);
-            val.y = (float)(d.y - pivot);
-            varies |= (__double_as_longlong(d.x) != pivot_bits) | (__double_as_longlong(d.y) != pivot_bits);
-        }
-        v[r] = val;
-        s1 += val.x + val.y;
-    }
-    const float mu = group_sum_f<T>(s1) / (float)N;
-    float ss = 0.f;
-#pragma unroll
-    for (int r = 0; r < P; r++) {
-        const int i0 = 2 * (t + r * T) - pad;
-        if (i0 >= 0) {
-            v[r].x -= mu;
-            v[r].y -= mu;
-            ss = fmaf(v[r].x, v[r].x, ss);
-            ss = fmaf(v[r].y, v[r].y, ss);
-        }
-    }
-    ss = group_sum_f<T>(ss);
-
-    // ---- forward FFT_M: radix-P pass through smem, radix-P pass in registers ----
-    fft_pass_compute_store<LOG2M, LOG2P, 0, float, cf>(v, sm, t, prm.twp);
-    __syncwarp();
-    fft_pass_load<LOG2M, LOG2P, 1, float>(v, sm, t);
-    Dft<P, float>::run(v);
-    // v[Perm<P>(j)] = Z[t + P*j]
-
-    // ---- |Y_k| for k = t + P*j; the mirror Z[M-k] sits in lane (P-t)%P, slot P-1-j
-    //      (lane 0: its own slot (P-j)%P) ----
-    const int lane = threadIdx.x & 31;
-    const int partner = (lane - t) + ((P - t) & (P - 1));
-    float acc = 0.f;
-#pragma unroll
-    for (int j = 0; j < P; j++) {
-        const cf zk = v[Perm<P>::at(j)];
-        const cf zp = v[Perm<P>::at(P - 1 - j)];
-        cf zm;
-        zm.x = __shfl_sync(0xffffffffu, zp.x, partner);
-        zm.y = __shfl_sync(0xffffffffu, zp.y, partner);
-        if (t == 0) zm = v[Perm<P>::at((P - j) & (P - 1))];
-        const int k = t + P * j;
-        const cf w = prm.twn[k];
-        const cf zmc = cconj(zm);
-        const cf e = cadd(zk, zmc);
-        const cf o = cmul_negi(csub(zk, zmc));
-        const cf wo = cmul(w, o);
-        const cf y = cadd(e, wo);                        // 2*Y_k
-        acc = fmaf(sqrtf(fmaf(y.x, y.x, y.y * y.y)), prm.A[k], acc);
-        if (k == 0) {                                    // Nyquist term 2*Y_M = e - w*o (w = 1)
-            const cf yn = csub(e, wo);
-            acc = fmaf(sqrtf(fmaf(yn.x, yn.x, yn.y * yn.y)), prm.A[M], acc);
-        }
-    }
-    acc = group_sum_f<T>(acc);
-    const bool any_varies = __ballot_sync(0xffffffffu, varies) >> (lane - t) & (T == 32 ? 0xffffffffu : ((1u << T) - 1u));
-
-    if (t == 0 && valid) {
-        const float var = ss / (float)(N - 1);
-        float U;
-        if (!any_varies) {
-            // every sample is bit-identical: the exact kernel finds std == 0 and scores exactly 0
-            // (xcorr.go:165-168), so 0 is a valid bound
-            U = 0.f;
-        } else if (!(var > 0.f) || !(var < 3.0e38f) || !(acc == acc)) {
-            // fp32 may flush a tiny variance to 0 or overflow a huge one: anything degenerate or
-            // non-finite goes to the exact kernel
-            U = 2.f;
-        } else {
-            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
-            if (!(U == U)) U = 2.f;
-        }
-        prm.out_U[pos] = U;
-    }
-}
-
-// ---- one-warp-per-series variant with the row staged in shared memory by one bulk async
-// copy (cp.async.bulk, SASS UBLKCP, completion on an mbarrier).  The whole 11.5 KB row is in
-// flight at once without holding registers, so the DRAM latency is paid once per series
-// instead of once per register-limited batch of loads; with the row in smem the mean is taken
-// in fp64, and the zero padding needs no per-lane predicates: slot Nh = N/2 of the row buffer
-// holds (mean, mean), every out-of-range complex index is clamped to it, and (y - mean)
-// rounds to exactly 0 there.  The |Y_f| bound is invariant under rotation of the padded
-// series, so the zeros may trail (index 0 = first sample) instead of leading.
-// The row buffer is dead once the samples are in registers and is reused as the FFT exchange
-// buffer.
+// ---- cp.async.bulk / mbarrier plumbing of the warp kernel (SASS UBLKCP, SYNCS) ----
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {

@@ -1,5 +1,6 @@
 // muse_screen_block.cuh -- the fp32 screening + fused refinement pass for FFT lengths above 2048
-// (n = 4096, 8192, 16384: series of 2050 .. 16384 samples, e.g. one week at one sample per minute).
+// (n = 4096, 8192, 16384: series of 2050 .. 16384 samples, e.g. one week at one sample per minute)
+// and below it (n = 512, 1024: series of 258 .. 1024 samples).
 //
 // Same mathematics and the same contract as score_screen_warp_kernel (muse_screen.cuh): a rigorous
 // upper bound U = (1/n) sum_f |Y_f||X_f| / std + slack for every series; a series whose U reaches the
@@ -25,18 +26,25 @@
 
 namespace muse {
 
+// LOG2M -> points per thread: 32 for M >= 2048, 16 for M = 512 (n = 1024), 8 for M = 256 (n = 512), so that a
+// block is never smaller than a warp.  The transform is radix P x P x R_LAST (R_LAST = M / P^2).
 template <int LOG2M>
 struct ScreenBlockCfg {
-    static_assert(LOG2M >= 11 && LOG2M <= 13, "block kernel: n = 4096 .. 16384");
-    using G = Geo<LOG2M, 5>;
-    static constexpr int T = G::T;                   // threads per series == block size (64, 128, 256)
+    static_assert((LOG2M >= 11 && LOG2M <= 13) || LOG2M == 9 || LOG2M == 8, "block kernel: n = 512, 1024, 4096 .. 16384");
+    static constexpr int LOG2P = LOG2M >= 11 ? 5 : (LOG2M == 9 ? 4 : 3);
+    using G = Geo<LOG2M, LOG2P>;
+    static constexpr int P = G::P;
+    static constexpr int T = G::T;                   // threads per series == block size (32 .. 256)
     static constexpr int NWARP = T / 32;
     static constexpr size_t SMEM = (size_t)(G::MP + 1) * sizeof(cf);
     static constexpr int LAST = G::NPASS - 1;        // NPASS == 3
-    static constexpr int LR_LAST = G::log2r(LAST);   // 1, 2, 3
+    static constexpr int LR_LAST = G::log2r(LAST);
     static constexpr int R_LAST = 1 << LR_LAST;
-    static constexpr int NB_LAST = 32 / R_LAST;
-    static constexpr int LS_LAST = 10;
+    static constexpr int NB_LAST = P / R_LAST;
+    static constexpr int LS_LAST = 2 * LOG2P;
+    static constexpr int TP = T + (T >> LOG2P);      // pad(t + T*x) = pad(t) + TP*x: T is a multiple of P
+    static constexpr int JP = (1 << LS_LAST) + (1 << (LS_LAST - LOG2P));   // pad(b + (j << LS_LAST)) = pad(b) + JP*j
+    static_assert(G::NPASS == 3 && T % 32 == 0 && T % P == 0, "geometry");
 };
 
 #if defined(__CUDACC__)
@@ -103,49 +111,49 @@ __device__ __forceinline__ float2 block_max_f2(float a, float b, float2 *red, in
     return s;
 }
 
-// Forward FFT_M of the 32 points per thread in v (input j of thread t = element t + T*j); on return
-// v[c*R_LAST + Perm<R_LAST>(j)] = Z[(t + c*T) + (j << 10)].  Ends WITHOUT a barrier after the last
+// Forward FFT_M of the P points per thread in v (input j of thread t = element t + T*j); on return
+// v[c*R_LAST + Perm<R_LAST>(j)] = Z[(t + c*T) + (j << LS_LAST)].  Ends WITHOUT a barrier after the last
 // pass' loads: the caller synchronises before it writes the exchange buffer again.
 //
-// Same passes as fft_pass_compute_store / fft_pass_load of muse_fft.cuh for Geo<LOG2M, 5>, with the
+// Same passes as fft_pass_compute_store / fft_pass_load of muse_fft.cuh for Geo<LOG2M, LOG2P>, with the
 // padded shared-memory indices written out as (per-thread base) + (compile-time offset): T is a
-// multiple of 32, so pad(t + T*x) = pad(t) + (T + T/32)*x and pad(q + 1024*p + 32*j) = q + 1056*p + 33*j.
+// multiple of P, so pad(t + T*x) = pad(t) + TP*x, and pad(q + P*P*p + P*j) = q + (P*P + P)*p + (P + 1)*j.
 // (The generic index arithmetic was 20 % of the kernel's instructions.)
 template <int LOG2M>
 __device__ __forceinline__ void block_fft(cf *v, cf *sm, int t, const cf *twp) {
     using C = ScreenBlockCfg<LOG2M>;
     using G = typename C::G;
-    constexpr int T = C::T, TP = T + T / 32;              // pad(t + T*x) = pad(t) + TP*x
-    const int pt = t + (t >> 5);                            // pad(t)
-    // pass 0: radix 32 over elements t + T*j, twiddle W_M^(j*t), scatter to 32*t + j
-    Dft<32, float>::run(v);
+    constexpr int T = C::T, TP = C::TP, P = C::P, LP = C::LOG2P;
+    const int pt = t + (t >> LP);                           // pad(t)
+    // pass 0: radix P over elements t + T*j, twiddle W_M^(j*t), scatter to P*t + j
+    Dft<P, float>::run(v);
     {
-        cf *dst = sm + 33 * t;
+        cf *dst = sm + (P + 1) * t;
         const cf *tw = twp + t;                             // row j-1, column t of the pass-0 table (T columns)
-        dst[0] = v[Perm<32>::at(0)];
+        dst[0] = v[Perm<P>::at(0)];
 #pragma unroll
-        for (int j = 1; j < 32; j++) dst[j] = cmul(v[Perm<32>::at(j)], tw[(j - 1) * T]);
+        for (int j = 1; j < P; j++) dst[j] = cmul(v[Perm<P>::at(j)], tw[(j - 1) * T]);
     }
     __syncthreads();
-    // pass 1: butterfly b = t: p = t >> 5, q = t & 31; inputs t + T*j; twiddle W_T^(j*p); scatter to q + 1024*p + 32*j
+    // pass 1: butterfly b = t: p = t / P, q = t % P; inputs t + T*j; twiddle W_T^(j*p); scatter to q + P*P*p + P*j
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] = sm[pt + TP * j];
+    for (int j = 0; j < P; j++) v[j] = sm[pt + TP * j];
     __syncthreads();
-    Dft<32, float>::run(v);
+    Dft<P, float>::run(v);
     {
-        const int p = t >> 5, q = t & 31;
-        cf *dst = sm + q + 1056 * p;
-        const cf *tw = twp + G::tw_off(1) + p;              // row j-1, column p of the pass-1 table (T/32 columns)
-        dst[0] = v[Perm<32>::at(0)];
+        const int p = t >> LP, q = t & (P - 1);
+        cf *dst = sm + q + (P * P + P) * p;
+        const cf *tw = twp + G::tw_off(1) + p;              // row j-1, column p of the pass-1 table (T/P columns)
+        dst[0] = v[Perm<P>::at(0)];
 #pragma unroll
-        for (int j = 1; j < 32; j++) dst[33 * j] = cmul(v[Perm<32>::at(j)], tw[(j - 1) * (T / 32)]);
+        for (int j = 1; j < P; j++) dst[(P + 1) * j] = cmul(v[Perm<P>::at(j)], tw[(j - 1) * (T / P)]);
     }
     __syncthreads();
-    // last pass: NB_LAST butterflies of radix R_LAST per thread, b = t + c*T, inputs b + (j << 10); no twiddles
+    // last pass: NB_LAST butterflies of radix R_LAST per thread, b = t + c*T, inputs b + (j << LS_LAST); no twiddles
 #pragma unroll
     for (int c = 0; c < C::NB_LAST; c++)
 #pragma unroll
-        for (int j = 0; j < C::R_LAST; j++) v[c * C::R_LAST + j] = sm[pt + TP * c + 1056 * j];
+        for (int j = 0; j < C::R_LAST; j++) v[c * C::R_LAST + j] = sm[pt + TP * c + C::JP * j];
 #pragma unroll
     for (int c = 0; c < C::NB_LAST; c++) Dft<C::R_LAST, float>::run(v + c * C::R_LAST);
 }
@@ -155,7 +163,7 @@ __global__ void __launch_bounds__(ScreenBlockCfg<LOG2M>::T, MINB)
 score_screen_block_kernel(const ScreenParams prm) {
     using C = ScreenBlockCfg<LOG2M>;
     using G = typename C::G;
-    constexpr int P = 32, M = G::M, T = C::T, NW = C::NWARP;
+    constexpr int P = C::P, M = G::M, T = C::T, NW = C::NWARP, LP = C::LOG2P;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red_d[NW];
     __shared__ float2 red_f[NW];
@@ -163,9 +171,9 @@ score_screen_block_kernel(const ScreenParams prm) {
     cf *sm = reinterpret_cast<cf *>(smem_raw);
 
     const int t = threadIdx.x;
-    constexpr int TP = T + T / 32;                      // pad(t + T*x) = pad(t) + TP*x (T is a multiple of 32)
-    const int pt = t + (t >> 5);                        // pad(t)
-    const int pm = M + M / 32 - t - ((t + 31) >> 5);    // pad(M - t) for t >= 1 (t = 0 pairs bin 0 with itself)
+    constexpr int TP = C::TP;                           // pad(t + T*x) = pad(t) + TP*x (T is a multiple of P)
+    const int pt = t + (t >> LP);                       // pad(t)
+    const int pm = M + (M >> LP) - t - ((t + P - 1) >> LP);   // pad(M - t) for t >= 1 (t = 0 pairs bin 0 with itself)
     const int N = prm.N;
     const int Nh = N >> 1;
     const int nz = (Nh + T - 1) / T;                 // rows of T complex slots that hold samples
@@ -187,7 +195,7 @@ score_screen_block_kernel(const ScreenParams prm) {
         cf v[P];
         double s0 = 0.0, s1 = 0.0, pivot = 0.0;
 #pragma unroll
-        for (int b0 = 0; b0 < P; b0 += 8) {
+        for (int b0 = 0; b0 < P; b0 += 8) {              // P is 8, 16 or 32
             cd x[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
@@ -226,7 +234,7 @@ score_screen_block_kernel(const ScreenParams prm) {
         for (int c = 0; c < C::NB_LAST; c++)
 #pragma unroll
             for (int j = 0; j < C::R_LAST; j++)
-                sm[pt + TP * c + 1056 * j] = v[c * C::R_LAST + Perm<C::R_LAST>::at(j)];      // pad((t + c*T) + (j << 10))
+                sm[pt + TP * c + C::JP * j] = v[c * C::R_LAST + Perm<C::R_LAST>::at(j)];      // pad((t + c*T) + (j << LS_LAST))
         __syncthreads();
 
         // ---- |2Y_k| and |2Y_(M-k)| for k = t + T*i < M/2 (k = 0 pairs with itself: DC and Nyquist) ----

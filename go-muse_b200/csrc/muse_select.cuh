@@ -321,24 +321,5 @@ __global__ void select_gather_kernel(const SelectState *st, const unsigned long 
     }
 }
 
-// Histogram of the screening bounds U (shared-memory privatised), MUSE_U_BINS bins of width
-// 1/MUSE_U_SCALE; the last bin collects everything above.
-#define MUSE_U_BINS 2048
-#define MUSE_U_SCALE 2000.0f
-__global__ void u_hist_kernel(const float *__restrict__ U, int64_t S, unsigned int *__restrict__ hist) {
-    __shared__ unsigned int h[MUSE_U_BINS];
-    for (int b = threadIdx.x; b < MUSE_U_BINS; b += blockDim.x) h[b] = 0;
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
-        const float u = U[i];
-        int b = u > 0.f ? (int)(u * MUSE_U_SCALE) : 0;
-        if (b >= MUSE_U_BINS) b = MUSE_U_BINS - 1;
-        atomicAdd(&h[b], 1u);
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < MUSE_U_BINS; b += blockDim.x)
-        if (h[b]) atomicAdd(&hist[b], h[b]);
-}
-
 }  // namespace muse
 #endif
