@@ -206,3 +206,86 @@ def test_screening_prunes_on_siggen_data(ctx):
         np.testing.assert_array_equal(x, y)
     assert 100 <= t.n_rescored <= 0.01 * S        # the fused fp32 second stage leaves a few hundred
     assert t.n_refined <= 0.2 * S
+
+
+def test_randomised_differential_screen_vs_exact(ctx):
+    """Random shapes, windows, thresholds, groupings and pathological rows (NaN, Inf, constants, huge offsets,
+    duplicates): the screened run must return exactly what the all-exact run returns, every time."""
+    rng = np.random.default_rng(20261018)
+    lengths = [258, 300, 480, 512, 700, 1000, 1024, 1026, 1440, 1600, 2048, 2050, 3000, 4096, 5000, 8192, 8200, 10080]
+    for trial in range(36):
+        N = int(lengths[trial % len(lengths)])
+        S = int(rng.integers(200, 3000 if N <= 2048 else 700))
+        Y = _adversarial(rng, S, N)
+        # extra pathologies
+        for _ in range(int(rng.integers(0, 6))):
+            i = int(rng.integers(0, S))
+            kind = int(rng.integers(0, 5))
+            if kind == 0:
+                Y[i, int(rng.integers(0, N))] = np.nan
+            elif kind == 1:
+                Y[i, int(rng.integers(0, N))] = np.inf
+            elif kind == 2:
+                Y[i] = Y[int(rng.integers(0, S))]             # exact duplicate: ties
+            elif kind == 3:
+                Y[i] = -Y[int(rng.integers(0, S))]            # mirrored: negative peak, same |score|
+            else:
+                Y[i] = 1e300 * rng.standard_normal(N)         # overflows fp32 and the fp64 variance
+        ref = np.zeros(N)
+        w = int(rng.integers(3, 40))
+        c = int(rng.integers(N // 4, 3 * N // 4))
+        ref[c:c + w] = rng.uniform(0.5, 3.0)
+        ref += rng.uniform(0.0, 0.3) * (rng.random(N) - 0.5)
+        nk = 3
+        ids = np.stack([rng.integers(0, max(2, S // int(rng.integers(2, 60))), S),
+                        rng.integers(0, 5, S), rng.integers(-1, 3, S)], axis=1).astype(np.int32)
+        store = mb.DeviceStore(ctx, N, nk, S)
+        store.append(Y, ids)
+        b = mb.DeviceBatch(ctx, store, ref)
+        for _ in range(3):
+            max_lag = int(rng.choice([0, 1, 15, 60, 240, N // 2, N, 5 * N]))
+            top_n = int(rng.choice([1, 4, 20, 100, S // 2 + 1, 2 * S]))
+            thr = float(rng.choice([0.0, 0.2, 0.5, 0.9, 0.999]))
+            sf = int(rng.choice([mb.SignFilter_ANY, mb.SignFilter_POS]))
+            cols = [[], [], [0], [1], [0, 2], [2, 1, 0]][int(rng.integers(0, 6))]
+            e = b.run(cols, max_lag, top_n, thr, sf, mode=mb.MODE_EXACT)
+            s = b.run(cols, max_lag, top_n, thr, sf, mode=mb.MODE_SCREEN)
+            assert b.timing().mode == mb.MODE_SCREEN
+            for x, y in zip(e, s):
+                np.testing.assert_array_equal(x, y, err_msg="N=%d S=%d lag=%d top=%d thr=%g cols=%s" % (N, S, max_lag, top_n, thr, cols))
+            if not cols:
+                pe = b.run_partial([], max_lag, top_n, thr, sf, mode=mb.MODE_EXACT)
+                np.testing.assert_array_equal(pe["score"], e[0])
+        b.close()
+        store.close()
+
+
+def test_scratch_pool_survives_batch_churn(ctx):
+    """Batches created and destroyed in every order on one context share pooled scratch; results must not change
+    when a batch inherits a smaller or larger set than its store needs."""
+    rng = np.random.default_rng(5)
+    stores, refs, want = [], [], []
+    for S, N in ((500, 480), (20000, 1440), (3000, 1440), (40000, 480)):
+        Y = _adversarial(rng, S, N)
+        ref = np.zeros(N)
+        ref[N // 2 - 5:N // 2 + 5] = 1.5
+        ref += 0.1 * (rng.random(N) - 0.5)
+        st = mb.DeviceStore(ctx, N, 1, S)
+        st.append(Y, (np.arange(S) % 17).astype(np.int32)[:, None])
+        stores.append(st)
+        refs.append(ref)
+        b = mb.DeviceBatch(ctx, st, ref)
+        want.append((b.run([], 60, 50, 0.3), b.run([0], 60, 50, 0.3)))
+        b.close()
+    order = [3, 0, 1, 2, 0, 3, 2, 1, 1, 0]
+    alive = []
+    for k in order:
+        b = mb.DeviceBatch(ctx, stores[k], refs[k])
+        alive.append(b)
+        for got, exp in zip((b.run([], 60, 50, 0.3), b.run([0], 60, 50, 0.3)), want[k]):
+            for x, y in zip(got, exp):
+                np.testing.assert_array_equal(x, y)
+        if len(alive) > 2:
+            alive.pop(0).close()
+    for b in alive:
+        b.close()
