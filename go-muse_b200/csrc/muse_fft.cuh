@@ -300,6 +300,13 @@ MUSE_HD void fft_pass_compute_store(cx<F> *v, cx<F> *sm, int t, const TW *tw) {
         const int b = t + c * G::T;
         const int p = b >> LS;
         const int q = b & ((1 << LS) - 1);
+        // Padded index of output j = pad(q + ((R*p + j) << LS)).  When j << LS is a multiple of the padding
+        // period the index is (per-butterfly base) + (compile-time offset); in pass 0 with R equal to the
+        // period it is (R + 1)*p + j.  The generic form costs a shift and two adds per element (a quarter
+        // of the exact kernel's instructions were such index arithmetic).
+        constexpr bool LIN = LS >= G::LOG2PAD;
+        constexpr bool LIN0 = (LS == 0 && LR == G::LOG2PAD);
+        const int base = LIN ? G::pad(q + ((R * p) << LS)) : (LIN0 ? (R + 1) * p : 0);
 #pragma unroll
         for (int j = 0; j < R; j++) {
             cx<F> val = v[c * R + Perm<R>::at(j)];
@@ -307,7 +314,8 @@ MUSE_HD void fft_pass_compute_store(cx<F> *v, cx<F> *sm, int t, const TW *tw) {
                 const TW w = twp[(j - 1) * COLS + p];     // W_NCUR^(j*p)
                 val = cmul(val, cx<F>{(F)w.x, (F)w.y});
             }
-            sm[G::pad(q + ((R * p + j) << LS))] = val;
+            const int idx = LIN ? base + (j << LS) + ((j << LS) >> G::LOG2PAD) : (LIN0 ? base + j : G::pad(q + ((R * p + j) << LS)));
+            sm[idx] = val;
         }
     }
 }
@@ -326,8 +334,15 @@ MUSE_HD void fft_pass_load(cx<F> *v, const cx<F> *sm, int t) {
         const int b = t + c * G::T;
         const int p = b >> LS;
         const int q = b & ((1 << LS) - 1);
+        // pad(q + ((p + (j << LNR)) << LS)) = pad(q + (p << LS)) + (compile-time offset) when j << (LNR + LS)
+        // is a multiple of the padding period
+        constexpr bool LIN = (LNR + LS) >= G::LOG2PAD;
+        const int base = G::pad(q + (p << LS));
 #pragma unroll
-        for (int j = 0; j < R; j++) v[c * R + j] = sm[G::pad(q + ((p + (j << LNR)) << LS))];
+        for (int j = 0; j < R; j++) {
+            const int idx = LIN ? base + (j << (LNR + LS)) + ((j << (LNR + LS)) >> G::LOG2PAD) : G::pad(q + ((p + (j << LNR)) << LS));
+            v[c * R + j] = sm[idx];
+        }
     }
 }
 
