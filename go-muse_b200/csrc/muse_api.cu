@@ -97,6 +97,7 @@ struct muse_group {
     int32_t max_id[16];
     int64_t global_offset;
     unsigned char *row_flags;   // [cap] screening: rows whose offset dwarfs their spread (filled lazily up to flags_upto)
+    double *row_mean;           // [cap] fp64 mean of each row (same pass)
     int64_t flags_cap, flags_upto;
 };
 
@@ -252,6 +253,7 @@ extern "C" void muse_group_destroy(muse_group *g) {
     if (g->slab) cudaFree(g->slab);
     if (g->labels) cudaFree(g->labels);
     if (g->row_flags) cudaFree(g->row_flags);
+    if (g->row_mean) cudaFree(g->row_mean);
     delete g;
 }
 
@@ -953,7 +955,7 @@ static cudaError_t launch_screen_warp_nz(const ScreenParams &p, int sm_count, cu
     auto kern = score_screen_warp_kernel<NZ>;
     const int warps = C::warps(p.N);
     const size_t wb = C::warp_bytes(p.N);
-    const size_t smem = wb * (size_t)warps;
+    const size_t smem = C::smem_bytes(p.N);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t blocks = (p.count + warps - 1) / warps;      // persistent: one block per SM
@@ -1016,15 +1018,18 @@ static int ensure_lower(muse_batch *b) {
 static int refresh_row_flags(muse_group *g) {
     if (g->flags_cap < g->cap) {
         if (g->row_flags) cudaFree(g->row_flags);
+        if (g->row_mean) cudaFree(g->row_mean);
         g->row_flags = nullptr;
+        g->row_mean = nullptr;
         CU(cudaMalloc(&g->row_flags, (size_t)g->cap));
+        CU(cudaMalloc(&g->row_mean, sizeof(double) * (size_t)g->cap));
         g->flags_cap = g->cap;
         g->flags_upto = 0;
     }
     if (g->flags_upto < g->size) {
         const int64_t count = g->size - g->flags_upto;
         const unsigned grid = (unsigned)std::min<int64_t>((count + 7) / 8, (int64_t)g->ctx->sm_count * 16);
-        row_offset_flags_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, (int)g->N, g->flags_upto, count, g->row_flags);
+        row_offset_flags_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, (int)g->N, g->flags_upto, count, g->row_flags, g->row_mean);
         CU(cudaGetLastError());
         g->flags_upto = g->size;
     }
@@ -1045,6 +1050,7 @@ static ScreenParams screen_params(muse_batch *b) {
     sp.sx = b->sx_f;
     sp.x_mid = b->x_mid;
     sp.row_flags = b->g->row_flags;
+    sp.row_mean = b->g->row_mean;
     sp.cut_bits = b->d_cut;
     sp.n_refined = reinterpret_cast<unsigned long long *>(b->d_cut + 2);
     sp.cut_hist = b->d_cut + 4;
@@ -1063,6 +1069,7 @@ static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t m
     int rc = refresh_row_flags(b->g);
     if (rc) return rc;
     sp.row_flags = b->g->row_flags;
+    sp.row_mean = b->g->row_mean;
     init_cut_kernel<<<1, 256, 0, b->ctx->stream>>>(b->d_cut, cut0);
     CU(cudaGetLastError());
     const int64_t n = b->n, pad = n - b->N;

@@ -59,6 +59,7 @@ struct ScreenParams {
     cf x_mid;             // Xt[M/2]
     float *out_L;         // [count] certain lower bound on a score that certainly passes the lag filter, else -1
     const unsigned char *row_flags;   // [count] 1: |mean| > MUSE_SCREEN_OFFSET_MAX * std (row_offset_flags_kernel): never bounded here
+    const double *row_mean;           // [count] fp64 mean of each row (same kernel, once per appended row)
     unsigned *cut_bits;   // running lower bound on the final top-N cut-off (float bits, only ever raised)
     unsigned *cut_hist;   // [MUSE_CUT_COARSE] coarse counts, then [MUSE_CUT_BINS] fine counts of lower bounds
     unsigned long long *n_refined;
@@ -210,7 +211,7 @@ __device__ __forceinline__ float refine_decide(float U, float s_in, float s_out,
 // flags[i] = 1 when row first+i has |mean| > MUSE_SCREEN_OFFSET_MAX * std (std > 0).  One warp per row;
 // sums are taken about the row's first sample so that the one-pass variance does not cancel.
 __global__ void row_offset_flags_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
-                                        unsigned char *__restrict__ flags) {
+                                        unsigned char *__restrict__ flags, double *__restrict__ means) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -232,24 +233,44 @@ __global__ void row_offset_flags_kernel(const double *__restrict__ slab, int64_t
             const double mean = pivot + s1 / N;
             const double var = (s2 - s1 * s1 / N) / (N - 1);
             flags[first + i] = (var > 0.0 && mean * mean > MUSE_SCREEN_OFFSET_MAX * MUSE_SCREEN_OFFSET_MAX * var) ? 1 : 0;
+            means[first + i] = mean;
         }
     }
 }
 
 struct ScreenWarpCfg {
     using G = Geo<10, 5>;                       // M = 1024 = 32 x 32: one warp per series
-    static constexpr int MAX_WARPS = 12;   // 3 warps per scheduler: up to 168 registers per thread
-    static constexpr size_t SMEM_BUDGET = 226 * 1024;
+    static constexpr int MAX_WARPS = 12;        // 3 warps per scheduler at up to 168 registers per thread (16 at 128 measured equal)
+    static constexpr int NREF = 2;              // exchange buffers for the (rare) second stage, shared under a lock
+    static constexpr size_t SMEM_BUDGET = 227 * 1024;
     static constexpr size_t EX_BYTES = ((size_t)(G::MP + 1) * sizeof(cf) + 127) / 128 * 128;   // padded FFT exchange buffer
-    static size_t row_bytes(int N) { return ((size_t)N * 8 + 127) / 128 * 128; }
-    static size_t warp_bytes(int N) { return row_bytes(N) + EX_BYTES; }
+    static size_t row_bytes(int N) { const size_t r = ((size_t)N * 8 + 127) / 128 * 128; return r > EX_BYTES ? r : EX_BYTES; }
+    static size_t warp_bytes(int N) { return row_bytes(N); }
     static int warps(int N) {
-        const size_t w = SMEM_BUDGET / warp_bytes(N);
+        const size_t w = (SMEM_BUDGET - NREF * EX_BYTES) / warp_bytes(N);
         return (int)(w > MAX_WARPS ? MAX_WARPS : w);
     }
-    // complex slots t + 32*r, r < nz, hold samples; the rest of the padded series is zero
+    static size_t smem_bytes(int N) { return (size_t)warps(N) * warp_bytes(N) + NREF * EX_BYTES; }
     static int nz(int N) { return (N / 2 + 31) / 32; }
 };
+
+__device__ __forceinline__ int ex_acquire(unsigned *locks, int t, int hint) {
+    int slot = hint & (ScreenWarpCfg::NREF - 1);
+    while (true) {
+        unsigned old = 1u;
+        if (t == 0) old = atomicCAS(&locks[slot], 0u, 1u);
+        if (__shfl_sync(0xffffffffu, old, 0) == 0u) break;
+        slot = (slot + 1) & (ScreenWarpCfg::NREF - 1);
+    }
+    return slot;
+}
+__device__ __forceinline__ void ex_release(unsigned *locks, int t, int slot) {
+    __syncwarp();
+    if (t == 0) {
+        __threadfence_block();
+        atomicExch(&locks[slot], 0u);
+    }
+}
 
 // Persistent kernel, one block per SM, every warp an independent pipeline over its own series
 // (pos = first, first + stride, ...): its row buffer is refilled by the next cp.async.bulk as
@@ -286,6 +307,7 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
     constexpr int P = 32, M = G::M;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[C::MAX_WARPS];
+    __shared__ unsigned ex_locks[C::NREF];
 
     const int w = threadIdx.x >> 5;
     const int t = threadIdx.x & 31;
@@ -295,7 +317,8 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
     const int pos0 = (int)(blockIdx.x * (blockDim.x >> 5)) + w;
     unsigned char *buf = smem_raw + (size_t)w * warp_bytes;
     const cd *rowc = reinterpret_cast<const cd *>(buf);
-    cf *sm = reinterpret_cast<cf *>(buf + row_bytes);
+    cf *sm = reinterpret_cast<cf *>(buf);                       // forward exchange: the row buffer itself
+    unsigned char *refbase = smem_raw + (size_t)(blockDim.x >> 5) * warp_bytes;
     const int N = prm.N;
     const int Nh = N >> 1;
     const unsigned bar = smem_u32(&bars[w]);
@@ -303,11 +326,12 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
     const bool lane0 = (t == 0);
     const bool last_in = t + (NZ - 1) * 32 < Nh;      // is this lane's slot of the last row a sample?
 
+    if (threadIdx.x < C::NREF) ex_locks[threadIdx.x] = 0u;
     if (t == 0) {
         mbar_init(bar, 1);
         if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)N * 8u, bar);
     }
-    __syncwarp();
+    __syncthreads();
 
     // mbarrier phase parity = iteration parity; it rides in bit 31 of the loop counter (count < 2^31):
     // a separate loop-carried register is one too many for the allocator at 168 and gets spilled
@@ -322,40 +346,24 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
             cut_raw = ld_relaxed_u32(prm.cut_bits);
             flag_raw = prm.row_flags[pos];      // not combined here: any use of the values would wait for the loads
         }
+        const double mu = prm.row_mean[pos];    // fp64 mean from the ingest pass (xcorr.go:85-86); in flight with the row
         mbar_wait(bar, phase);      // every lane waits itself (one polling lane + __syncwarp measured 3x slower)
 
-        // ---- row -> registers; mean in fp64 (xcorr.go:85-86) ----
-        constexpr int KEEP = NZ;       // rows kept in registers across the reduction (a smaller KEEP re-reads the rest; measured slower)
-        cd d[KEEP];
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int r = 0; r < NZ; r++) {
-            const cd x = (r < NZ - 1 || last_in) ? rowc[t + r * 32] : cd{0.0, 0.0};
-            if (r < KEEP) d[r] = x;
-            s0 += x.x;
-            s1 += x.y;
-        }
-        double sum = s0 + s1;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        const double mu = sum / (double)N;
-
-        // ---- centred samples in fp32, then hand the buffer back to the copy engine ----
+        // ---- centred samples in fp32 straight from the row buffer ----
         cf v[P];
         cf ss2{0.f, 0.f};
 #pragma unroll
         for (int r = 0; r < P; r++) {
             if (r < NZ) {
-                const cd x = (r == NZ - 1 && !last_in) ? cd{mu, mu} : (r < KEEP ? d[r] : rowc[t + r * 32]);
+                const cd x = (r == NZ - 1 && !last_in) ? cd{mu, mu} : rowc[t + r * 32];
                 v[r] = cf{(float)(x.x - mu), (float)(x.y - mu)};
                 ss2 = pfma(v[r], v[r], ss2);
             } else {
                 v[r] = cf{0.f, 0.f};
             }
         }
-        __syncwarp();
+        __syncwarp();                       // the row is consumed: the buffer becomes the exchange buffer
         const int next = pos + stride;      // < 2^31: the launcher keeps count + stride below it
-        if (t == 0 && next < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
         const float ss = group_sum_f<32>(ss2.x + ss2.y);
 
         // ---- forward FFT_1024: pruned radix-32, twiddle, exchange through smem, radix-32 ----
@@ -368,7 +376,11 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
         }
         __syncwarp();
         fft_pass_load<10, 5, 1, float>(v, sm, t);
-        __syncwarp();                                   // the exchange buffer is free for the next series
+        __syncwarp();
+        if (t == 0 && next < count) {       // the exchange is over: hand the buffer to the copy engine for the next row
+            asm volatile("" ::"r"(__float_as_uint(v[P - 1].y)) : "memory");
+            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
+        }
         Dft<P, float>::run(v);                          // v[Perm(j)] = Z[t + 32*j]
 
         // ---- |2Y_k| and |2Y_(M-k)| for k = t + 32*j, j < 16 ----
@@ -463,15 +475,19 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
 #pragma unroll
             for (int j = 0; j < P; j++) u[j] = v[Perm<P>::at(j)];
             Dft<P, float>::run(u);
+            {
+                const int slot = ex_acquire(ex_locks, t, w);
+                cf *smr = reinterpret_cast<cf *>(refbase + (size_t)slot * C::EX_BYTES);
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                cf val = u[Perm<P>::at(j)];
-                if (j > 0) val = cmul(val, prm.twp[(j - 1) * 32 + t]);
-                sm[G::pad(32 * t + j)] = val;
+                for (int j = 0; j < P; j++) {
+                    cf val = u[Perm<P>::at(j)];
+                    if (j > 0) val = cmul(val, prm.twp[(j - 1) * 32 + t]);
+                    smr[G::pad(32 * t + j)] = val;
+                }
+                __syncwarp();
+                fft_pass_load<10, 5, 1, float>(u, smr, t);
+                ex_release(ex_locks, t, slot);
             }
-            __syncwarp();
-            fft_pass_load<10, 5, 1, float>(u, sm, t);
-            __syncwarp();
             Dft<P, float>::run(u);      // u[Perm(j)] = (cc'[2i+1], cc'[2i]), i = t + 32*j; cc' = std * cc rotated by pad
             // ---- max |cc'| inside and outside the lag window ----
             float m_in = 0.f, m_out = 0.f;
