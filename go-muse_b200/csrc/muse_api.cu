@@ -613,7 +613,7 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
     if (!b->d_flag) CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
     if (!b->d_counters) CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
     if (!b->d_sel) CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
-    if (!b->d_cut) CU(cudaMalloc(&b->d_cut, sizeof(unsigned) * (4 + MUSE_CUT_COARSE + MUSE_CUT_BINS)));
+    if (!b->d_cut) CU(cudaMalloc(&b->d_cut, sizeof(unsigned) * (4 + MUSE_CUT_WORDS)));
     if (!b->h_pin) {
         b->h_pin_bytes = (size_t)4 << 20;
         CU(cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault));
@@ -786,6 +786,7 @@ struct RunArgs {
     int64_t max_lag, top_n;
     double threshold;
     int32_t sign_filter, mode, signed_scores;
+    int32_t list_only;   // fused runs: the caller reads scores only through the exact list (no NaN fill of the score array)
 };
 
 struct Rec {
@@ -848,7 +849,7 @@ static int setup_group_table(muse_batch *b, const RunArgs &a, KeyCols &kc, Group
 // fused screened runs launch the exact kernel over at most this many listed series without knowing
 // the list length on the host; run_fused_overflow finishes a longer list after the fact
 #define MUSE_EXACT_UB 32768
-static int run_fused_overflow(muse_batch *b, int64_t n_exact);
+static int run_fused_overflow(muse_batch *b, int64_t n_exact, bool refill);
 
 // Produces the selected records on the host (unsorted).  apply_filter == 0 keeps every
 // representative (grouped multi-GPU partials).
@@ -895,7 +896,7 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
         if (b->fused_run == 1 && (int64_t)h_n[2] > std::min<int64_t>(S, MUSE_EXACT_UB)) {
             // rare: more exact candidates than the fixed launch covered -> finish them and select again
             const int64_t n_exact = (int64_t)h_n[2];
-            int rc = run_fused_overflow(b, n_exact);
+            int rc = run_fused_overflow(b, n_exact, false);
             if (rc) return rc;
             b->fused_run = 0;
             rc = run_select(b, a, apply_filter, limit, recs);
@@ -1061,7 +1062,8 @@ static ScreenParams screen_params(muse_batch *b) {
 // Arms the fused refinement of the warp kernel: running cut-off = cut0 (+inf: bounds only),
 // counters and histogram cleared, lag window in the kernel's rotated cc index.
 __global__ void init_cut_kernel(unsigned *state, float cut0) {
-    for (int i = threadIdx.x; i < 4 + MUSE_CUT_COARSE + MUSE_CUT_BINS; i += blockDim.x) state[i] = (i == 0) ? __float_as_uint(cut0) : 0u;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 + MUSE_CUT_WORDS) state[i] = (i == 0) ? __float_as_uint(cut0) : 0u;
 }
 
 static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t max_lag, int64_t top_n, double threshold) {
@@ -1070,7 +1072,7 @@ static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t m
     if (rc) return rc;
     sp.row_flags = b->g->row_flags;
     sp.row_mean = b->g->row_mean;
-    init_cut_kernel<<<1, 256, 0, b->ctx->stream>>>(b->d_cut, cut0);
+    init_cut_kernel<<<(4 + MUSE_CUT_WORDS + 255) / 256, 256, 0, b->ctx->stream>>>(b->d_cut, cut0);
     CU(cudaGetLastError());
     const int64_t n = b->n, pad = n - b->N;
     if (max_lag < 0) max_lag = -1;                          // nothing passes |lag| <= max_lag
@@ -1147,7 +1149,7 @@ static int score_fused(muse_batch *b, const RunArgs &a) {
     CU(launch_screen(b, sp, st));
     b->timing.n_launches += 2;
     CU(cudaEventRecord(b->ev[1], st));
-    CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "cannot be in the result"
+    if (!a.list_only) CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "cannot be in the result"
     const unsigned blocks = (unsigned)((S + 255) / 256);
     survivors_cut_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, b->d_cut, b->d_list, b->d_counters + 2);
     b->timing.n_launches++;
@@ -1198,8 +1200,14 @@ static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
 }
 
 // The exact list was longer than the launch bound: score the rest now that its length is known.
-static int run_fused_overflow(muse_batch *b, int64_t n_exact) {
+// refill: the run skipped the NaN fill of the score array (list_only) and the caller is about to
+// read it as a whole -- fill it and score the complete list again.
+static int run_fused_overflow(muse_batch *b, int64_t n_exact, bool refill) {
     const int64_t S = b->g->size;
+    if (refill) {
+        CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, b->ctx->stream));
+        return score_exact_all(b, 0, b->d_list, n_exact);
+    }
     if (n_exact <= std::min<int64_t>(S, MUSE_EXACT_UB)) return MUSE_OK;
     return score_exact_all(b, 0, b->d_list + MUSE_EXACT_UB, n_exact - MUSE_EXACT_UB);
 }
@@ -1297,7 +1305,7 @@ extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t
             b->timing_pending = 0;
             const unsigned long long *h_n = reinterpret_cast<const unsigned long long *>(b->h_pin);
             if (b->fused_run == 1) {
-                rc = run_fused_overflow(b, (int64_t)h_n[2]);
+                rc = run_fused_overflow(b, (int64_t)h_n[2], true);
                 if (rc) return rc;
                 b->fused_run = 0;
             }
@@ -1350,8 +1358,10 @@ extern "C" int64_t muse_batch_partial_capacity(muse_batch *b, const int32_t *key
 // same stream (ncclAllGather of the records) follows directly.
 // Queues (no synchronisation): scores, filter, device-side top_n of an UNGROUPED run as muse_partial
 // records in device memory, the counters into the pinned mailbox, and the end-of-run event.
-static int queue_topn_records(muse_batch *b, const RunArgs &a, muse_partial *d_out, int64_t capacity) {
+static int queue_topn_records(muse_batch *b, const RunArgs &a_in, muse_partial *d_out, int64_t capacity) {
     static_assert(sizeof(PartialRec) == sizeof(muse_partial), "PartialRec mirrors muse_partial");
+    RunArgs a = a_in;
+    a.list_only = 1;
     const int64_t top_n = a.top_n;
     int rc = run_scores(b, a);
     if (rc) return rc;
@@ -1363,7 +1373,13 @@ static int queue_topn_records(muse_batch *b, const RunArgs &a, muse_partial *d_o
         Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
         GroupTable gt;
         memset(&gt, 0, sizeof(gt));
-        emit_candidates_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(gt, nullptr, b->d_score, b->d_lag, S, f, cand);
+        if (b->fused_run == 1) {
+            // only the listed series have scores: filter those (the list's length stays on the device)
+            const int64_t lim = std::min<int64_t>(S, MUSE_EXACT_UB);
+            emit_listed_kernel<<<(unsigned)((lim + 255) / 256), 256, 0, st>>>(b->d_list, b->d_counters + 2, lim, b->d_score, b->d_lag, f, cand);
+        } else {
+            emit_candidates_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(gt, nullptr, b->d_score, b->d_lag, S, f, cand);
+        }
         b->timing.n_launches++;
     }
     // the grid covers MUSE_PARTIAL_RANK_CAP candidates; blocks past the real count (device side) leave at once

@@ -42,9 +42,10 @@ typedef cx<float> cf;
 // the slack.  Rows beyond it are flagged once per store by row_offset_flags_kernel (a register for
 // the mean across the FFT costs this kernel 5 %) and always go to the exact kernel.
 #define MUSE_SCREEN_OFFSET_MAX 1e8
-// running cut-off: lower bounds are counted in MUSE_CUT_BINS bins of [0, 1], MUSE_CUT_COARSE groups of 64
-#define MUSE_CUT_BINS 4096
-#define MUSE_CUT_COARSE 64
+// running cut-off: lower bounds are counted in MUSE_CUT_BINS = 64^3 bins of [0, 1] (3.8e-6 wide, far below the
+// 2e-4 slack), with 64^2 and 64 group counters above them (MUSE_CUT_WORDS counters in all)
+#define MUSE_CUT_BINS 262144
+#define MUSE_CUT_WORDS (64 + 64 * 64 + MUSE_CUT_BINS)
 
 struct ScreenParams {
     const double *slab;
@@ -61,7 +62,7 @@ struct ScreenParams {
     const unsigned char *row_flags;   // [count] 1: |mean| > MUSE_SCREEN_OFFSET_MAX * std (row_offset_flags_kernel): never bounded here
     const double *row_mean;           // [count] fp64 mean of each row (same kernel, once per appended row)
     unsigned *cut_bits;   // running lower bound on the final top-N cut-off (float bits, only ever raised)
-    unsigned *cut_hist;   // [MUSE_CUT_COARSE] coarse counts, then [MUSE_CUT_BINS] fine counts of lower bounds
+    unsigned *cut_hist;   // [MUSE_CUT_WORDS] 64 coarse, 64*64 middle, 64^3 fine counts of lower bounds
     unsigned long long *n_refined;
     int top_n;            // series needed above the cut before it may rise
     int win_lo, win_len;  // lag window in the kernel's rotated cc index: (idx - win_lo) mod n <= win_len
@@ -135,57 +136,47 @@ __device__ __forceinline__ void mbar_test(unsigned bar, unsigned parity) {
 // Warp-collective: count the certain lower bound L of a series that certainly passes the filter and
 // try to raise the running cut-off to the top_n-th largest lower bound counted so far.  All counts
 // only grow, so every value read is a lower bound on the true count and any cut-off derived from
-// them stays valid; lanes walk the bins from the top down (64 coarse groups, then the 64 fine bins
-// of the group in which the count reaches top_n).
+// them stays valid; lanes walk the counters from the top down, three levels of 64.
+// One level of the walk: lanes read the 64 counters of a group from the top down (two per lane), find the
+// counter in which the running count reaches `need`, and return its index within the group (-1: the
+// group does not hold enough); `need` is reduced by what lies above that counter.
+__device__ __forceinline__ int cut_level(const unsigned *cnt, int t, unsigned &need) {
+    const unsigned h = ld_relaxed_u32(&cnt[63 - 2 * t]), l = ld_relaxed_u32(&cnt[62 - 2 * t]);
+    unsigned incl = h + l;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (t >= off) incl += o;
+    }
+    const unsigned excl = incl - (h + l);
+    const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
+    if (!hit) return -1;
+    const int leader = __ffs(hit) - 1;
+    const bool upper = excl + h >= need;
+    const int idx = upper ? 63 - 2 * t : 62 - 2 * t;
+    const unsigned above = upper ? excl : excl + h;
+    need -= __shfl_sync(0xffffffffu, above, leader);
+    return __shfl_sync(0xffffffffu, idx, leader);
+}
+
 __device__ __forceinline__ void cut_count_and_raise(const ScreenParams &prm, float L, int t) {
     int bin = (int)(L * (float)MUSE_CUT_BINS);
     bin = bin < 0 ? 0 : (bin >= MUSE_CUT_BINS ? MUSE_CUT_BINS - 1 : bin);
-    unsigned *coarse = prm.cut_hist, *fine = prm.cut_hist + MUSE_CUT_COARSE;
+    unsigned *coarse = prm.cut_hist, *mid = coarse + 64, *fine = mid + 64 * 64;
     if (t == 0) {
         atomicAdd(&fine[bin], 1u);
-        atomicAdd(&coarse[bin >> 6], 1u);
+        atomicAdd(&mid[bin >> 6], 1u);
+        atomicAdd(&coarse[bin >> 12], 1u);
     }
     __syncwarp();
-    int cbin = -1;
     unsigned need = (unsigned)prm.top_n;
-    {
-        const unsigned h = ld_relaxed_u32(&coarse[63 - 2 * t]), l = ld_relaxed_u32(&coarse[62 - 2 * t]);
-        unsigned incl = h + l;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
-            if (t >= off) incl += o;
-        }
-        const unsigned excl = incl - (h + l);
-        const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
-        if (hit) {
-            const int leader = __ffs(hit) - 1;
-            const bool upper = excl + h >= need;
-            const int cb = upper ? 63 - 2 * t : 62 - 2 * t;
-            const unsigned above = upper ? excl : excl + h;
-            cbin = __shfl_sync(0xffffffffu, cb, leader);
-            need -= __shfl_sync(0xffffffffu, above, leader);
-        }
-    }
-    if (cbin >= 0) {
-        const unsigned *f = fine + cbin * 64;
-        const unsigned h = ld_relaxed_u32(&f[63 - 2 * t]), l = ld_relaxed_u32(&f[62 - 2 * t]);
-        unsigned incl = h + l;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
-            if (t >= off) incl += o;
-        }
-        const unsigned excl = incl - (h + l);
-        const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);
-        if (hit) {
-            const int leader = __ffs(hit) - 1;
-            if (t == leader) {
-                const int fb = cbin * 64 + (excl + h >= need ? 63 - 2 * t : 62 - 2 * t);
-                atomicMax(prm.cut_bits, __float_as_uint((float)fb / (float)MUSE_CUT_BINS));
-            }
-        }
-    }
+    const int c = cut_level(coarse, t, need);
+    if (c < 0) return;
+    const int m = cut_level(mid + c * 64, t, need);
+    if (m < 0) return;                  // the three levels are incremented separately: a reader may see them out of step
+    const int f = cut_level(fine + (c * 64 + m) * 64, t, need);
+    if (f < 0) return;
+    if (t == 0) atomicMax(prm.cut_bits, __float_as_uint((float)((c * 64 + m) * 64 + f) / (float)MUSE_CUT_BINS));
 }
 
 // Refined decision for one series from the fp32 maxima of |cc| inside / outside the lag window

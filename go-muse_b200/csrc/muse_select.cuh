@@ -172,6 +172,36 @@ __global__ void emit_candidates_kernel(GroupTable gt, const int64_t *__restrict_
     }
 }
 
+// Emit candidates from a LIST of series (the fused path's exact list): entry i < min(*n_list, limit) is a
+// series with an exact score; the ones that pass results.go:46-52 are appended like emit_candidates_kernel does.
+__global__ void emit_listed_kernel(const int32_t *__restrict__ list, const unsigned long long *__restrict__ n_list,
+                                   long long limit, const double *__restrict__ score, const int32_t *__restrict__ lag,
+                                   FilterArgs f, Cand out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n = *n_list;
+    bool emit = false;
+    double sc = 0.0;
+    int32_t idx = 0;
+    if (i < limit && (unsigned long long)i < n) {
+        idx = list[i];
+        sc = score[idx];
+        emit = (sc == sc) && (!f.apply || passed(f, sc, lag[idx]));
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(out.n, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (emit) {
+        const unsigned long long pos = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+        out.key[pos] = score_bits(sc);
+        out.idx[pos] = idx;
+        out.lagsgn[pos] = 2 * lag[idx] + (sc < 0.0 ? 1 : 0);
+    }
+}
+
 // ---- device-side top-N of a short candidate list, written as muse_partial records ------
 // Rank by counting: candidate i's position in the (|score| desc, index asc) order is the number of
 // candidates that come before it; those with a position < top_n write their own muse_partial
