@@ -15,11 +15,8 @@
 //     consecutive addresses); the NEXT row of the block is pulled into L2 by one
 //     cp.async.bulk.prefetch.L2 at the top of the iteration, so the DRAM latency is paid under the
 //     previous series' FFT and the loads themselves hit L2;
-//   * centring: the whole row does not fit in registers as fp64 next to the fp32 FFT data, so the
-//     samples are converted as (y - pivot), pivot = the fp64 mean of the first 2T samples (one block
-//     reduction), and the fp64 mean of (y - pivot) is subtracted in fp32.  The rounding is then
-//     relative to |y - pivot| <= |y - mean| + |mean - pivot|, and |mean - pivot| <= std*sqrt(N/(2T)) = 4.5 std,
-//     which costs a factor below 6 on the 6e-8 input term of the error budget in muse_screen.cuh.
+//   * centring: the fp64 mean of every row is computed once at ingest (row_offset_flags_kernel), so the
+//     samples are converted as (float)(y - mean) on the way in and no block reduction precedes the transform.
 #pragma once
 
 #include "muse_screen.cuh"
@@ -62,18 +59,6 @@ __device__ __forceinline__ void l2_prefetch(const void *p, unsigned bytes) {
 }
 
 // Block-wide sums / maxima: every thread returns the same value (same order of operations).
-template <int NWARP>
-__device__ __forceinline__ double block_sum_d(double x, double *red, int tid) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-    if ((tid & 31) == 0) red[tid >> 5] = x;
-    __syncthreads();
-    double s = red[0];
-#pragma unroll
-    for (int w = 1; w < NWARP; w++) s += red[w];
-    __syncthreads();
-    return s;
-}
 template <int NWARP>
 __device__ __forceinline__ float2 block_sum_f2(float a, float b, float2 *red, int tid) {
 #pragma unroll
@@ -165,7 +150,6 @@ score_screen_block_kernel(const ScreenParams prm) {
     using G = typename C::G;
     constexpr int P = C::P, M = G::M, T = C::T, NW = C::NWARP, LP = C::LOG2P;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double red_d[NW];
     __shared__ float2 red_f[NW];
     __shared__ unsigned bc_word[2];                  // running cut-off and row flag, broadcast by thread 0
     cf *sm = reinterpret_cast<cf *>(smem_raw);
@@ -176,7 +160,6 @@ score_screen_block_kernel(const ScreenParams prm) {
     const int pm = M + (M >> LP) - t - ((t + P - 1) >> LP);   // pad(M - t) for t >= 1 (t = 0 pairs bin 0 with itself)
     const int N = prm.N;
     const int Nh = N >> 1;
-    const int nz = (Nh + T - 1) / T;                 // rows of T complex slots that hold samples
     const int count = (int)prm.count;
     const unsigned row_bytes = (unsigned)N * 8u;
 
@@ -189,41 +172,24 @@ score_screen_block_kernel(const ScreenParams prm) {
             flag_raw = prm.row_flags[pos];
         }
 
-        // ---- (y - pivot) -> fp32 registers, fp64 sum of (y - pivot); pivot = fp64 mean of the first 2T
-        //      samples.  Loads go out in batches of 8 rows (8 x 16 bytes in flight per thread) ahead of
-        //      their use; the first batch is issued before the pivot's block reduction ----
+        // ---- centred samples -> fp32 registers.  The fp64 mean comes from the ingest pass
+        //      (row_offset_flags_kernel), so there is no block reduction before the transform; loads go
+        //      out in batches of 8 rows (8 x 16 bytes in flight per thread) ahead of their use ----
+        const double mu = prm.row_mean[pos];
         cf v[P];
-        double s0 = 0.0, s1 = 0.0, pivot = 0.0;
+        cf ss2{0.f, 0.f};
 #pragma unroll
         for (int b0 = 0; b0 < P; b0 += 8) {              // P is 8, 16 or 32
             cd x[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const int j = t + (b0 + q) * T;
-                x[q] = j < Nh ? load_pair_stream(rowp + 2 * j) : cd{0.0, 0.0};
+                x[q] = j < Nh ? load_pair_stream(rowp + 2 * j) : cd{mu, mu};
             }
-            if (b0 == 0) pivot = block_sum_d<NW>(x[0].x + x[0].y, red_d, t) / (double)(2 * T);   // Nh > M/2 >= T: row 0 is all samples
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                const int j = t + (b0 + q) * T;
-                cf val{0.f, 0.f};
-                if (j < Nh) {
-                    const double dx = x[q].x - pivot, dy = x[q].y - pivot;
-                    s0 += dx;
-                    s1 += dy;
-                    val = cf{(float)dx, (float)dy};
-                }
-                v[b0 + q] = val;
-            }
-        }
-        const double dmean = block_sum_d<NW>(s0 + s1, red_d, t) / (double)N;   // mean - pivot
-        const float mf = (float)dmean;
-        cf ss2{0.f, 0.f};
-#pragma unroll
-        for (int r = 0; r < P; r++) {
-            if (r < nz && t + r * T < Nh) {
-                v[r] = cf{v[r].x - mf, v[r].y - mf};
-                ss2 = pfma(v[r], v[r], ss2);
+                v[b0 + q] = cf{(float)(x[q].x - mu), (float)(x[q].y - mu)};      // exactly 0 in the padding
+                ss2 = pfma(v[b0 + q], v[b0 + q], ss2);
             }
         }
 
