@@ -96,9 +96,8 @@ struct muse_group {
     int32_t *labels;    // [nkeys][cap]
     int32_t max_id[16];
     int64_t global_offset;
-    unsigned char *row_flags;   // [cap] screening: rows whose offset dwarfs their spread (filled lazily up to flags_upto)
-    double *row_mean;           // [cap] fp64 mean of each row (same pass)
-    int64_t flags_cap, flags_upto;
+    RowStat *row_stat;          // [cap] screening: fp64 mean and fp32 1/std of each row (filled lazily up to stats_upto)
+    int64_t stats_cap, stats_upto;
 };
 
 struct muse_batch : RunScratch {
@@ -252,8 +251,7 @@ extern "C" void muse_group_destroy(muse_group *g) {
     cudaSetDevice(g->ctx->device);
     if (g->slab) cudaFree(g->slab);
     if (g->labels) cudaFree(g->labels);
-    if (g->row_flags) cudaFree(g->row_flags);
-    if (g->row_mean) cudaFree(g->row_mean);
+    if (g->row_stat) cudaFree(g->row_stat);
     delete g;
 }
 
@@ -449,7 +447,7 @@ extern "C" int muse_group_clear(muse_group *g) {
     CU(cudaSetDevice(g->ctx->device));
     CU(cudaStreamSynchronize(g->ctx->stream));
     g->size = 0;
-    g->flags_upto = 0;
+    g->stats_upto = 0;
     for (int k = 0; k < 16; k++) g->max_id[k] = -1;
     return MUSE_OK;
 }
@@ -1015,24 +1013,21 @@ static int ensure_lower(muse_batch *b) {
     return MUSE_OK;
 }
 
-// Per-row offset flags of the store, computed once for rows appended since the last screened run.
-static int refresh_row_flags(muse_group *g) {
-    if (g->flags_cap < g->cap) {
-        if (g->row_flags) cudaFree(g->row_flags);
-        if (g->row_mean) cudaFree(g->row_mean);
-        g->row_flags = nullptr;
-        g->row_mean = nullptr;
-        CU(cudaMalloc(&g->row_flags, (size_t)g->cap));
-        CU(cudaMalloc(&g->row_mean, sizeof(double) * (size_t)g->cap));
-        g->flags_cap = g->cap;
-        g->flags_upto = 0;
+// Per-row statistics of the store (RowStat), computed once for rows appended since the last screened run.
+static int refresh_row_stats(muse_group *g) {
+    if (g->stats_cap < g->cap) {
+        if (g->row_stat) cudaFree(g->row_stat);
+        g->row_stat = nullptr;
+        CU(cudaMalloc(&g->row_stat, sizeof(RowStat) * (size_t)g->cap));
+        g->stats_cap = g->cap;
+        g->stats_upto = 0;
     }
-    if (g->flags_upto < g->size) {
-        const int64_t count = g->size - g->flags_upto;
+    if (g->stats_upto < g->size) {
+        const int64_t count = g->size - g->stats_upto;
         const unsigned grid = (unsigned)std::min<int64_t>((count + 7) / 8, (int64_t)g->ctx->sm_count * 16);
-        row_offset_flags_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, (int)g->N, g->flags_upto, count, g->row_flags, g->row_mean);
+        row_stats_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, (int)g->N, g->stats_upto, count, g->row_stat);
         CU(cudaGetLastError());
-        g->flags_upto = g->size;
+        g->stats_upto = g->size;
     }
     return MUSE_OK;
 }
@@ -1050,8 +1045,7 @@ static ScreenParams screen_params(muse_batch *b) {
     sp.out_U = b->d_U;
     sp.sx = b->sx_f;
     sp.x_mid = b->x_mid;
-    sp.row_flags = b->g->row_flags;
-    sp.row_mean = b->g->row_mean;
+    sp.row_stat = b->g->row_stat;
     sp.cut_bits = b->d_cut;
     sp.n_refined = reinterpret_cast<unsigned long long *>(b->d_cut + 2);
     sp.cut_hist = b->d_cut + 4;
@@ -1068,10 +1062,9 @@ __global__ void init_cut_kernel(unsigned *state, float cut0) {
 
 static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t max_lag, int64_t top_n, double threshold) {
     if (!screen_is_fused(b->log2m)) return MUSE_OK;
-    int rc = refresh_row_flags(b->g);
+    int rc = refresh_row_stats(b->g);
     if (rc) return rc;
-    sp.row_flags = b->g->row_flags;
-    sp.row_mean = b->g->row_mean;
+    sp.row_stat = b->g->row_stat;
     init_cut_kernel<<<(4 + MUSE_CUT_WORDS + 255) / 256, 256, 0, b->ctx->stream>>>(b->d_cut, cut0);
     CU(cudaGetLastError());
     const int64_t n = b->n, pad = n - b->N;

@@ -47,6 +47,17 @@ typedef cx<float> cf;
 #define MUSE_CUT_BINS 262144
 #define MUSE_CUT_WORDS (64 + 64 * 64 + MUSE_CUT_BINS)
 
+// Per-row statistics of the store, computed once per appended row (the batched mean/std kernel of the
+// z-normalisation, xcorr.go:84-95): the fp64 mean, and 1/std in fp32 -- or NaN when no fp32 statement may be
+// made about the row (constant row, variance outside [MUSE_SCREEN_VAR_MIN, MUSE_SCREEN_VAR_MAX], non-finite
+// samples, |mean| > MUSE_SCREEN_OFFSET_MAX * std): the NaN propagates into the bound and sends the series to
+// the exact kernel.
+struct alignas(16) RowStat {
+    double mean;
+    float rstd;
+    unsigned pad;
+};
+
 struct ScreenParams {
     const double *slab;
     int64_t ld;
@@ -59,8 +70,7 @@ struct ScreenParams {
     const float4 *sx;     // (Xt[k].x, Xt[k].y, Xt[M-k].x, Xt[M-k].y) in fp32, k < M/2 (Xt = X/(2n))
     cf x_mid;             // Xt[M/2]
     float *out_L;         // [count] certain lower bound on a score that certainly passes the lag filter, else -1
-    const unsigned char *row_flags;   // [count] 1: |mean| > MUSE_SCREEN_OFFSET_MAX * std (row_offset_flags_kernel): never bounded here
-    const double *row_mean;           // [count] fp64 mean of each row (same kernel, once per appended row)
+    const RowStat *row_stat;          // [count] fp64 mean and fp32 1/std of each row (row_stats_kernel, once per appended row)
     unsigned *cut_bits;   // running lower bound on the final top-N cut-off (float bits, only ever raised)
     unsigned *cut_hist;   // [MUSE_CUT_WORDS] 64 coarse, 64*64 middle, 64^3 fine counts of lower bounds
     unsigned long long *n_refined;
@@ -199,10 +209,11 @@ __device__ __forceinline__ float refine_decide(float U, float s_in, float s_out,
     return fminf(U, u32);
 }
 
-// flags[i] = 1 when row first+i has |mean| > MUSE_SCREEN_OFFSET_MAX * std (std > 0).  One warp per row;
-// sums are taken about the row's first sample so that the one-pass variance does not cancel.
-__global__ void row_offset_flags_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
-                                        unsigned char *__restrict__ flags, double *__restrict__ means) {
+// RowStat of rows first .. first+count-1.  One warp per row; sums are taken about the row's first sample so
+// that the one-pass variance does not cancel (|row[0] - mean| <= sqrt(N-1) * std, so the cancellation costs at
+// most a factor N of the 1e-16).
+__global__ void row_stats_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
+                                 RowStat *__restrict__ stat) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -223,8 +234,13 @@ __global__ void row_offset_flags_kernel(const double *__restrict__ slab, int64_t
         if (lane == 0) {
             const double mean = pivot + s1 / N;
             const double var = (s2 - s1 * s1 / N) / (N - 1);
-            flags[first + i] = (var > 0.0 && mean * mean > MUSE_SCREEN_OFFSET_MAX * MUSE_SCREEN_OFFSET_MAX * var) ? 1 : 0;
-            means[first + i] = mean;
+            const bool ok = var >= (double)MUSE_SCREEN_VAR_MIN && var <= (double)MUSE_SCREEN_VAR_MAX &&
+                            mean * mean <= MUSE_SCREEN_OFFSET_MAX * MUSE_SCREEN_OFFSET_MAX * var;      // false for NaN / Inf
+            RowStat r;
+            r.mean = mean;
+            r.rstd = ok ? (float)(1.0 / sqrt(var)) : __int_as_float(0x7fc00000);
+            r.pad = 0u;
+            stat[first + i] = r;
         }
     }
 }
@@ -332,30 +348,25 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
         // running cut-off: one lane reads it (so that the whole warp takes the same branch below) at
         // the top of the iteration; the value is consumed only after U is known, a thousand
         // instructions later, so the L2 round trip stays off the critical path.  +inf = no refinement
-        unsigned cut_raw = 0u, flag_raw = 0u;
-        if (t == 0) {
-            cut_raw = ld_relaxed_u32(prm.cut_bits);
-            flag_raw = prm.row_flags[pos];      // not combined here: any use of the values would wait for the loads
-        }
-        const double mu = prm.row_mean[pos];    // fp64 mean from the ingest pass (xcorr.go:85-86); in flight with the row
+        unsigned cut_raw = 0u;
+        if (t == 0) cut_raw = ld_relaxed_u32(prm.cut_bits);
+        const RowStat rs = prm.row_stat[pos];   // fp64 mean and 1/std from the ingest pass (xcorr.go:84-95); in flight with the row
+        const double mu = rs.mean;
         mbar_wait(bar, phase);      // every lane waits itself (one polling lane + __syncwarp measured 3x slower)
 
         // ---- centred samples in fp32 straight from the row buffer ----
         cf v[P];
-        cf ss2{0.f, 0.f};
 #pragma unroll
         for (int r = 0; r < P; r++) {
             if (r < NZ) {
                 const cd x = (r == NZ - 1 && !last_in) ? cd{mu, mu} : rowc[t + r * 32];
                 v[r] = cf{(float)(x.x - mu), (float)(x.y - mu)};
-                ss2 = pfma(v[r], v[r], ss2);
             } else {
                 v[r] = cf{0.f, 0.f};
             }
         }
         __syncwarp();                       // the row is consumed: the buffer becomes the exchange buffer
         const int next = pos + stride;      // < 2^31: the launcher keeps count + stride below it
-        const float ss = group_sum_f<32>(ss2.x + ss2.y);
 
         // ---- forward FFT_1024: pruned radix-32, twiddle, exchange through smem, radix-32 ----
         Dft32Lead<NZ, float>::run(v);
@@ -405,25 +416,17 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
         }
         acc = group_sum_f<32>(acc);
 
-        const float var = ss / (float)(N - 1);
-        float U;
-        if (!(var >= MUSE_SCREEN_VAR_MIN) || !(var <= MUSE_SCREEN_VAR_MAX) || !(acc == acc)) {
-            // constant series (every y - mean rounds to 0; exact score 0), or a variance outside
-            // the window in which fp32 squares neither flush nor overflow, or NaN/Inf samples:
-            // the exact kernel decides
-            U = 2.f;
-        } else {
-            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
-            if (!(U == U)) U = 2.f;
-        }
+        // rstd is NaN for a row no fp32 statement may be made about (RowStat); NaN/Inf samples make acc NaN:
+        // either way the bound is NaN and the exact kernel decides
+        float U = acc * rs.rstd * 1.00001f + MUSE_SCREEN_SLACK;
+        if (!(U == U)) U = 2.f;
         float L = -1.f;
-        // The two broadcasts must not be scheduled before this point: they would wait for the loads
-        // issued at the top of the iteration (measured: +8 % kernel time).  Their source lane
+        // The broadcast must not be scheduled before this point: it would wait for the load
+        // issued at the top of the iteration (measured: +8 % kernel time).  Its source lane
         // therefore depends on acc, which exists only now; it is 0 unless acc has one particular
         // NaN pattern, and then lane 1's zeros merely send the series through the refinement.
         const int bsrc = (__float_as_uint(acc) == 0x7fc12345u) ? 1 : 0;
         const float cut_now = __uint_as_float(__shfl_sync(0xffffffffu, cut_raw, bsrc));
-        if (__shfl_sync(0xffffffffu, flag_raw, bsrc)) U = 2.f;   // offset too large against the spread for any fp32 statement: the exact kernel decides
         if (U >= cut_now && U < 1.5f) {      // warp-uniform: U comes out of a butterfly reduction
             // ---- conj(Y)*X on the mirror pairs of the split (pointwise_pair), in place:
             //      Z'[k] -> own slot j;  Z'[M-k] -> the partner's slot 31-j (lane 0: its own slot 32-j) ----
@@ -499,7 +502,7 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
                 m_in = fmaxf(m_in, __shfl_xor_sync(0xffffffffu, m_in, off));
                 m_out = fmaxf(m_out, __shfl_xor_sync(0xffffffffu, m_out, off));
             }
-            const float rstd = rsqrtf(var);
+            const float rstd = rs.rstd;
             const float s_in = m_in * rstd, s_out = m_out * rstd;
             U = refine_decide(U, s_in, s_out, L, prm.grouped);
             if (t == 0) atomicAdd(prm.n_refined, 1ull);

@@ -15,7 +15,7 @@
 //     consecutive addresses); the NEXT row of the block is pulled into L2 by one
 //     cp.async.bulk.prefetch.L2 at the top of the iteration, so the DRAM latency is paid under the
 //     previous series' FFT and the loads themselves hit L2;
-//   * centring: the fp64 mean of every row is computed once at ingest (row_offset_flags_kernel), so the
+//   * centring: the fp64 mean and 1/std of every row are computed once at ingest (row_stats_kernel), so the
 //     samples are converted as (float)(y - mean) on the way in and no block reduction precedes the transform.
 #pragma once
 
@@ -151,7 +151,7 @@ score_screen_block_kernel(const ScreenParams prm) {
     constexpr int P = C::P, M = G::M, T = C::T, NW = C::NWARP, LP = C::LOG2P;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ float2 red_f[NW];
-    __shared__ unsigned bc_word[2];                  // running cut-off and row flag, broadcast by thread 0
+    __shared__ unsigned bc_word[1];                  // running cut-off, broadcast by thread 0
     cf *sm = reinterpret_cast<cf *>(smem_raw);
 
     const int t = threadIdx.x;
@@ -165,19 +165,18 @@ score_screen_block_kernel(const ScreenParams prm) {
 
     for (int pos = blockIdx.x; pos < count; pos += gridDim.x) {
         const double *rowp = prm.slab + (int64_t)pos * prm.ld;
-        unsigned cut_raw = 0u, flag_raw = 0u;
+        unsigned cut_raw = 0u;
         if (t == 0) {
             if (pos + (int)gridDim.x < count) l2_prefetch(prm.slab + (int64_t)(pos + (int)gridDim.x) * prm.ld, row_bytes);
             cut_raw = ld_relaxed_u32(prm.cut_bits);
-            flag_raw = prm.row_flags[pos];
         }
 
         // ---- centred samples -> fp32 registers.  The fp64 mean comes from the ingest pass
-        //      (row_offset_flags_kernel), so there is no block reduction before the transform; loads go
+        //      (row_stats_kernel), so there is no block reduction before the transform; loads go
         //      out in batches of 8 rows (8 x 16 bytes in flight per thread) ahead of their use ----
-        const double mu = prm.row_mean[pos];
+        const RowStat rs = prm.row_stat[pos];
+        const double mu = rs.mean;
         cf v[P];
-        cf ss2{0.f, 0.f};
 #pragma unroll
         for (int b0 = 0; b0 < P; b0 += 8) {              // P is 8, 16 or 32
             cd x[8];
@@ -189,7 +188,6 @@ score_screen_block_kernel(const ScreenParams prm) {
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 v[b0 + q] = cf{(float)(x[q].x - mu), (float)(x[q].y - mu)};      // exactly 0 in the padding
-                ss2 = pfma(v[b0 + q], v[b0 + q], ss2);
             }
         }
 
@@ -231,19 +229,14 @@ score_screen_block_kernel(const ScreenParams prm) {
             const cf q = pmul(z, z);
             acc = fmaf(sqrt_approx(q.x + q.y), 2.f * prm.a_mid, acc);
             bc_word[0] = cut_raw;
-            bc_word[1] = flag_raw;
         }
-        const float2 sums = block_sum_f2<NW>(acc, ss2.x + ss2.y, red_f, t);   // barrier inside: bc_word is visible
+        const float2 sums = block_sum_f2<NW>(acc, 0.f, red_f, t);   // barrier inside: bc_word is visible
         acc = sums.x;
-        const float var = sums.y / (float)(N - 1);
         const float cut_now = __uint_as_float(bc_word[0]);
-        float U;
-        if (!(var >= MUSE_SCREEN_VAR_MIN) || !(var <= MUSE_SCREEN_VAR_MAX) || !(acc == acc) || bc_word[1]) {
-            U = 2.f;                                               // see score_screen_warp_kernel
-        } else {
-            U = acc * rsqrtf(var) * 1.00001f + MUSE_SCREEN_SLACK;
-            if (!(U == U)) U = 2.f;
-        }
+        // rstd is NaN for a row no fp32 statement may be made about (RowStat); NaN/Inf samples make acc NaN:
+        // either way the bound is NaN and the exact kernel decides
+        float U = acc * rs.rstd * 1.00001f + MUSE_SCREEN_SLACK;
+        if (!(U == U)) U = 2.f;
         float L = -1.f;
         if (U >= cut_now && U < 1.5f) {                            // block-uniform
             // ---- conj(Y)*X on the mirror pairs, in place in shared memory (each pair has one owner) ----
@@ -291,7 +284,7 @@ score_screen_block_kernel(const ScreenParams prm) {
                     m_out = fmaxf(m_out, fmaxf(in0 ? 0.f : a0, in1 ? 0.f : a1));
                 }
             const float2 mx = block_max_f2<NW>(m_in, m_out, red_f, t);
-            const float rstd = rsqrtf(var);
+            const float rstd = rs.rstd;
             U = refine_decide(U, mx.x * rstd, mx.y * rstd, L, prm.grouped);
             if (t == 0) atomicAdd(prm.n_refined, 1ull);
             if (t < 32 && L >= prm.thr && L >= cut_now) cut_count_and_raise(prm, L, t);
