@@ -103,3 +103,42 @@ def test_kernel_phases_on_cpu():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "ALL OK" in out.stdout
+
+
+def test_merge_partials_against_a_model():
+    """muse_merge_partials against a direct Python model on random shard outputs: group max across shards
+    BEFORE the filter (muse_batch.go:87-89), ties by lowest global series index, filter
+    (results.go:46-52), top-N in descending |score| (results.go:81-85); padding and NaN records ignored."""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 2**32 - 1), st.integers(0, 60), st.integers(1, 12), st.integers(0, 12),
+           st.sampled_from([0.0, 0.25, 0.5, 0.75]), st.sampled_from([0, 1, -1]), st.integers(0, 30))
+    def check(seed, n, n_groups, max_lag, thr, sign, top_n):
+        rng = np.random.default_rng(seed)
+        parts = np.zeros(n, dtype=mb.PARTIAL_DTYPE)
+        parts["group_key"] = rng.integers(0, n_groups, n)
+        parts["score"] = rng.choice([0.0, 0.25, 0.5, 0.75, 1.0, -0.5, -0.75, np.nan], n)
+        parts["series_idx"] = rng.permutation(10 * n + 10)[:n]
+        parts["lag"] = rng.integers(-15, 16, n)
+        parts["flags"] = rng.choice([0, 0, 0, 1], n)
+        best = {}
+        for p in parts:
+            if (p["flags"] & 1) or p["score"] != p["score"]:
+                continue
+            q = best.get(int(p["group_key"]))
+            if q is None or abs(p["score"]) > abs(q["score"]) or \
+                    (abs(p["score"]) == abs(q["score"]) and p["series_idx"] < q["series_idx"]):
+                best[int(p["group_key"])] = p
+        keep = [p for p in best.values()
+                if abs(int(p["lag"])) <= max_lag and abs(p["score"]) >= thr and
+                (sign == 0 or (p["score"] > 0 and sign == 1) or (p["score"] < 0 and sign == -1))]
+        keep.sort(key=lambda p: (-abs(p["score"]), int(p["series_idx"])))
+        keep = keep[:top_n]
+        sc, lg, ix = mb.merge_partials(parts, max_lag, top_n, thr, sign)
+        assert ix.tolist() == [int(p["series_idx"]) for p in keep]
+        assert lg.tolist() == [int(p["lag"]) for p in keep]
+        assert sc.tolist() == [float(p["score"]) for p in keep]
+
+    check()
