@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the peer-memory push")
     args = ap.parse_args()
     dflt = {"c3": (1_000_000, 1440, 60), "c4": (1_250_000, 10080, 240)}[args.workload]
     args.series = args.series if args.series is not None else dflt[0]
@@ -218,6 +219,28 @@ def main():
         cols = [0, 1]
     ref = mb.synth_reference(SEED, N)
     batch = mb.DeviceBatch(ctx, store, ref)
+    exchange, exchange_kind = None, None
+    if world > 1:
+        exchange_kind = "nccl-allgather"
+        if not grouped and not args.nccl_exchange:
+            try:
+                exchange = mb.Exchange(ctx, max(1, args.top_n))      # all ranks succeed or all raise
+                exchange_kind = "nvlink-peer-push"
+            except mb.MuseError as e:
+                if rank == 0:
+                    print("bench: %s -> NCCL all-gather" % e, file=sys.stderr)
+
+    def exchange_step(b):
+        # the selection kernel stores the shard's top_n into every rank's receive buffer over NVLink peer
+        # memory and releases a flag; one call = scores, push, wait for the peers, merge (same result on every
+        # rank).  None: some shard's candidate list was too long for the device-side select -> all ranks take
+        # the NCCL all-gather path together
+        r = exchange.run(b, args.max_lag, args.top_n, args.threshold, 0, mode=mode) if exchange else None
+        if r is None:
+            # the shard's top_n stay on the device, ONE small NCCL all-gather of fixed-size records on the
+            # library's stream, one copy to the host, merge on every rank
+            r = mb.allgather_merge_device(b, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
+        return r
 
     def step():
         if world == 1:
@@ -226,9 +249,7 @@ def main():
             # every group representative of the shard, unfiltered (F2); sizes differ per rank
             parts = batch.run_partial(cols, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
             return mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0)
-        # the shard's top_n stay on the device, ONE small NCCL all-gather of fixed-size records on the
-        # library's stream, one copy to the host, merge on every rank
-        return mb.allgather_merge_device(batch, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
+        return exchange_step(batch)
 
     def barrier():
         if world > 1:
@@ -283,7 +304,7 @@ def main():
             if world == 1:
                 r = b2.run([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)   # Run; results land on the host
             else:
-                r = mb.allgather_merge_device(b2, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
+                r = exchange_step(b2)
             b2.close()
             return r
 
@@ -300,7 +321,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": world * S * N / dt, "unit": UNIT, "h2d_bytes_per_step": int(S * N * 8 + S * 2 * 4 + N * 8),
-               "d2h_bytes_per_step": int(len(out[0]) * 24), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "d2h_bytes_per_step": int(len(out[0]) * 24) if world == 1 else int(world * max(1, args.top_n) * 32), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                "api": "muse_group_clear + muse_group_append(pinned host rows) + muse_batch_create + muse_batch_run"}
         st2.close()
         del host
@@ -342,13 +363,15 @@ def main():
             "data": "synthetic", "config": dict(workload(args), mode_used=used_mode,
                                                 rescored_per_step=n_rescored / max(1, args.steps),
                                                 refined_per_step=n_refined / max(1, args.steps),
-                                                tail_ms=sum(tail_ms) / max(1, len(tail_ms))),
+                                                tail_ms=sum(tail_ms) / max(1, len(tail_ms)), exchange=exchange_kind),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "top": {"score": float(out[0][0]) if len(out[0]) else None, "n": int(len(out[0]))},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if exchange:
+            exchange.close()
         dist.destroy_process_group()
 
 

@@ -1514,6 +1514,169 @@ extern "C" int muse_merge_partials(const muse_partial *parts, int64_t n_parts, i
     return MUSE_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// multi-GPU exchange over NVLink peer memory (one process per GPU)
+// ------------------------------------------------------------------------------------
+struct muse_exchange {
+    muse_ctx *ctx;
+    int rank, world;
+    int64_t capacity;                 // records per rank per step
+    unsigned char *base;              // local buffer: recs[2][world][capacity] then flags[2][world] (IPC-exported)
+    size_t recs_bytes;                // bytes of ONE parity's records
+    unsigned char *peer_base[MUSE_EXCHANGE_MAX_RANKS];   // every rank's buffer as seen from here (own: base)
+    bool opened;
+    unsigned long long epoch;
+    unsigned *d_done;
+    int *d_status;
+    unsigned char *h_recs;            // pinned copy of the local records of one step
+};
+
+static size_t exchange_bytes(int world, int64_t capacity) {
+    return 2 * (size_t)world * (size_t)capacity * sizeof(muse_partial) + 2 * (size_t)world * sizeof(unsigned long long);
+}
+
+extern "C" int muse_exchange_create(muse_ctx *ctx, int32_t rank, int32_t world, int64_t capacity, muse_exchange **out) {
+    if (!ctx || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_exchange_create: NULL argument");
+    if (world < 1 || world > MUSE_EXCHANGE_MAX_RANKS || rank < 0 || rank >= world || capacity < 1)
+        return fail(MUSE_ERR_INVALID_ARG, "muse_exchange_create: rank %d of %d, capacity %lld", rank, world, (long long)capacity);
+    CU(cudaSetDevice(ctx->device));
+    muse_exchange *x = new muse_exchange();
+    memset(x, 0, sizeof(*x));
+    x->ctx = ctx;
+    x->rank = rank;
+    x->world = world;
+    x->capacity = capacity;
+    x->recs_bytes = (size_t)world * (size_t)capacity * sizeof(muse_partial);
+    const size_t bytes = exchange_bytes(world, capacity);
+    CU(cudaMalloc(&x->base, bytes));
+    CU(cudaMemset(x->base, 0, bytes));
+    CU(cudaMalloc(&x->d_done, sizeof(unsigned)));
+    CU(cudaMemset(x->d_done, 0, sizeof(unsigned)));
+    CU(cudaMalloc(&x->d_status, sizeof(int)));
+    CU(cudaMemset(x->d_status, 0, sizeof(int)));
+    CU(cudaHostAlloc((void **)&x->h_recs, x->recs_bytes + 64, cudaHostAllocDefault));
+    x->peer_base[rank] = x->base;
+    x->opened = (world == 1);
+    CU(cudaDeviceSynchronize());
+    *out = x;
+    return MUSE_OK;
+}
+
+extern "C" int muse_exchange_ipc_handle(muse_exchange *x, void *handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!x || !handle64) return fail(MUSE_ERR_INVALID_ARG, "muse_exchange_ipc_handle: NULL argument");
+    CU(cudaSetDevice(x->ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, x->base));
+    memcpy(handle64, &h, sizeof(h));
+    return MUSE_OK;
+}
+
+extern "C" int muse_exchange_open_peers(muse_exchange *x, const void *handles) {
+    if (!x || !handles) return fail(MUSE_ERR_INVALID_ARG, "muse_exchange_open_peers: NULL argument");
+    CU(cudaSetDevice(x->ctx->device));
+    for (int r = 0; r < x->world; r++) {
+        if (r == x->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char *)handles + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer_base[r] = (unsigned char *)p;
+    }
+    x->opened = true;
+    return MUSE_OK;
+}
+
+extern "C" void muse_exchange_destroy(muse_exchange *x) {
+    if (!x) return;
+    cudaSetDevice(x->ctx->device);
+    cudaStreamSynchronize(x->ctx->stream);
+    for (int r = 0; r < x->world; r++)
+        if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+    cudaFree(x->base);
+    cudaFree(x->d_done);
+    cudaFree(x->d_status);
+    if (x->h_recs) cudaFreeHost(x->h_recs);
+    delete x;
+}
+
+// One multi-GPU step of an UNGROUPED run: scores, filter, the shard's top_n pushed into every rank's receive
+// buffer by the selection kernel itself (partial_topn_push_kernel), wait for all the peers' flags, one copy of
+// the gathered records to the host, merge.  Every rank returns the same global result.  MUSE_ERR_UNSUPPORTED
+// ("host path needed") when some shard's candidate list was too long for the device-side select: every rank
+// sees the same marker and can fall back together.
+extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t max_lag, int64_t top_n, double threshold,
+                                       int32_t sign_filter, int32_t mode, double *scores, int64_t *lags, int64_t *series_idx,
+                                       int64_t *n_out) {
+    int rc = check_batch(b);
+    if (rc) return rc;
+    if (!x || !n_out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_exchange: NULL argument");
+    if (x->ctx != b->ctx) return fail(MUSE_ERR_INVALID_ARG, "exchange belongs to another context");
+    if (!x->opened) return fail(MUSE_ERR_INVALID_ARG, "muse_exchange_open_peers has not been called");
+    if (top_n < 0) top_n = 0;
+    if (top_n > x->capacity) return fail(MUSE_ERR_INVALID_ARG, "exchange capacity %lld < top_n %lld", (long long)x->capacity, (long long)top_n);
+    if (top_n > 0 && (!scores || !lags || !series_idx)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_exchange: NULL output");
+    CU(cudaSetDevice(b->ctx->device));
+    *n_out = 0;
+    RunArgs a{nullptr, 0, max_lag, top_n, threshold, sign_filter, mode, 0};
+    a.list_only = 1;
+    rc = run_scores(b, a);
+    if (rc) return rc;
+    const int64_t S = b->g->size;
+    cudaStream_t st = b->ctx->stream;
+    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 2, st));
+    if (S > 0) {
+        FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
+        Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
+        if (b->fused_run == 1) {
+            const int64_t lim = std::min<int64_t>(S, MUSE_EXACT_UB);
+            emit_listed_kernel<<<(unsigned)((lim + 255) / 256), 256, 0, st>>>(b->d_list, b->d_counters + 2, lim, b->d_score, b->d_lag, f, cand);
+        } else {
+            GroupTable gt;
+            memset(&gt, 0, sizeof(gt));
+            emit_candidates_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(gt, nullptr, b->d_score, b->d_lag, S, f, cand);
+        }
+        b->timing.n_launches++;
+    }
+    x->epoch++;
+    const int par = (int)(x->epoch & 1ull);
+    ExchangePeers ex;
+    memset(&ex, 0, sizeof(ex));
+    for (int r = 0; r < x->world; r++) {
+        ex.recs[r] = reinterpret_cast<PartialRec *>(x->peer_base[r] + (size_t)par * x->recs_bytes);
+        ex.flags[r] = reinterpret_cast<unsigned long long *>(x->peer_base[r] + 2 * x->recs_bytes) + (size_t)par * x->world;
+    }
+    ex.world = x->world;
+    ex.rank = x->rank;
+    ex.epoch = x->epoch;
+    ex.done_blocks = x->d_done;
+    const long long exact_bound = b->fused_run == 1 ? (long long)std::min<int64_t>(S, MUSE_EXACT_UB) : -1;
+    const unsigned pblocks = (unsigned)std::min<int64_t>((std::max<int64_t>(S, 1) + 7) / 8, (int64_t)b->ctx->sm_count * 8);
+    partial_topn_push_kernel<<<pblocks, 256, 0, st>>>(b->d_ckey, b->d_cidx, b->d_clag, b->d_counters, (long long)top_n,
+                                                      (long long)b->g->global_offset, exact_bound, (long long)x->capacity, ex);
+    // 2 s at ~2 GHz: a peer that never arrives must not hang the box
+    exchange_wait_kernel<<<1, 32, 0, st>>>(ex.flags[x->rank], x->world, x->epoch, 4000000000ll, x->d_status);
+    b->timing.n_launches += 2;
+    CU(cudaGetLastError());
+    int *h_status = reinterpret_cast<int *>(x->h_recs + x->recs_bytes);
+    CU(cudaMemcpyAsync(x->h_recs, x->peer_base[x->rank] + (size_t)par * x->recs_bytes, x->recs_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_status, x->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(b->h_pin, b->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(b->ev[3], st));
+    b->timing_pending = 1;
+    CU(cudaStreamSynchronize(st));
+    if (*h_status) {
+        CU(cudaMemsetAsync(x->d_status, 0, sizeof(int), st));
+        return fail(MUSE_ERR_CUDA, "muse_batch_run_exchange: a peer did not deliver its records within the time limit");
+    }
+    const muse_partial *recs = reinterpret_cast<const muse_partial *>(x->h_recs);
+    for (int r = 0; r < x->world; r++)
+        if (recs[(size_t)r * x->capacity].flags == 2)
+            return fail(MUSE_ERR_UNSUPPORTED, "host path needed: rank %d's candidate list was too long for the device-side select", r);
+    return muse_merge_partials(recs, (int64_t)x->world * x->capacity, max_lag, top_n, threshold, sign_filter, scores, lags,
+                               series_idx, n_out);
+}
+
 extern "C" int muse_batch_last_timing(const muse_batch *cb, muse_timing *out) {
     if (!cb || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_last_timing: NULL argument");
     muse_batch *b = const_cast<muse_batch *>(cb);

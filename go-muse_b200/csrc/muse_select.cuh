@@ -264,6 +264,104 @@ partial_topn_kernel(const unsigned long long *__restrict__ ckey, const int32_t *
     }
 }
 
+// ---- the same top-N, pushed straight into every GPU's receive buffer over NVLink peer memory ------
+// Multi-GPU exchange fused into the selection: instead of leaving the shard's records in local memory
+// for a collective, every record is stored to slot [rank] of the receive buffer of EVERY rank (peer
+// pointers from cudaIpcOpenMemHandle; 32-byte stores over NVLink / NVSwitch), the last block of the grid
+// fences (system scope) and releases flag[rank] = epoch on every peer.  exchange_wait_kernel then
+// acquires all the flags of the local buffer: when it returns, the records of all shards are local.
+#define MUSE_EXCHANGE_MAX_RANKS 16
+struct ExchangePeers {
+    PartialRec *recs[MUSE_EXCHANGE_MAX_RANKS];            // base of rank r's receive records for this parity: [world][capacity]
+    unsigned long long *flags[MUSE_EXCHANGE_MAX_RANKS];   // rank r's flags for this parity: [world]
+    int world, rank;
+    unsigned long long epoch;
+    unsigned *done_blocks;                                // local: blocks of this launch that have finished
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+partial_topn_push_kernel(const unsigned long long *__restrict__ ckey, const int32_t *__restrict__ cidx,
+                         const int32_t *__restrict__ clag, const unsigned long long *__restrict__ counters, long long top_n,
+                         long long global_offset, long long exact_list_bound, long long capacity, ExchangePeers ex) {
+    const unsigned long long n = counters[0];
+    const bool overflow = n > MUSE_PARTIAL_RANK_CAP || (exact_list_bound >= 0 && counters[2] > (unsigned long long)exact_list_bound);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long take = overflow ? 0 : ((long long)n < top_n ? (long long)n : top_n);
+    const long long slot0 = (long long)ex.rank * capacity;
+    for (long long r = take + gtid; r < capacity; r += (long long)gridDim.x * blockDim.x) {
+        const PartialRec pad{0ull, 0.0, 0ll, 0, (overflow && r == 0) ? 2 : 1};
+        for (int d = 0; d < ex.world; d++) ex.recs[d][slot0 + r] = pad;
+    }
+    if (!overflow) {
+        const int lane = threadIdx.x & 31;
+        const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+        for (unsigned long long i = (unsigned long long)gtid >> 5; i < n; i += nwarps) {
+            const unsigned long long k = ckey[i];
+            const unsigned ix = (unsigned)cidx[i];
+            unsigned before = 0;
+            unsigned long long j = lane;
+            for (; j + 96 < n; j += 128) {
+                const unsigned long long k0 = ckey[j], k1 = ckey[j + 32], k2 = ckey[j + 64], k3 = ckey[j + 96];
+                const unsigned i0 = (unsigned)cidx[j], i1 = (unsigned)cidx[j + 32], i2 = (unsigned)cidx[j + 64], i3 = (unsigned)cidx[j + 96];
+                before += (k0 > k || (k0 == k && i0 < ix)) ? 1u : 0u;
+                before += (k1 > k || (k1 == k && i1 < ix)) ? 1u : 0u;
+                before += (k2 > k || (k2 == k && i2 < ix)) ? 1u : 0u;
+                before += (k3 > k || (k3 == k && i3 < ix)) ? 1u : 0u;
+            }
+            for (; j < n; j += 32) {
+                const unsigned long long kj = ckey[j];
+                before += (kj > k || (kj == k && (unsigned)cidx[j] < ix)) ? 1u : 0u;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
+            if ((long long)before < top_n) {
+                const int ls = clag[i];
+                const double a = __longlong_as_double((long long)k);
+                const long long gi = global_offset + (long long)ix;
+                const PartialRec rec{(unsigned long long)gi, (ls & 1) ? -a : a, gi, (ls - (ls & 1)) / 2, 0};
+                for (int d = lane; d < ex.world; d += 32) ex.recs[d][slot0 + before] = rec;      // one lane per destination
+            }
+        }
+    }
+    // last block of the grid: everything this GPU stored is ordered before the flags it releases
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ex.done_blocks, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if (threadIdx.x < ex.world) st_release_sys_u64(&ex.flags[threadIdx.x][ex.rank], ex.epoch);
+    if (threadIdx.x == 0) *ex.done_blocks = 0u;
+}
+
+// Lane r waits until rank r's flag in the LOCAL buffer has reached `epoch` (bounded spin); status != 0: timed out.
+__global__ void exchange_wait_kernel(const unsigned long long *flags, int world, unsigned long long epoch,
+                                     long long timeout_cycles, int *status) {
+    const int r = threadIdx.x;
+    bool ok = true;
+    if (r < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(&flags[r]) < epoch) {
+            if (clock64() - t0 > timeout_cycles) {
+                ok = false;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    if (!ok) *status = 1;
+}
+
 // ---- radix select of the top_n candidates by (key desc, idx asc) ---------------------
 // 96-bit composite (key, ~idx) examined 16 bits at a time, most significant first.
 // State lives on the device; round r narrows [prefix] and the remaining rank.

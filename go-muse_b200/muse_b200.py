@@ -124,6 +124,12 @@ ABI = {
     "muse_batch_run_partial": (C.c_int, [_vp, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                          C.c_int32, _vp, C.c_int64, _ip64]),
     "muse_batch_run_partial_device": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32, _vp, C.c_int64]),
+    "muse_exchange_create": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.POINTER(_vp)]),
+    "muse_exchange_ipc_handle": (C.c_int, [_vp, _vp]),
+    "muse_exchange_open_peers": (C.c_int, [_vp, _vp]),
+    "muse_exchange_destroy": (None, [_vp]),
+    "muse_batch_run_exchange": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32,
+                                          _dp, _ip64, _ip64, _ip64]),
     "muse_batch_partial_capacity": (C.c_int64, [_vp, _ip32, C.c_int32, C.c_int64]),
     "muse_merge_partials": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                       _dp, _ip64, _ip64, _ip64]),
@@ -748,3 +754,67 @@ def allgather_merge_device(batch: DeviceBatch, max_lag: int, top_n: int, thresho
         parts = batch.run_partial([], max_lag, top_n, threshold, sign_filter, mode=mode)
         return allgather_merge(parts, max_lag, top_n, threshold, sign_filter, fixed_capacity=top_n)
     return merge_partials(allp, max_lag, top_n, threshold, sign_filter)
+
+
+class Exchange:
+    """muse_exchange: the shard's top_n records go into every rank's receive buffer over NVLink peer memory,
+    written by the selection kernel itself (no library collective on the data path).  Setup exchanges the CUDA
+    IPC handles once with torch.distributed (any backend); ranks must call run() the same number of times."""
+
+    def __init__(self, ctx: Context, capacity: int):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.h = _vp()
+        self.capacity = int(capacity)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        # every rank takes every collective below whatever happened locally, and all of them raise together
+        # when any rank failed (CUDA IPC closed in this container, no peer access): callers fall back as one
+        err, mine = None, C.create_string_buffer(64)
+        try:
+            _check(lib().muse_exchange_create(ctx.h, rank, world, self.capacity, C.byref(self.h)))
+            _check(lib().muse_exchange_ipc_handle(self.h, C.cast(mine, _vp)))
+        except MuseError as e:
+            err = str(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, (bytes(mine.raw), err))
+        if all(e is None for _, e in handles):
+            try:
+                blob = C.create_string_buffer(b"".join(h for h, _ in handles), 64 * world)
+                _check(lib().muse_exchange_open_peers(self.h, C.cast(blob, _vp)))
+            except MuseError as e:
+                err = str(e)
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        bad = [(r, e) for r, e in enumerate(errs) if e is not None]
+        if bad:
+            self.close()
+            raise MuseError(MUSE_ERR_UNSUPPORTED, "peer-memory exchange unavailable (rank %d: %s)" % bad[0])
+        dist.barrier()
+
+    def run(self, batch: DeviceBatch, max_lag: int, top_n: int, threshold: float, sign_filter: int = 0,
+            mode: int = MODE_AUTO):
+        """One multi-GPU step; returns the merged (scores, lags, series_idx) -- identical on every rank -- or None
+        when every rank must take the host path (a candidate list too long for the device-side select)."""
+        cap = max(1, int(top_n))
+        sc = np.zeros(cap)
+        lg = np.zeros(cap, dtype=np.int64)
+        ix = np.zeros(cap, dtype=np.int64)
+        n_out = C.c_int64(0)
+        rc = lib().muse_batch_run_exchange(batch.h, self.h, max_lag, top_n, threshold, sign_filter, mode, _d(sc),
+                                           lg.ctypes.data_as(_ip64), ix.ctypes.data_as(_ip64), C.byref(n_out))
+        if rc == MUSE_ERR_UNSUPPORTED:
+            return None
+        _check(rc)
+        k = int(n_out.value)
+        return sc[:k], lg[:k], ix[:k]
+
+    def close(self):
+        if self.h:
+            lib().muse_exchange_destroy(self.h)
+            self.h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -206,6 +206,24 @@ int  muse_batch_run_partial(muse_batch *b, const int32_t *key_cols, int32_t n_ke
  * select -- call muse_batch_run_partial instead.  Timings: muse_batch_last_timing. */
 int  muse_batch_run_partial_device(muse_batch *b, int64_t max_lag, int64_t top_n, double threshold,
                                    int32_t sign_filter, int32_t mode, muse_partial *d_out, int64_t capacity);
+/* ---- multi-GPU exchange over NVLink peer memory (one process per GPU, one box) ------------
+ * The shard's top_n records are stored by the selection kernel itself into the receive buffer of EVERY
+ * rank (peer pointers from CUDA IPC handles), followed by a system-scope flag; a step is then ONE call:
+ * scores, filter, push, wait for the peers, merge -- no library collective and no host code between
+ * the kernels.  Setup: every rank creates an exchange, the ranks swap the 64-byte handles of
+ * muse_exchange_ipc_handle (any out-of-band channel, e.g. an all-gather of bytes), and each calls
+ * muse_exchange_open_peers with the world_size x 64 bytes in rank order.  Ranks must call
+ * muse_batch_run_exchange the same number of times (the steps are matched by an epoch counter).
+ * MUSE_ERR_UNSUPPORTED: some shard's candidate list was too long for the device-side select -- every
+ * rank gets the same answer and can take muse_batch_run_partial + an all-gather instead. */
+typedef struct muse_exchange muse_exchange;
+int  muse_exchange_create(muse_ctx *ctx, int32_t rank, int32_t world_size, int64_t capacity, muse_exchange **out);
+int  muse_exchange_ipc_handle(muse_exchange *x, void *handle64);
+int  muse_exchange_open_peers(muse_exchange *x, const void *handles);
+void muse_exchange_destroy(muse_exchange *x);
+int  muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t max_lag, int64_t top_n, double threshold,
+                             int32_t sign_filter, int32_t mode,
+                             double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
 /* Upper bound on the records run_partial can emit for these arguments. */
 int64_t muse_batch_partial_capacity(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
                                     int64_t top_n);
