@@ -19,6 +19,7 @@
 #include "muse_screen_block.cuh"
 #include "muse_select.cuh"
 #include "muse_synth.cuh"
+#include "muse_xcorr.cuh"
 
 using namespace muse;
 
@@ -1511,6 +1512,92 @@ extern "C" int muse_merge_partials(const muse_partial *parts, int64_t n_parts, i
         series_idx[i] = v[i].series_idx;
     }
     *n_out = (int64_t)v.size();
+    return MUSE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// many reference queries against one resident store (BASELINE.json configs[4])
+// ------------------------------------------------------------------------------------
+// Round-1 form: one NewBatch + Run per reference on the resident slab, inside the library -- the store, its
+// row statistics and the run scratch (context pool) are shared, results of query q land in row q of the
+// outputs.  Every query still streams the slab once (HBM-bound, 2.3 ms per 1 M x 1440 series); the multi-query
+// bound pass that reads the slab once for ALL queries is DESIGN.md section 8's next step.
+extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len,
+                              const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n, double threshold,
+                              int32_t sign_filter, int32_t mode, double *scores, int64_t *lags, int64_t *series_idx,
+                              int64_t *n_out) {
+    if (!ctx || !g || (!refs && n_refs > 0) || !n_out) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_run: NULL argument");
+    if (n_refs < 0 || top_n < 0) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_run: n_refs %lld, top_n %lld", (long long)n_refs, (long long)top_n);
+    if (top_n > 0 && (!scores || !lags || !series_idx)) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_run: NULL output");
+    for (int64_t q = 0; q < n_refs; q++) {
+        muse_batch *b = nullptr;
+        int rc = muse_batch_create(ctx, g, refs + (size_t)q * (size_t)ref_len, ref_len, &b);
+        if (rc == MUSE_ERR_STDDEV_ZERO) {   // muse_batch.go:38-41: this query has no Batch; the others do
+            n_out[q] = -1;
+            continue;
+        }
+        if (rc) return rc;
+        rc = muse_batch_run_ex(b, key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, 0,
+                               scores ? scores + (size_t)q * (size_t)top_n : nullptr, lags ? lags + (size_t)q * (size_t)top_n : nullptr,
+                               series_idx ? series_idx + (size_t)q * (size_t)top_n : nullptr, n_out + q);
+        muse_batch_destroy(b);
+        if (rc) return rc;
+    }
+    return MUSE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// generic xCorr (xcorr.go:102-153): any n, optional z-normalisation
+// ------------------------------------------------------------------------------------
+extern "C" int muse_xcorr(muse_ctx *ctx, const double *x, int64_t x_len, const double *y, int64_t y_len, int64_t n,
+                          int32_t normalize, double *cc, int64_t cc_capacity, int64_t *n_out, int64_t *lag, double *value,
+                          int32_t *std_zero) {
+    if (!ctx || !x || !y || !n_out || !lag || !value) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: NULL argument");
+    if (x_len < 1 || y_len < 1) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: empty input (x %lld, y %lld samples)", (long long)x_len, (long long)y_len);
+    const int64_t nn = std::max(n, std::max(x_len, y_len));   // xcorr.go:104-106
+    if (nn > (1ll << 24)) return fail(MUSE_ERR_UNSUPPORTED, "muse_xcorr: n = %lld above 2^24 (direct evaluation)", (long long)nn);
+    if (cc && cc_capacity < nn) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: cc holds %lld values, n = %lld", (long long)cc_capacity, (long long)nn);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    *n_out = nn;
+    *lag = 0;
+    *value = 0.0;
+    if (std_zero) *std_zero = 0;
+    // one allocation: x, y, xp, yp, cc (doubles), then lag, value, flag
+    const size_t nd = (size_t)x_len + (size_t)y_len + 3 * (size_t)nn;
+    unsigned char *d = nullptr;
+    CU(cudaMalloc(&d, nd * sizeof(double) + 32));
+    double *dx = reinterpret_cast<double *>(d), *dy = dx + x_len, *dxp = dy + y_len, *dyp = dxp + nn, *dcc = dyp + nn;
+    long long *dlag = reinterpret_cast<long long *>(dcc + nn);
+    double *dval = reinterpret_cast<double *>(dlag + 1);
+    int *dflag = reinterpret_cast<int *>(dval + 1);
+    struct Tail { long long lag; double val; int flag; int pad; } tail;
+    auto body = [&]() -> int {
+        CU(cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)x_len, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)y_len, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(dlag, 0, 32, st));
+        xcorr_prepare_kernel<<<2, 256, 0, st>>>(dx, x_len, dy, y_len, nn, normalize ? 1 : 0, dxp, dyp, dflag);
+        // xcorr.go:139-142: gonum's inverse transform is unnormalised (n x the correlation); the reference scales
+        // by 1/(n(n-1)) for z-normalised inputs and by 1/n otherwise -> 1/(n-1) and 1 on a direct sum
+        const double scale = normalize ? 1.0 / (double)(nn - 1) : 1.0;
+        xcorr_direct_kernel<<<(unsigned)((nn + XC_LAGS - 1) / XC_LAGS), XC_LAGS, 0, st>>>(dxp, dyp, nn, scale, dcc);
+        xcorr_argmax_kernel<<<1, 256, 0, st>>>(dcc, nn, dlag, dval);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&tail, dlag, sizeof(tail), cudaMemcpyDeviceToHost, st));
+        if (cc) CU(cudaMemcpyAsync(cc, dcc, sizeof(double) * (size_t)nn, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return MUSE_OK;
+    };
+    const int rc = body();
+    cudaFree(d);
+    if (rc) return rc;
+    if (normalize && tail.flag) {   // xcorr.go:109-126: (nil, 0, 0)
+        if (std_zero) *std_zero = 1;
+        *n_out = 0;
+        return MUSE_OK;
+    }
+    *lag = tail.lag;
+    *value = tail.val;
     return MUSE_OK;
 }
 

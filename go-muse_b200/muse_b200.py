@@ -124,6 +124,10 @@ ABI = {
     "muse_batch_run_partial": (C.c_int, [_vp, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                          C.c_int32, _vp, C.c_int64, _ip64]),
     "muse_batch_run_partial_device": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32, _vp, C.c_int64]),
+    "muse_multi_run": (C.c_int, [_vp, _vp, _dp, C.c_int64, C.c_int64, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double,
+                                 C.c_int32, C.c_int32, _dp, _ip64, _ip64, _ip64]),
+    "muse_xcorr": (C.c_int, [_vp, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int32, _dp, C.c_int64, _ip64, _ip64,
+                             C.POINTER(C.c_double), _ip32]),
     "muse_exchange_create": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.POINTER(_vp)]),
     "muse_exchange_ipc_handle": (C.c_int, [_vp, _vp]),
     "muse_exchange_open_peers": (C.c_int, [_vp, _vp]),
@@ -384,6 +388,41 @@ def merge_partials(parts: np.ndarray, max_lag: int, top_n: int, threshold: float
     return sc[:k], lg[:k], ix[:k]
 
 
+def multi_run(store: "DeviceStore", refs, key_cols: Sequence[int], max_lag: int, top_n: int, threshold: float,
+              sign_filter: int = 0, mode: int = MODE_AUTO):
+    """muse_multi_run: every row of refs as a NewBatch + Run against the resident store.  Returns one
+    (scores, lags, series_idx) triple per reference, None where the reference has zero std."""
+    R = np.ascontiguousarray(refs, dtype=np.float64)
+    assert R.ndim == 2
+    Q, cap = R.shape[0], max(1, int(top_n))
+    kc = np.asarray(list(key_cols), dtype=np.int32)
+    sc = np.zeros((max(Q, 1), cap))
+    lg = np.zeros((max(Q, 1), cap), dtype=np.int64)
+    ix = np.zeros((max(Q, 1), cap), dtype=np.int64)
+    n_out = np.zeros(max(Q, 1), dtype=np.int64)
+    _check(lib().muse_multi_run(store.ctx.h, store.h, _d(R), Q, R.shape[1], kc.ctypes.data_as(_ip32) if kc.size else None,
+                                kc.size, max_lag, top_n, threshold, sign_filter, mode, _d(sc), lg.ctypes.data_as(_ip64),
+                                ix.ctypes.data_as(_ip64), n_out.ctypes.data_as(_ip64)))
+    return [None if n_out[q] < 0 else (sc[q, :n_out[q]].copy(), lg[q, :n_out[q]].copy(), ix[q, :n_out[q]].copy())
+            for q in range(Q)]
+
+
+def xCorr(x, y, n: int, normalize: bool, ctx: Optional[Context] = None):
+    """xcorr.go:102-153 on the device, any n: (cc, lag, value); (None, 0, 0.0) when a normalised input has
+    zero std (:109-126).  n is raised to max(n, len(x), len(y)) (:104-106)."""
+    ctx = ctx or default_context()
+    xa = np.ascontiguousarray(x, dtype=np.float64)
+    ya = np.ascontiguousarray(y, dtype=np.float64)
+    nn = max(int(n), xa.size, ya.size)
+    cc = np.zeros(max(nn, 1))
+    n_out, lag, val, z = C.c_int64(0), C.c_int64(0), C.c_double(0.0), C.c_int32(0)
+    _check(lib().muse_xcorr(ctx.h, _d(xa), xa.size, _d(ya), ya.size, int(n), int(bool(normalize)), _d(cc), cc.size,
+                            C.byref(n_out), C.byref(lag), C.byref(val), C.byref(z)))
+    if z.value:
+        return None, 0, 0.0
+    return cc[:int(n_out.value)], int(lag.value), float(val.value)
+
+
 # ----------------------------------------------------------------------------------
 # go-muse API mirror
 # ----------------------------------------------------------------------------------
@@ -551,6 +590,15 @@ class Score:
     def to_json(self):
         return {"labels": self.Labels.labels if self.Labels else None, "lag": self.Lag,
                 "percentScore": self.PercentScore}
+
+    def MarshalJSON(self) -> str:
+        """What encoding/json writes for the Go struct (scores.go:11-15): keys labels / lag / percentScore in
+        field order; *Labels has only unexported fields (labels.go:14-17), so a non-nil one is `{}`."""
+        import json
+        if self.PercentScore != self.PercentScore or abs(self.PercentScore) == float("inf"):
+            raise ValueError("json: unsupported value: %r" % self.PercentScore)     # as encoding/json
+        return '{"labels":%s,"lag":%d,"percentScore":%s}' % ("{}" if self.Labels is not None else "null", self.Lag,
+                                                           json.dumps(float(self.PercentScore)))
 
 
 class Results:
@@ -766,6 +814,9 @@ class Exchange:
         self.ctx = ctx
         self.h = _vp()
         self.capacity = int(capacity)
+        if not (dist.is_available() and dist.is_initialized()):      # a single process: the push targets only itself
+            _check(lib().muse_exchange_create(ctx.h, 0, 1, self.capacity, C.byref(self.h)))
+            return
         rank, world = dist.get_rank(), dist.get_world_size()
         # every rank takes every collective below whatever happened locally, and all of them raise together
         # when any rank failed (CUDA IPC closed in this container, no peer access): callers fall back as one

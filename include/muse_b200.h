@@ -189,6 +189,27 @@ int  muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t max_lag, fl
  * return value; KAT support).  *std_zero is set when xcorr.go:165-168 applies. */
 int  muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, int32_t *std_zero);
 
+/* Many reference queries against ONE resident store: n_refs x (NewBatch + Batch.Run) (muse_batch.go:23-52,
+ * :99-130) in one call.  refs: host rows [n_refs][ref_len]; outputs: row q of scores / lags / series_idx
+ * (capacity top_n each row) and n_out[q] = results of query q, or -1 when reference q has std == 0
+ * (muse_batch.go:38-41: NewBatch fails for that query only).  Arguments as muse_batch_run_ex. */
+int  muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len,
+                    const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n, double threshold,
+                    int32_t sign_filter, int32_t mode,
+                    double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
+
+/* xCorr(x, y, n, normalize) of xcorr.go:102-153 for ANY n (the FFT kernels above exist for powers of
+ * two; the reference's own KATs use n = 5): n' = max(n, x_len, y_len) (:104-106), optional z-normalisation
+ * of both inputs (:108-127), LEADING zero pads (:128-129), cc[k] = sum_t xp[(t+k) mod n'] * yp[t], divided
+ * by n'-1 when normalised (:139-140 on gonum's unnormalised inverse), arg-max of |cc| with the first index winning and the wrap to
+ * (-n'/2, n'/2] (:145-151).  Evaluated directly in fp64 on the device (a utility, one pair per call).
+ * x, y: host rows.  cc (host, may be NULL): n' values when cc_capacity >= n'.  *n_out = n', or 0 with
+ * *std_zero = 1, *lag = 0, *value = 0 when a normalised input has std == 0 (:109-126, the reference returns
+ * (nil, 0, 0)). */
+int  muse_xcorr(muse_ctx *ctx, const double *x, int64_t x_len, const double *y, int64_t y_len, int64_t n,
+                int32_t normalize, double *cc, int64_t cc_capacity, int64_t *n_out, int64_t *lag, double *value,
+                int32_t *std_zero);
+
 /* ---- multi-GPU: shard-local partials and their merge -------------------------
  * One store per GPU holds a contiguous block of the series (global offset set with
  * muse_group_set_global_offset).  run_partial produces this shard's group

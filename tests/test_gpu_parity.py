@@ -198,6 +198,56 @@ def test_xcorr_vector_kats(ctx, kats):
         assert abs(sc[0] - max(-1.0, min(1.0, want_mv))) <= 1e-12 and lg[0] == want_lag
 
 
+def test_generic_xcorr_kats(ctx, kats):
+    # TestXCorr (xcorr_test.go:86-202): n = 5, normalised and not, a constant input -> (nil, 0, 0)
+    k = kats["x_corr"]
+    for c in k["cases"]:
+        cc, lag, mv = mb.xCorr(c["x"], c["y"], len(c["x"]), c["normalize"], ctx)
+        if c["cc"] is None:
+            assert cc is None and lag == 0 and mv == 0.0
+            continue
+        assert np.max(np.abs(cc - np.array(c["cc"], dtype=float))) <= k["tol"]
+        assert lag == c["lag"] and np.sign(mv) == c["sign"]
+        want_cc, want_lag, want_mv = mo.x_corr(c["x"], c["y"], len(c["x"]), c["normalize"])
+        assert np.max(np.abs(cc - want_cc)) <= 1e-12 and lag == want_lag and abs(mv - want_mv) <= 1e-12
+
+
+@pytest.mark.parametrize("lx,ly,n", [(5, 5, 5), (7, 5, 0), (5, 9, 12), (480, 480, 512), (1000, 1000, 1000),
+                                     (1441, 1440, 2048), (3001, 2999, 3001), (16385, 16385, 32768)])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_generic_xcorr_matches_oracle(ctx, lx, ly, n, normalize):
+    # any n (not only powers of two), inputs of different lengths, n below / at / above the lengths;
+    # the last shape is BenchmarkXCorr's (xcorr_test.go:310-326)
+    rng = np.random.default_rng(lx * 31 + ly * 7 + n)
+    x, y = rng.random(lx), rng.random(ly)
+    y[ly // 3] += 25.0
+    x[lx // 2] += 25.0
+    cc, lag, mv = mb.xCorr(x, y, n, normalize, ctx)
+    want_cc, want_lag, want_mv = mo.x_corr(x, y, n, normalize)
+    assert cc.shape == want_cc.shape
+    scale = max(1.0, float(np.max(np.abs(want_cc))))
+    assert np.max(np.abs(cc - want_cc)) <= SCORE_TOL * scale
+    assert lag == want_lag and abs(mv - want_mv) <= SCORE_TOL * scale
+
+
+def test_generic_xcorr_edge_cases(ctx):
+    # a constant input is only an error when normalising (xcorr.go:108-127)
+    cc, lag, mv = mb.xCorr([3, 3, 3, 3], [0, 1, 0, 0], 4, False, ctx)
+    np.testing.assert_allclose(cc, [3, 3, 3, 3])
+    assert (lag, mv) == (0, 3.0)                     # first index wins the tie (xcorr.go:39-50)
+    assert mb.xCorr([3, 3, 3, 3], [0, 1, 0, 0], 4, True, ctx) == (None, 0, 0.0)
+    assert mb.xCorr([0, 1, 0, 0], [2, 2, 2, 2], 4, True, ctx) == (None, 0, 0.0)
+    # all-zero correlation: index 0, value 0
+    cc, lag, mv = mb.xCorr([0, 0, 0], [1, 2, 3], 3, False, ctx)
+    assert not cc.any() and (lag, mv) == (0, 0.0)
+    # NaN samples never win the arg-max (math.Abs(NaN) > x is false)
+    cc, lag, mv = mb.xCorr([1, 0, 0, 0], [float("nan"), 0, 0, 0], 4, False, ctx)
+    want_cc, want_lag, want_mv = mo.x_corr([1, 0, 0, 0], [float("nan"), 0, 0, 0], 4, False)
+    assert lag == want_lag
+    with pytest.raises(mb.MuseError):
+        mb.xCorr([], [1.0], 4, False, ctx)
+
+
 def test_run_matches_oracle_ungrouped_and_grouped(ctx):
     rng = np.random.default_rng(11)
     S, N = 6000, 480
@@ -360,3 +410,68 @@ def test_c_oracle_agrees_at_larger_size(ctx):
         _, _, ties = mo.score_series_batch(ref, Y[i:i + 1], want_ties=True)
         assert lg[i] in ties[0]
     assert bad.size <= 50
+
+
+def test_peer_memory_exchange_single_rank(ctx):
+    # muse_batch_run_exchange with world_size 1: the selection kernel pushes into its own receive buffer, waits
+    # on its own flag, merges -> must be the plain Run; repeated calls alternate the two buffer parities
+    rng = np.random.default_rng(5)
+    S, N = 20000, 480
+    ref, Y = _siggen(rng, S, N)
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    b = mb.DeviceBatch(ctx, store, ref)
+    ex = mb.Exchange(ctx, 64)
+    for max_lag, top_n, thr in ((15, 50, 0.3), (15, 64, 0.0), (3, 1, 0.9), (15, 50, 0.3), (0, 7, 0.0)):
+        want = b.run([], max_lag, top_n, thr)
+        got = ex.run(b, max_lag, top_n, thr)
+        assert got is not None
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g, w)
+    with pytest.raises(mb.MuseError):
+        ex.run(b, 15, 65, 0.3)                      # above the exchange's capacity
+    ex.close()
+
+
+def test_peer_memory_exchange_two_gpus():
+    # two ranks, one per GPU (skipped on a one-GPU box): tools/exchange_check.py compares the peer-memory push
+    # with the NCCL all-gather path and the host path for several argument sets
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CHECK_SERIES="200000")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "exchange_check.py")],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ALL IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_multi_reference_run_equals_separate_batches(ctx):
+    # muse_multi_run: Q references against one resident store == Q x (NewBatch + Run); a constant reference
+    # fails for itself only (muse_batch.go:38-41)
+    rng = np.random.default_rng(17)
+    S, N, Q = 3000, 480, 5
+    _, Y = _siggen(rng, S, N)
+    refs = np.zeros((Q, N))
+    for q in range(Q):
+        m = int(rng.integers(100, 380))
+        refs[q, m:m + 4 + 2 * q] = 1.0 + q
+        refs[q] += 0.1 * (rng.random(N) - 0.5)
+    refs[3] = 7.0
+    ids = np.stack([np.arange(S) // 30, np.arange(S) % 30], axis=1).astype(np.int32)
+    store = mb.DeviceStore(ctx, N, 2, S)
+    store.append(Y, ids)
+    for cols in ([], [0]):
+        got = mb.multi_run(store, refs, cols, 20, 15, 0.2)
+        assert got[3] is None
+        for q in (0, 1, 2, 4):
+            b = mb.DeviceBatch(ctx, store, refs[q])
+            want = b.run(cols, 20, 15, 0.2)
+            for g, w in zip(got[q], want):
+                np.testing.assert_array_equal(g, w)
+            wsc, wlg, wix = co.batch_run(refs[q], Y, (ids[:, 0] if cols else None), 20, 15, 0.2)
+            assert np.max(np.abs(got[q][0] - wsc), initial=0) <= SCORE_TOL
+            np.testing.assert_array_equal(got[q][1], wlg)
+            np.testing.assert_array_equal(got[q][2], wix)
+            b.close()
