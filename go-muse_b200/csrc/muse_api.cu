@@ -17,6 +17,7 @@
 #include "../../include/muse_b200.h"
 #include "muse_exact.cuh"
 #include "muse_screen_block.cuh"
+#include "muse_screen_multi.cuh"
 #include "muse_select.cuh"
 #include "muse_synth.cuh"
 #include "muse_xcorr.cuh"
@@ -54,6 +55,7 @@ extern "C" const char *muse_version(void) { return "muse_b200 0.1 (sm_100a)"; }
 // per-context pool across muse_batch_create / muse_batch_destroy, because cudaMalloc / cudaFree /
 // cudaHostAlloc of these cost milliseconds to seconds (measured: a NewBatch + Run + destroy cycle per
 // request spent 3 s in cudaFree/cudaFreeHost once in four) while the run itself takes 2.7 ms.
+#define MUSE_SCRATCH_POOL 20   // scratch sets kept per context: a multi-query launch has ScreenMultiCfg::QC batches alive at once
 struct RunScratch {
     int64_t scratch_cap;
     double *d_score;
@@ -76,6 +78,19 @@ struct RunScratch {
     int64_t table_cap;
     unsigned long long *d_gmax, *d_hkeys;
     int32_t *d_gidx;
+    // tables of the reference side.  tab_n: the FFT length the twiddle tables (twM, twn, twp_f, swtw) were filled
+    // for -- a set that comes back from the pool with the same n keeps them, only the per-reference ones
+    // (d_ref, Xt, sw_f, sx_f, d_mid) are rewritten by muse_batch_create
+    int64_t tab_n, d_ref_cap;
+    int tab_screen;                   // twp_f / swtw / sw_f / sx_f exist for tab_n
+    double *d_ref;                    // padded copy of the reference row
+    cd *Xt, *twM, *twn;
+    cf *twp_f;                        // fp32 screening pass: per-pass twiddles
+    float2 *swtw;                     // split twiddles exp(-2*pi*i*k/n), k < M/2, fp32
+    float4 *sw_f;                     // fused kernels: (twn, A[k], A[M-k]) per k < M/2
+    float4 *sx_f;                     // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
+    float *d_mid;                     // [0] std-zero flag of the reference (as float bits), [1] A[M/2], [2..3] Xt[M/2] in fp32
+    cudaEvent_t ev[4];
 };
 
 struct muse_ctx {
@@ -106,19 +121,14 @@ struct muse_batch : RunScratch {
     muse_group *g;
     int64_t N, n;
     int log2m;
-    double *d_ref;      // padded copy of the reference row
-    cd *Xt, *twM, *twn;
-    // fp32 screening pass (n = 512, 2048 .. 16384): tables
+    // fp32 screening pass (n = 512, 2048 .. 16384): the tables live in RunScratch
     int screen_ok;
-    cf *twp_f;
-    float4 *sw_f;          // fused kernels: (twn, A[k], A[M-k]) per k < M/2
     float a_mid;
-    float4 *sx_f;          // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
     cf x_mid;
-    cudaEvent_t ev[4];
     muse_timing timing;
     int timing_pending;    // the last run was queued without a final synchronisation (muse_batch_run_partial_device)
     int fused_run;         // 1: score_fused, 2: score_fused_grouped (d_counters[2] = exact list length, [3] = refined)
+    int prescreened;       // d_U and the cut-off state were filled by score_screen_multi_kernel: the next fused run starts at its tail
 };
 
 struct DeviceGuard {
@@ -159,6 +169,9 @@ static void scratch_free(RunScratch &r) {
     cudaFree(r.d_U); cudaFree(r.d_list); cudaFree(r.d_L);
     cudaFree(r.d_gmax); cudaFree(r.d_hkeys); cudaFree(r.d_gidx);
     cudaFree(r.d_flag); cudaFree(r.d_counters); cudaFree(r.d_sel); cudaFree(r.d_cut);
+    cudaFree(r.d_ref); cudaFree(r.Xt); cudaFree(r.twM); cudaFree(r.twn);
+    cudaFree(r.twp_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.d_mid);
+    for (int i = 0; i < 4; i++) if (r.ev[i]) cudaEventDestroy(r.ev[i]);
     if (r.h_pin) cudaFreeHost(r.h_pin);
     memset(&r, 0, sizeof(r));
 }
@@ -526,45 +539,79 @@ static int screen_is_fused(int log2m) { return log2m >= 8 && log2m <= 13; }
 static int screen_log2m_supported(int log2m) { return screen_is_fused(log2m); }
 static int screen_log2p(int log2m) { return log2m >= 10 ? 5 : (log2m == 9 ? 4 : 3); }
 
-static int rc_screen_tables(muse_batch *b) {
-    b->screen_ok = 0;
-    if (!screen_log2m_supported(b->log2m) || (b->N & 1)) return MUSE_OK;
-    const int64_t M = b->n / 2;
-    const int log2p = screen_log2p(b->log2m);
+// The per-reference tables of the fp32 kernels, from Xt on the device: weights of the bound
+// A[k] = |Xt[k]| * (1 at DC and Nyquist, else 2) rounded UP (the bound must not shrink), one 16-byte entry per
+// mirror pair (k, M-k), k < M/2, with the split twiddle exp(-2*pi*i*k/n); the two reference coefficients of the
+// second stage; and A[M/2], Xt[M/2] for the host (kernel parameters).
+__global__ void screen_tables_kernel(const cd *__restrict__ Xt, int M, const float2 *__restrict__ swtw, float4 *__restrict__ sw,
+                                     float4 *__restrict__ sx, float *__restrict__ mid) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > M / 2) return;
+    const cd a = Xt[k], c = Xt[M - k];
+    if (k == M / 2) {
+        mid[1] = __double2float_ru(hypot(a.x, a.y) * 2.0);
+        mid[2] = (float)a.x;
+        mid[3] = (float)a.y;
+        return;
+    }
+    const float wa = __double2float_ru(hypot(a.x, a.y) * (k == 0 ? 1.0 : 2.0));
+    const float wc = __double2float_ru(hypot(c.x, c.y) * (k == 0 ? 1.0 : 2.0));     // k = 0: M - k is the Nyquist bin
+    const float2 w = swtw[k];
+    sw[k] = make_float4(w.x, w.y, wa, wc);
+    sx[k] = make_float4((float)a.x, (float)a.y, (float)c.x, (float)c.y);
+}
+
+// Twiddle tables of FFT length n (they depend on n alone): filled when the scratch set was last used for another n.
+static int ensure_ref_tables(muse_batch *b, int64_t ld) {
+    const int64_t n = b->n, M = n / 2;
     cudaStream_t st = b->ctx->stream;
+    if (b->d_ref_cap < ld) {
+        cudaFree(b->d_ref);
+        b->d_ref = nullptr;
+        CU(cudaMalloc(&b->d_ref, sizeof(double) * (size_t)ld));
+        b->d_ref_cap = ld;
+    }
+    if (!b->d_mid) CU(cudaMalloc(&b->d_mid, sizeof(float) * 4));
+    const bool want_screen = screen_log2m_supported(b->log2m);
+    if (b->tab_n == n && (b->tab_screen || !want_screen)) return MUSE_OK;
+    cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
+    b->Xt = b->twM = b->twn = nullptr;
+    b->twp_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
+    b->tab_n = 0;
+    b->tab_screen = 0;
     const long double PI2 = 6.283185307179586476925286766559005768L;
-    std::vector<cf> twp((size_t)M + 64);
-    fill_pass_twiddles(b->log2m, log2p, twp.data(), [&](long long num, long long den) {
-        return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
+    const int log2p = exact_log2p(b->log2m);
+    std::vector<cd> twM((size_t)M + 16);
+    fill_pass_twiddles(b->log2m, log2p, twM.data(), [&](long long num, long long den) {
+        return cd{(double)cosl(-PI2 * num / den), (double)sinl(-PI2 * num / den)};
     });
-    std::vector<cd> X((size_t)M + 1);
-    CU(cudaMemcpyAsync(X.data(), b->Xt, sizeof(cd) * (size_t)(M + 1), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    // weights of the bound: A[k] = |Xt[k]| * (1 at DC and Nyquist, else 2), rounded UP (the bound must not shrink)
-    std::vector<float> A((size_t)M + 1);
-    for (int64_t k = 0; k <= M; k++) {
-        const double a = hypot(X[(size_t)k].x, X[(size_t)k].y) * ((k == 0 || k == M) ? 1.0 : 2.0);
-        float f = (float)a;
-        if ((double)f < a) f = nextafterf(f, INFINITY);
-        A[(size_t)k] = f;
+    // twiddle tables, correctly rounded from long double
+    std::vector<cd> twn((size_t)(M / 2 + 1));
+    for (int64_t k = 0; k <= M / 2; k++) twn[(size_t)k] = cd{(double)cosl(-PI2 * k / n), (double)sinl(-PI2 * k / n)};
+    CU(cudaMalloc(&b->Xt, sizeof(cd) * (size_t)(M + 1)));
+    CU(cudaMalloc(&b->twM, sizeof(cd) * twM.size()));
+    CU(cudaMalloc(&b->twn, sizeof(cd) * (size_t)(M / 2 + 1)));
+    CU(cudaMemcpyAsync(b->twM, twM.data(), sizeof(cd) * twM.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->twn, twn.data(), sizeof(cd) * (size_t)(M / 2 + 1), cudaMemcpyHostToDevice, st));
+    std::vector<cf> twp;
+    std::vector<float2> swtw;
+    if (want_screen) {
+        twp.resize((size_t)M + 64);
+        fill_pass_twiddles(b->log2m, screen_log2p(b->log2m), twp.data(), [&](long long num, long long den) {
+            return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
+        });
+        swtw.resize((size_t)M / 2);
+        for (int64_t k = 0; k < M / 2; k++) swtw[(size_t)k] = make_float2((float)cosl(-PI2 * k / n), (float)sinl(-PI2 * k / n));
+        CU(cudaMalloc(&b->twp_f, sizeof(cf) * twp.size()));
+        CU(cudaMalloc(&b->swtw, sizeof(float2) * swtw.size()));
+        CU(cudaMalloc(&b->sw_f, sizeof(float4) * (size_t)(M / 2)));
+        CU(cudaMalloc(&b->sx_f, sizeof(float4) * (size_t)(M / 2)));
+        CU(cudaMemcpyAsync(b->twp_f, twp.data(), sizeof(cf) * twp.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(b->swtw, swtw.data(), sizeof(float2) * swtw.size(), cudaMemcpyHostToDevice, st));
     }
-    // one 16-byte entry per mirror pair (k, M-k), k < M/2: the split twiddle exp(-2*pi*i*k/n) with the two
-    // weights, and the two reference coefficients of the second stage
-    std::vector<float4> sw((size_t)M / 2), sx((size_t)M / 2);
-    for (int64_t k = 0; k < M / 2; k++) {
-        sw[(size_t)k] = make_float4((float)cosl(-PI2 * k / b->n), (float)sinl(-PI2 * k / b->n), A[(size_t)k], A[(size_t)(M - k)]);
-        sx[(size_t)k] = make_float4((float)X[(size_t)k].x, (float)X[(size_t)k].y, (float)X[(size_t)(M - k)].x, (float)X[(size_t)(M - k)].y);
-    }
-    b->a_mid = A[(size_t)M / 2];
-    b->x_mid = cf{(float)X[(size_t)M / 2].x, (float)X[(size_t)M / 2].y};
-    CU(cudaMalloc(&b->sw_f, sizeof(float4) * sw.size()));
-    CU(cudaMalloc(&b->sx_f, sizeof(float4) * sx.size()));
-    CU(cudaMalloc(&b->twp_f, sizeof(cf) * twp.size()));
-    CU(cudaMemcpyAsync(b->sw_f, sw.data(), sizeof(float4) * sw.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->sx_f, sx.data(), sizeof(float4) * sx.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->twp_f, twp.data(), sizeof(cf) * twp.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-    b->screen_ok = 1;
+    CU(cudaStreamSynchronize(st));      // the host vectors go out of scope
+    b->tab_n = n;
+    b->tab_screen = want_screen ? 1 : 0;
     return MUSE_OK;
 }
 
@@ -588,27 +635,29 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
     while ((1LL << l) < M) l++;
     b->log2m = l;
     cudaStream_t st = ctx->stream;
-    for (int i = 0; i < 4; i++) CU(cudaEventCreate(&b->ev[i]));
-    CU(cudaMalloc(&b->d_ref, sizeof(double) * (size_t)g->ld));
-    CU(cudaMalloc(&b->Xt, sizeof(cd) * (size_t)(M + 1)));
-    const int log2p = exact_log2p(b->log2m);
-    std::vector<cd> twM((size_t)M + 16);
-    const long double PI2 = 6.283185307179586476925286766559005768L;
-    fill_pass_twiddles(b->log2m, log2p, twM.data(), [&](long long num, long long den) {
-        return cd{(double)cosl(-PI2 * num / den), (double)sinl(-PI2 * num / den)};
-    });
-    CU(cudaMalloc(&b->twM, sizeof(cd) * twM.size()));
-    CU(cudaMalloc(&b->twn, sizeof(cd) * (size_t)(M / 2 + 1)));
-    {   // scratch of an earlier batch on this context, if there is one (the largest fits most stores)
+    {   // scratch of an earlier batch on this context, if there is one: a set whose tables were filled for this FFT
+        // length is preferred, then the largest (it fits most stores)
         std::lock_guard<std::mutex> lk(ctx->mu);
         if (!ctx->pool.empty()) {
             size_t best = 0;
+            auto better = [&](const RunScratch &x, const RunScratch &y) {
+                if ((x.tab_n == n) != (y.tab_n == n)) return x.tab_n == n;
+                return x.scratch_cap > y.scratch_cap;
+            };
             for (size_t i = 1; i < ctx->pool.size(); i++)
-                if (ctx->pool[i].scratch_cap > ctx->pool[best].scratch_cap) best = i;
+                if (better(ctx->pool[i], ctx->pool[best])) best = i;
             static_cast<RunScratch &>(*b) = ctx->pool[best];
             ctx->pool.erase(ctx->pool.begin() + (long)best);
         }
     }
+    auto bail = [&](int code) {
+        muse_batch_destroy(b);
+        return code;
+    };
+    for (int i = 0; i < 4; i++)
+        if (!b->ev[i] && cudaEventCreate(&b->ev[i]) != cudaSuccess) return bail(fail(MUSE_ERR_CUDA, "cudaEventCreate failed"));
+    int rc = ensure_ref_tables(b, g->ld);
+    if (rc) return bail(rc);
     if (!b->d_flag) CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
     if (!b->d_counters) CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
     if (!b->d_sel) CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
@@ -618,11 +667,6 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
         CU(cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault));
     }
     CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
-    // twiddle tables, correctly rounded from long double
-    std::vector<cd> twn((size_t)(M / 2 + 1));
-    for (int64_t k = 0; k <= M / 2; k++) twn[(size_t)k] = cd{(double)cosl(-PI2 * k / n), (double)sinl(-PI2 * k / n)};
-    CU(cudaMemcpyAsync(b->twM, twM.data(), sizeof(cd) * twM.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->twn, twn.data(), sizeof(cd) * (size_t)(M / 2 + 1), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(b->d_ref, 0, sizeof(double) * (size_t)g->ld, st));
     CU(cudaMemcpyAsync(b->d_ref, ref, sizeof(double) * (size_t)ref_len, cudaMemcpyHostToDevice, st));
     // X on the device through the same forward path the series take
@@ -637,14 +681,27 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
     p.out_X = b->Xt;
     p.out_flag = b->d_flag;
     CU(launch_exact<MODE_REF>(b->log2m, p, st));
-    int32_t flag = 0;
-    CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    b->screen_ok = 0;
+    const bool screen = b->tab_screen && !(b->N & 1);
+    if (screen) {
+        screen_tables_kernel<<<(unsigned)((M / 2 + 1 + 255) / 256), 256, 0, st>>>(b->Xt, (int)M, b->swtw, b->sw_f, b->sx_f, b->d_mid);
+        CU(cudaGetLastError());
+    }
+    // one round trip: the std-zero flag of the reference and the two middle-bin values the kernels take by value
+    int32_t *h_flag = reinterpret_cast<int32_t *>(b->h_pin);
+    float *h_mid = reinterpret_cast<float *>(b->h_pin + 16);
+    CU(cudaMemcpyAsync(h_flag, b->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (screen) CU(cudaMemcpyAsync(h_mid, b->d_mid, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (flag) {   // muse_batch.go:38-41
+    if (*h_flag) {   // muse_batch.go:38-41
         muse_batch_destroy(b);
         return fail(MUSE_ERR_STDDEV_ZERO, "Invalid input query, Standard deviation of zero");
     }
-    rc_screen_tables(b);
+    if (screen) {
+        b->a_mid = h_mid[1];
+        b->x_mid = cf{h_mid[2], h_mid[3]};
+        b->screen_ok = 1;
+    }
     *out = b;
     return MUSE_OK;
 }
@@ -667,15 +724,12 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
     cudaStreamSynchronize(b->ctx->stream);
     {   // the store-sized scratch goes back to the context (at most 4 sets are kept)
         std::lock_guard<std::mutex> lk(b->ctx->mu);
-        if (b->ctx->pool.size() < 4) {
+        if (b->ctx->pool.size() < MUSE_SCRATCH_POOL) {
             b->ctx->pool.push_back(static_cast<RunScratch &>(*b));
             memset(static_cast<RunScratch *>(b), 0, sizeof(RunScratch));
         }
     }
     scratch_free(*b);
-    cudaFree(b->d_ref); cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn);
-    cudaFree(b->twp_f); cudaFree(b->sw_f); cudaFree(b->sx_f);
-    for (int i = 0; i < 4; i++) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     delete b;
 }
 
@@ -1138,10 +1192,15 @@ static int score_fused(muse_batch *b, const RunArgs &a) {
     cudaStream_t st = b->ctx->stream;
     ScreenParams sp = screen_params(b);
     const float thr_lo = a.threshold > 0 ? (float)a.threshold * 0.999999f : 0.f;   // never above the fp64 threshold
-    int rc = arm_refinement(b, sp, thr_lo, a.max_lag, a.top_n, a.threshold);
-    if (rc) return rc;
-    CU(launch_screen(b, sp, st));
-    b->timing.n_launches += 2;
+    int rc = MUSE_OK;
+    if (b->prescreened) {      // muse_multi_run: this query's bounds and cut-off came out of the multi-query launch
+        b->prescreened = 0;
+    } else {
+        rc = arm_refinement(b, sp, thr_lo, a.max_lag, a.top_n, a.threshold);
+        if (rc) return rc;
+        CU(launch_screen(b, sp, st));
+        b->timing.n_launches += 2;
+    }
     CU(cudaEventRecord(b->ev[1], st));
     if (!a.list_only) CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "cannot be in the result"
     const unsigned blocks = (unsigned)((S + 255) / 256);
@@ -1522,6 +1581,68 @@ extern "C" int muse_merge_partials(const muse_partial *parts, int64_t n_parts, i
 // row statistics and the run scratch (context pool) are shared, results of query q land in row q of the
 // outputs.  Every query still streams the slab once (HBM-bound, 2.3 ms per 1 M x 1440 series); the multi-query
 // bound pass that reads the slab once for ALL queries is DESIGN.md section 8's next step.
+template <int NZ>
+static cudaError_t launch_screen_multi_nz(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st) {
+    using C = ScreenMultiCfg;
+    auto kern = score_screen_multi_kernel<NZ>;
+    const int warps = C::warps(p.N);
+    const size_t smem = C::smem_bytes(p.N);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t blocks = (p.count + warps - 1) / warps;      // persistent: one block per SM
+    if (blocks > sm_count) blocks = sm_count;
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(p, d_queries, nq, (unsigned)C::warp_bytes(p.N), (unsigned)C::row_bytes(p.N));
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_screen_multi(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st) {
+    switch (ScreenWarpCfg::nz(p.N)) {
+#define MUSE_NZ_CASE(z) case z: return launch_screen_multi_nz<z>(p, d_queries, nq, sm_count, st);
+        MUSE_NZ_CASE(17) MUSE_NZ_CASE(18) MUSE_NZ_CASE(19) MUSE_NZ_CASE(20) MUSE_NZ_CASE(21) MUSE_NZ_CASE(22)
+        MUSE_NZ_CASE(23) MUSE_NZ_CASE(24) MUSE_NZ_CASE(25) MUSE_NZ_CASE(26) MUSE_NZ_CASE(27) MUSE_NZ_CASE(28)
+        MUSE_NZ_CASE(29) MUSE_NZ_CASE(30) MUSE_NZ_CASE(31) MUSE_NZ_CASE(32)
+#undef MUSE_NZ_CASE
+    }
+    return cudaErrorInvalidValue;
+}
+
+// Up to ScreenMultiCfg::QC queries in ONE pass over the slab: every batch gets its cut-off state armed, the
+// multi-query kernel fills each batch's bounds (d_U) and cut-off, and each batch is marked `prescreened` so that
+// its next fused run starts at the tail (survivors -> exact fp64 kernel -> filter -> top-N).
+static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag, int64_t top_n, double threshold) {
+    cudaStream_t st = ctx->stream;
+    std::vector<MultiQuery> hq((size_t)nq);
+    ScreenParams sp0;
+    float thr_lo = threshold > 0 ? (float)threshold * 0.999999f : 0.f;
+    if (getenv("MUSE_MULTI_BOUNDS_ONLY")) thr_lo = INFINITY;      // timing probe only (tools/c5_probe.py): no second stage, empty results
+    for (int q = 0; q < nq; q++) {
+        muse_batch *b = bs[q];
+        int rc = ensure_scratch(b);
+        if (rc) return rc;
+        ScreenParams sp = screen_params(b);
+        rc = arm_refinement(b, sp, thr_lo, max_lag, top_n, threshold);
+        if (rc) return rc;
+        if (q == 0) sp0 = sp;
+        MultiQuery &m = hq[(size_t)q];
+        memset(&m, 0, sizeof(m));
+        m.sw = b->sw_f;
+        m.sx = b->sx_f;
+        m.x_mid = b->x_mid;
+        m.a_mid = b->a_mid;
+        m.cut = b->d_cut;
+        m.out_U = b->d_U;
+    }
+    MultiQuery *d_q = nullptr;
+    CU(cudaMalloc(&d_q, sizeof(MultiQuery) * (size_t)nq));
+    cudaError_t e = cudaMemcpyAsync(d_q, hq.data(), sizeof(MultiQuery) * (size_t)nq, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_screen_multi(sp0, d_q, nq, ctx->sm_count, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // hq and d_q are released below
+    cudaFree(d_q);
+    CU(e);
+    for (int q = 0; q < nq; q++) bs[q]->prescreened = 1;
+    return MUSE_OK;
+}
+
 extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len,
                               const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n, double threshold,
                               int32_t sign_filter, int32_t mode, double *scores, int64_t *lags, int64_t *series_idx,
@@ -1529,18 +1650,43 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
     if (!ctx || !g || (!refs && n_refs > 0) || !n_out) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_run: NULL argument");
     if (n_refs < 0 || top_n < 0) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_run: n_refs %lld, top_n %lld", (long long)n_refs, (long long)top_n);
     if (top_n > 0 && (!scores || !lags || !series_idx)) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_run: NULL output");
-    for (int64_t q = 0; q < n_refs; q++) {
-        muse_batch *b = nullptr;
-        int rc = muse_batch_create(ctx, g, refs + (size_t)q * (size_t)ref_len, ref_len, &b);
-        if (rc == MUSE_ERR_STDDEV_ZERO) {   // muse_batch.go:38-41: this query has no Batch; the others do
-            n_out[q] = -1;
-            continue;
+    if (n_key_cols < 0 || (n_key_cols > 0 && !key_cols)) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_run: bad key columns");
+    CU(cudaSetDevice(ctx->device));
+    // the one-pass multi-query kernel exists for the shape the single-query warp kernel serves (FFT length 2048,
+    // ungrouped, unsigned scores, a sign filter unsigned scores can pass, a store worth screening, a device-side
+    // top-N); everything else is n_refs x (NewBatch + Run) on the resident store
+    const bool one_pass = n_key_cols == 0 && mode != MUSE_MODE_EXACT && sign_filter != MUSE_SIGN_NEG && ref_len == g->N &&
+                          (ref_len & 1) == 0 && next_pow2(ref_len) == 2048 && top_n > 0 && top_n <= 65536 &&
+                          top_n * 4 <= g->size && (g->size >= 16384 || mode == MUSE_MODE_SCREEN) && n_refs > 1;
+    constexpr int QC = ScreenMultiCfg::QC;
+    for (int64_t q0 = 0; q0 < n_refs; q0 += QC) {
+        const int nq = (int)std::min<int64_t>(QC, n_refs - q0);
+        muse_batch *bs[QC];
+        int64_t which[QC];
+        int live = 0, rc = MUSE_OK;
+        for (int i = 0; i < nq && rc == MUSE_OK; i++) {
+            muse_batch *b = nullptr;
+            rc = muse_batch_create(ctx, g, refs + (size_t)(q0 + i) * (size_t)ref_len, ref_len, &b);
+            if (rc == MUSE_ERR_STDDEV_ZERO) {   // muse_batch.go:38-41: this query has no Batch; the others do
+                n_out[q0 + i] = -1;
+                rc = MUSE_OK;
+                continue;
+            }
+            if (rc == MUSE_OK) {
+                bs[live] = b;
+                which[live++] = q0 + i;
+            }
         }
-        if (rc) return rc;
-        rc = muse_batch_run_ex(b, key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, 0,
-                               scores ? scores + (size_t)q * (size_t)top_n : nullptr, lags ? lags + (size_t)q * (size_t)top_n : nullptr,
-                               series_idx ? series_idx + (size_t)q * (size_t)top_n : nullptr, n_out + q);
-        muse_batch_destroy(b);
+        if (rc == MUSE_OK && one_pass && live > 1) rc = screen_multi(ctx, bs, live, max_lag, top_n, threshold);
+        for (int i = 0; i < live; i++) {
+            const int64_t q = which[i];
+            if (rc == MUSE_OK)
+                rc = muse_batch_run_ex(bs[i], key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter,
+                                       bs[i]->prescreened ? MUSE_MODE_SCREEN : mode, 0,
+                                       scores ? scores + (size_t)q * (size_t)top_n : nullptr, lags ? lags + (size_t)q * (size_t)top_n : nullptr,
+                                       series_idx ? series_idx + (size_t)q * (size_t)top_n : nullptr, n_out + q);
+            muse_batch_destroy(bs[i]);
+        }
         if (rc) return rc;
     }
     return MUSE_OK;

@@ -289,3 +289,39 @@ def test_scratch_pool_survives_batch_churn(ctx):
             alive.pop(0).close()
     for b in alive:
         b.close()
+
+
+@pytest.mark.parametrize("N", [1440, 1030, 2048])
+def test_one_pass_multi_query_run_equals_exact_runs(ctx, N):
+    # muse_multi_run at FFT length 2048: score_screen_multi_kernel bounds ALL queries of a launch in one pass over
+    # the slab (16 per launch: 21 queries = 16 + 5), each query then finishes on its own tail.  Every query must
+    # return exactly what its own all-exact Batch.Run returns; a constant reference fails for itself only.
+    rng = np.random.default_rng(N + 7)
+    S, Q = 30000, 21
+    Y = _adversarial(rng, S, N)
+    refs = np.zeros((Q, N))
+    for q in range(Q):
+        m, w = int(rng.integers(N // 4, 3 * N // 4)), int(rng.integers(3, 21))
+        refs[q, m:m + w] = 1.5
+        refs[q] += 0.1 * (rng.random(N) - 0.5)
+    refs[5] = -2.5                                         # sigma = 0 (muse_batch.go:38-41)
+    refs[9] = np.sin(2 * np.pi * np.arange(N) / 37.0)      # matches the sinusoid rows at some lag
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y)
+    for max_lag, top_n, thr in ((60, 100, 0.5), (N, 40, 0.0), (5, 7000, 0.2)):
+        got = mb.multi_run(store, refs, [], max_lag, top_n, thr, mode=mb.MODE_SCREEN)
+        assert got[5] is None
+        for q in range(Q):
+            if q == 5:
+                continue
+            b = mb.DeviceBatch(ctx, store, refs[q])
+            want = b.run([], max_lag, top_n, thr, mode=mb.MODE_EXACT)
+            b.close()
+            for g, w_ in zip(got[q], want):
+                np.testing.assert_array_equal(g, w_)       # bit-identical scores, lags and indices
+    # and the oracle agrees
+    wsc, wlg, wix = co.batch_run(refs[0], Y, None, 60, 100, 0.5)
+    sc, lg, ix = mb.multi_run(store, refs[:2], [], 60, 100, 0.5, mode=mb.MODE_SCREEN)[0]
+    assert np.max(np.abs(sc - wsc), initial=0) <= 1e-9
+    np.testing.assert_array_equal(lg, wlg)
+    np.testing.assert_array_equal(ix, wix)

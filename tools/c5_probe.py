@@ -17,10 +17,19 @@ for q in range(Q):                                   # rect mids / widths varied
     mid, w = int(rng.integers(540, 900)), int(rng.integers(3, 21))
     refs[q, mid - w // 2: mid - w // 2 + w] = 1.5
     refs[q] += 0.1 * (rng.random(N) - 0.5)
-mb.multi_run(store, refs[:2], [], 60, 100, 0.5)      # warm-up: row statistics, scratch pool
+mb.multi_run(store, refs, [], 60, 100, 0.5)          # warm-up: row statistics, scratch pool of every batch of a launch
 ctx.synchronize()
+REP = int(os.environ.get("C5_REP", "3"))
 t0 = time.perf_counter()
-out = mb.multi_run(store, refs, [], 60, 100, 0.5)
-dt = time.perf_counter() - t0
+for _ in range(REP):
+    out = mb.multi_run(store, refs, [], 60, 100, 0.5)
+dt = (time.perf_counter() - t0) / REP
 print("C5 probe: %d refs x %d series x %d samples: %.1f ms (%.2f ms per query) = %.1f G pair-samples/s; results per query: %s"
       % (Q, S, N, dt * 1e3, dt * 1e3 / Q, Q * S * N / dt / 1e9, [len(o[0]) for o in out][:8]), flush=True)
+if os.environ.get("C5_REFINED"):
+    for q in range(min(Q, 8)):
+        b = mb.DeviceBatch(ctx, store, refs[q])
+        b.run([], 60, 100, 0.5)
+        tm = b.timing()
+        print("query %d alone: %.2f ms, refined %d, exact-scored %d" % (q, tm.total_ms, tm.n_refined, tm.n_rescored), flush=True)
+        b.close()
