@@ -183,36 +183,44 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
             mg_mid = lane0 ? 2.f * sqrt_approx(q.x + q.y) : 0.f;      // k = 512: lane 0, slot 16
         }
 
+        // ---- all bounds first (lane q keeps query q's), four queries per step: their 8 accumulation chains and 4
+        //      butterfly reductions overlap (one at a time leaves a warp waiting on 8 FFMA2 and 5 dependent shuffles) ----
         float my_U = 2.f;
-        // four queries per step: their 8 accumulation chains and 4 butterfly reductions overlap (one query at a
-        // time leaves a warp waiting ~300 cycles on a chain of 8 FFMA2 and 5 dependent shuffles)
-        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int q = 0; q < nq; q++) {
-            if ((q & 3) == 0) {
+        for (int q = 0; q < nq; q += 4) {
+            float acc4[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int qi = q + i < nq ? q + i : nq - 1;
-                    const cf *Aq = sA + (size_t)qi * (M / 2) + t;
-                    cf a0{0.f, 0.f}, a1{0.f, 0.f};
+            for (int i = 0; i < 4; i++) {
+                const int qi = q + i < nq ? q + i : nq - 1;
+                const cf *Aq = sA + (size_t)qi * (M / 2) + t;
+                cf a0{0.f, 0.f}, a1{0.f, 0.f};
 #pragma unroll
-                    for (int j = 0; j < P / 2; j += 2) {
-                        a0 = pfma(mg[j], Aq[32 * j], a0);
-                        a1 = pfma(mg[j + 1], Aq[32 * (j + 1)], a1);
-                    }
-                    acc4[i] = fmaf(mg_mid, sAmid[qi], (a0.x + a0.y) + (a1.x + a1.y));
+                for (int j = 0; j < P / 2; j += 2) {
+                    a0 = pfma(mg[j], Aq[32 * j], a0);
+                    a1 = pfma(mg[j + 1], Aq[32 * (j + 1)], a1);
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) acc4[i] += __shfl_xor_sync(0xffffffffu, acc4[i], off);
-                }
+                acc4[i] = fmaf(mg_mid, sAmid[qi], (a0.x + a0.y) + (a1.x + a1.y));
             }
-            const int qs = q & 3;
-            const float acc = qs == 0 ? acc4[0] : (qs == 1 ? acc4[1] : (qs == 2 ? acc4[2] : acc4[3]));
-            float U = acc * rs.rstd * 1.00001f + MUSE_SCREEN_SLACK;
-            if (!(U == U)) U = 2.f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc4[i] += __shfl_xor_sync(0xffffffffu, acc4[i], off);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float U = acc4[i] * rs.rstd * 1.00001f + MUSE_SCREEN_SLACK;
+                if (!(U == U)) U = 2.f;
+                if (t == q + i) my_U = U;      // q + i >= nq: a duplicate of the last query on a lane without one
+            }
+        }
+        // ---- then the second stage for every query whose bound reaches ITS running cut-off (the magnitudes are dead
+        //      by now; consecutive refinements of one series run the same code back to back) ----
+        unsigned todo = __ballot_sync(0xffffffffu, t < nq && my_U >= __uint_as_float(cut_raw) && my_U < 1.5f);
+        while (todo) {
+            const int q = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float U = __shfl_sync(0xffffffffu, my_U, q);
             const float cut_now = __uint_as_float(__shfl_sync(0xffffffffu, cut_raw, q));
-            if (U >= cut_now && U < 1.5f) {      // warp-uniform
+            {
                 // ---- second stage for query q: spectrum back from the stash, conj(Y)*X_q, inverse FFT, window maxima ----
                 const MultiQuery mq = queries[q];
                 cf z[P];
