@@ -1887,8 +1887,8 @@ extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t 
     const unsigned pblocks = (unsigned)std::min<int64_t>((std::max<int64_t>(S, 1) + 7) / 8, (int64_t)b->ctx->sm_count * 8);
     partial_topn_push_kernel<<<pblocks, 256, 0, st>>>(b->d_ckey, b->d_cidx, b->d_clag, b->d_counters, (long long)top_n,
                                                       (long long)b->g->global_offset, exact_bound, (long long)x->capacity, ex);
-    // 2 s at ~2 GHz: a peer that never arrives must not hang the box
-    exchange_wait_kernel<<<1, 32, 0, st>>>(ex.flags[x->rank], x->world, x->epoch, 4000000000ll, x->d_status);
+    // ~10 s at ~2 GHz: ranks may be a whole host->device upload apart, but a peer that never arrives must not hang the box
+    exchange_wait_kernel<<<1, 32, 0, st>>>(ex.flags[x->rank], x->world, x->epoch, 20000000000ll, x->d_status);
     b->timing.n_launches += 2;
     CU(cudaGetLastError());
     int *h_status = reinterpret_cast<int *>(x->h_recs + x->recs_bytes);

@@ -475,3 +475,45 @@ def test_multi_reference_run_equals_separate_batches(ctx):
             np.testing.assert_array_equal(got[q][1], wlg)
             np.testing.assert_array_equal(got[q][2], wix)
             b.close()
+
+
+def test_incremental_store_growth(ctx):
+    # Group.Add after the first upload and after a Batch exists.  The store grows (slab
+    # reallocation, row statistics extended for the new rows only), the existing batch sees the new series.
+    rng = np.random.default_rng(23)
+    S, N = 24000, 1440
+    ref, Y = _siggen(rng, S, N)
+    store = mb.DeviceStore(ctx, N, 0, 16)                 # tiny reservation: forces several reallocations
+    b = None
+    done = 0
+    for chunk in (5000, 1, 12999, 6000):
+        store.append(Y[done:done + chunk])
+        done += chunk
+        if b is None:
+            b = mb.DeviceBatch(ctx, store, ref)
+        for mode in (mb.MODE_SCREEN, mb.MODE_EXACT):
+            sc, lg, ix = b.run([], 60, 50, 0.3, mode=mode)
+            wsc, wlg, wix = co.batch_run(ref, Y[:done], None, 60, 50, 0.3)
+            assert np.max(np.abs(sc - wsc), initial=0) <= SCORE_TOL
+            np.testing.assert_array_equal(lg, wlg)
+            np.testing.assert_array_equal(ix, wix)
+    assert store.size() == S
+    # the same through the facade: Add between two Runs of one Batch (Results is not reset between Runs, results.go:55-72)
+    g = mb.NewGroup("grow")
+    mk = lambda i: mb.NewSeries(Y[i, :480].copy(), mb.NewLabels({"host": "h%d" % i}))
+    g.Add(*[mk(i) for i in range(0, 300)])
+    batch = mb.NewBatch(mb.NewSeries(ref[480:960].copy()), g, mb.NewResults(20, 400, 0.0, mb.SignFilter_ANY), 1)
+    batch.Run(None)
+    first, _ = batch.Results.Fetch()
+    g.Add(*[mk(i) for i in range(300, 700)])
+    with pytest.raises(mb.MuseError):
+        g.Add(mk(5))                                       # duplicate UID (group.go:39-41)
+    with pytest.raises(mb.MuseError):
+        g.Add(mb.NewSeries(Y[0, :100].copy(), mb.NewLabels({"host": "short"})))   # length (group.go:45-51)
+    batch.Run(None)
+    second, _ = batch.Results.Fetch()
+    sl = mo.score_series_batch(ref[480:960], Y[:700, :480])
+    want = sorted([(min(abs(float(s)), 1.0), i) for i, (s, l) in enumerate(zip(*sl)) if abs(l) <= 20], key=lambda x: (-x[0], x[1]))[:400]
+    assert len(first) <= 300 and len(second) == len(want)
+    for got, (ws, wi) in zip(second, want):
+        assert abs(got.PercentScore - ws) <= SCORE_TOL and got.Labels is g.series[wi].Labels()
