@@ -154,15 +154,96 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_c5(args, mb, torch, dist, rank, local_rank, world, mode):
+    """BASELINE.json configs[4]: Q reference queries against ONE store of --series series, sharded by series over
+    the GPUs (strong scaling).  A step = muse_multi_run on the shard (every series transformed once per 16 queries)
+    + one all-gather of the shards' per-query top-N + the per-query merge.  Not the headline line."""
+    ctx = mb.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    S_total, N, Q, top_n = args.series, args.length, args.queries, args.top_n
+    lo, hi = rank * S_total // world, (rank + 1) * S_total // world
+    store = mb.DeviceStore(ctx, N, 2, hi - lo)
+    store.append_synthetic(hi - lo, SEED, lo)
+    store.set_global_offset(lo)
+    rng = np.random.default_rng(3)
+    refs = np.zeros((Q, N))
+    for q in range(Q):                                   # rect mids / widths varied (SURVEY 8d C5)
+        mid, w = int(rng.integers(N // 2 - N // 8, N // 2 + N // 8)), int(rng.integers(3, 21))
+        refs[q, mid - w // 2: mid - w // 2 + w] = 1.5
+        refs[q] += 0.1 * (rng.random(N) - 0.5)
+
+    def step():
+        out = mb.multi_run(store, refs, [], args.max_lag, top_n, args.threshold, 0, mode=mode)
+        if world == 1:
+            return out
+        # fixed-size records per query: (score, lag, global index), padded with score -1
+        rec = np.full((Q, top_n, 3), -1.0)
+        for q, o in enumerate(out):
+            k = len(o[0])
+            rec[q, :k, 0], rec[q, :k, 1], rec[q, :k, 2] = o[0], o[1], o[2]
+        mine = torch.from_numpy(rec).cuda(non_blocking=True)
+        allr = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.cpu().numpy()
+        merged = []
+        for q in range(Q):
+            r = allr[:, q].reshape(-1, 3)
+            r = r[r[:, 0] >= 0]
+            order = np.lexsort((r[:, 2], -r[:, 0]))[:top_n]     # score desc, index asc (results.go:81-85)
+            merged.append((r[order, 0], r[order, 1].astype(np.int64), r[order, 2].astype(np.int64)))
+        return merged
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        out = step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.finish()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    if rank == 0:
+        line = {
+            "metric": "pair-samples/sec for Q reference queries against one sharded store (BASELINE.json configs[4])",
+            "value": Q * S_total * N / (ms * 1e-3), "unit": "pair-samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C5: %d reference queries x %d series x %d fp64 samples, maxLag=%d, topN=%d, threshold=%g, "
+                                   "ungrouped, store sharded by series over %d GPU(s)" % (Q, S_total, N, args.max_lag, top_n, args.threshold, world),
+                       "queries": Q, "series_total": S_total, "series_len": N, "ms_per_query": ms / Q,
+                       "l2": "each shard (%.2f GB) is far larger than the 126 MB L2" % ((hi - lo) * N * 8 / 1e9)},
+            "clocks": clocks, "top": {"score": float(out[0][0][0]) if len(out[0][0]) else None, "n": int(len(out[0][0]))},
+        }
+        print(json.dumps(line), flush=True)
+    store.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4"],
+    ap.add_argument("--queries", type=int, default=256, help="--workload c5: reference queries per step")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
                     help="c3 (default, the configuration the metric is quoted on) or c4: 1.25 M x 10080 per GPU, maxLag 240, "
-                         "grouped by two labels (not a headline line: BASELINE.json configs[3])")
+                         "grouped by two labels (not a headline line: BASELINE.json configs[3]); c5: --queries references "
+                         "against 1 M x 1440 series sharded over the GPUs (BASELINE.json configs[4], pair-samples/s)")
     ap.add_argument("--series", type=int, default=None)
     ap.add_argument("--length", type=int, default=None)
     ap.add_argument("--max-lag", type=int, default=None)
@@ -175,7 +256,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the peer-memory push")
     args = ap.parse_args()
-    dflt = {"c3": (1_000_000, 1440, 60), "c4": (1_250_000, 10080, 240)}[args.workload]
+    dflt = {"c3": (1_000_000, 1440, 60), "c4": (1_250_000, 10080, 240), "c5": (1_000_000, 1440, 60)}[args.workload]
     args.series = args.series if args.series is not None else dflt[0]
     args.length = args.length if args.length is not None else dflt[1]
     args.max_lag = args.max_lag if args.max_lag is not None else dflt[2]
@@ -202,6 +283,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     mode = {"auto": mb.MODE_AUTO, "exact": mb.MODE_EXACT, "screen": mb.MODE_SCREEN}[args.mode]
+    if args.workload == "c5":
+        run_c5(args, mb, torch, dist, rank, local_rank, world, mode)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     ctx = mb.Context(local_rank)
     stream = torch.cuda.Stream()

@@ -100,6 +100,7 @@ struct muse_ctx {
     cudaStream_t own_stream;   // created with the context
     std::mutex mu;
     std::vector<RunScratch> pool;   // scratch sets of destroyed batches, reused by the next muse_batch_create
+    void *d_multi_q;                // query table of score_screen_multi_kernel (ScreenMultiCfg::QC entries)
 };
 
 struct muse_group {
@@ -180,6 +181,7 @@ extern "C" void muse_ctx_destroy(muse_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (RunScratch &r : c->pool) scratch_free(r);
+    cudaFree(c->d_multi_q);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -1318,6 +1320,59 @@ static int finish_timing(muse_batch *b) {
 
 static int queue_topn_records(muse_batch *b, const RunArgs &a, muse_partial *d_out, int64_t capacity);
 
+// Ungrouped runs with a device-side top-N, in two halves so that several batches can share ONE synchronisation
+// (muse_multi_run): queue = scores, filter, rank, copy of the top_n records into the batch's pinned mailbox;
+// finish (after the stream has been synchronised) = read the mailbox, or -- when the candidate list was too long for
+// the device-side select, or the fused path's exact launch did not cover its list -- finish on the host path from
+// the scores already on the device.
+static bool device_topn_applies(const muse_batch *b, const RunArgs &a) {
+    return a.n_key_cols == 0 && a.top_n > 0 && a.top_n <= 65536 && b->g->size > 0;
+}
+
+static int device_topn_queue(muse_batch *b, const RunArgs &a) {
+    muse_partial *d_rec = reinterpret_cast<muse_partial *>(b->d_skey);      // free scratch in this path
+    int rc = queue_topn_records(b, a, d_rec, a.top_n);
+    if (rc) return rc;
+    cudaStream_t st = b->ctx->stream;
+    CU(cudaMemcpyAsync(b->h_pin + 64, d_rec, sizeof(muse_partial) * (size_t)a.top_n, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(b->ev[3], st));
+    return MUSE_OK;
+}
+
+static int device_topn_finish(muse_batch *b, const RunArgs &a, double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out) {
+    const int64_t top_n = a.top_n;
+    const muse_partial *h_rec = reinterpret_cast<const muse_partial *>(b->h_pin + 64);
+    if (h_rec[0].flags != 2) {
+        int64_t k = 0;
+        for (; k < top_n && h_rec[k].flags == 0; k++) {
+            scores[k] = h_rec[k].score;
+            lags[k] = h_rec[k].lag;
+            series_idx[k] = h_rec[k].series_idx;
+        }
+        *n_out = k;
+        muse_timing t;
+        return muse_batch_last_timing(b, &t);      // settles timing_pending (events are complete)
+    }
+    b->timing_pending = 0;
+    const unsigned long long *h_n = reinterpret_cast<const unsigned long long *>(b->h_pin);
+    int rc;
+    if (b->fused_run == 1) {
+        rc = run_fused_overflow(b, (int64_t)h_n[2], true);
+        if (rc) return rc;
+        b->fused_run = 0;
+    }
+    std::vector<Rec> recs2;
+    rc = run_select(b, a, 1, top_n, recs2);
+    if (rc) return rc;
+    for (size_t i = 0; i < recs2.size(); i++) {
+        scores[i] = recs2[i].score();
+        lags[i] = recs2[i].lag();
+        series_idx[i] = b->g->global_offset + recs2[i].idx;
+    }
+    *n_out = (int64_t)recs2.size();
+    return finish_timing(b);
+}
+
 extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n,
                                  double threshold, int32_t sign_filter, int32_t mode, int32_t signed_scores, double *scores,
                                  int64_t *lags, int64_t *series_idx, int64_t *n_out) {
@@ -1329,49 +1384,15 @@ extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t
     CU(cudaSetDevice(b->ctx->device));
     RunArgs a{key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, signed_scores};
     *n_out = 0;
-    if (n_key_cols == 0 && top_n > 0 && top_n <= 65536 && b->g->size > 0) {
+    if (device_topn_applies(b, a)) {
         // ungrouped: filter and top-N on the device, ONE copy of top_n records to the host
         rc = ensure_scratch(b);
         if (rc) return rc;
         if (top_n * 4 <= b->scratch_cap) {
-            muse_partial *d_rec = reinterpret_cast<muse_partial *>(b->d_skey);      // free scratch in this path
-            rc = queue_topn_records(b, a, d_rec, top_n);
+            rc = device_topn_queue(b, a);
             if (rc) return rc;
-            cudaStream_t st = b->ctx->stream;
-            const muse_partial *h_rec = reinterpret_cast<const muse_partial *>(b->h_pin + 64);
-            CU(cudaMemcpyAsync(b->h_pin + 64, d_rec, sizeof(muse_partial) * (size_t)top_n, cudaMemcpyDeviceToHost, st));
-            CU(cudaEventRecord(b->ev[3], st));
-            CU(cudaStreamSynchronize(st));
-            if (h_rec[0].flags != 2) {
-                int64_t k = 0;
-                for (; k < top_n && h_rec[k].flags == 0; k++) {
-                    scores[k] = h_rec[k].score;
-                    lags[k] = h_rec[k].lag;
-                    series_idx[k] = h_rec[k].series_idx;
-                }
-                *n_out = k;
-                muse_timing t;
-                return muse_batch_last_timing(b, &t);      // settles timing_pending (events are complete)
-            }
-            // the candidate list was too long for the device-side select (or the fused path's exact launch
-            // did not cover its list): the host path below finishes from the scores already on the device
-            b->timing_pending = 0;
-            const unsigned long long *h_n = reinterpret_cast<const unsigned long long *>(b->h_pin);
-            if (b->fused_run == 1) {
-                rc = run_fused_overflow(b, (int64_t)h_n[2], true);
-                if (rc) return rc;
-                b->fused_run = 0;
-            }
-            std::vector<Rec> recs2;
-            rc = run_select(b, a, 1, top_n, recs2);
-            if (rc) return rc;
-            for (size_t i = 0; i < recs2.size(); i++) {
-                scores[i] = recs2[i].score();
-                lags[i] = recs2[i].lag();
-                series_idx[i] = b->g->global_offset + recs2[i].idx;
-            }
-            *n_out = (int64_t)recs2.size();
-            return finish_timing(b);
+            CU(cudaStreamSynchronize(b->ctx->stream));
+            return device_topn_finish(b, a, scores, lags, series_idx, n_out);
         }
     }
     rc = run_scores(b, a);
@@ -1632,13 +1653,12 @@ static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag,
         m.cut = b->d_cut;
         m.out_U = b->d_U;
     }
-    MultiQuery *d_q = nullptr;
-    CU(cudaMalloc(&d_q, sizeof(MultiQuery) * (size_t)nq));
-    cudaError_t e = cudaMemcpyAsync(d_q, hq.data(), sizeof(MultiQuery) * (size_t)nq, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = launch_screen_multi(sp0, d_q, nq, ctx->sm_count, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // hq and d_q are released below
-    cudaFree(d_q);
-    CU(e);
+    // the query table lives with the context (stream-ordered reuse: copy and launch go down the same stream; a copy
+    // from pageable memory has left the host buffer when the call returns), so nothing here waits for the kernel
+    if (!ctx->d_multi_q) CU(cudaMalloc(&ctx->d_multi_q, sizeof(MultiQuery) * (size_t)ScreenMultiCfg::QC));
+    MultiQuery *d_q = static_cast<MultiQuery *>(ctx->d_multi_q);
+    CU(cudaMemcpyAsync(d_q, hq.data(), sizeof(MultiQuery) * (size_t)nq, cudaMemcpyHostToDevice, st));
+    CU(launch_screen_multi(sp0, d_q, nq, ctx->sm_count, st));
     for (int q = 0; q < nq; q++) bs[q]->prescreened = 1;
     return MUSE_OK;
 }
@@ -1677,10 +1697,28 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
                 which[live++] = q0 + i;
             }
         }
-        if (rc == MUSE_OK && one_pass && live > 1) rc = screen_multi(ctx, bs, live, max_lag, top_n, threshold);
+        bool queued = false;
+        if (rc == MUSE_OK && one_pass && live > 1) {
+            rc = screen_multi(ctx, bs, live, max_lag, top_n, threshold);
+            // the tails of all queries of the launch are queued back to back; ONE synchronisation for the lot
+            for (int i = 0; i < live && rc == MUSE_OK; i++) {
+                RunArgs a{nullptr, 0, max_lag, top_n, threshold, sign_filter, MUSE_MODE_SCREEN, 0};
+                rc = device_topn_queue(bs[i], a);
+            }
+            if (rc == MUSE_OK) {
+                cudaError_t e = cudaStreamSynchronize(ctx->stream);
+                if (e != cudaSuccess) rc = fail(MUSE_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+            }
+            queued = rc == MUSE_OK;
+        }
         for (int i = 0; i < live; i++) {
             const int64_t q = which[i];
-            if (rc == MUSE_OK)
+            if (rc == MUSE_OK && queued) {
+                RunArgs a{nullptr, 0, max_lag, top_n, threshold, sign_filter, MUSE_MODE_SCREEN, 0};
+                n_out[q] = 0;
+                rc = device_topn_finish(bs[i], a, scores + (size_t)q * (size_t)top_n, lags + (size_t)q * (size_t)top_n,
+                                        series_idx + (size_t)q * (size_t)top_n, n_out + q);
+            } else if (rc == MUSE_OK)
                 rc = muse_batch_run_ex(bs[i], key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter,
                                        bs[i]->prescreened ? MUSE_MODE_SCREEN : mode, 0,
                                        scores ? scores + (size_t)q * (size_t)top_n : nullptr, lags ? lags + (size_t)q * (size_t)top_n : nullptr,
