@@ -617,7 +617,10 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     return MUSE_OK;
 }
 
-extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out) {
+// NewBatch in two halves, so that the references of a multi-query launch share ONE round trip: queue = everything
+// up to the copies of the std-zero flag and the middle-bin values into the batch's pinned mailbox; finish (after the
+// stream has been synchronised) = the error of muse_batch.go:38-41 (the batch is destroyed) or the by-value parameters.
+static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out) {
     if (!ctx || !g || !ref || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_create: NULL argument");
     if (g->ctx != ctx) return fail(MUSE_ERR_INVALID_ARG, "group belongs to another context");
     if (ref_len != g->N)   // muse_batch.go:24-28
@@ -694,16 +697,39 @@ extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref
     float *h_mid = reinterpret_cast<float *>(b->h_pin + 16);
     CU(cudaMemcpyAsync(h_flag, b->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (screen) CU(cudaMemcpyAsync(h_mid, b->d_mid, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    b->screen_ok = screen ? -1 : 0;      // -1: pending until batch_create_finish
+    *out = b;
+    return MUSE_OK;
+}
+
+static int batch_create_finish(muse_batch *b) {
+    const int32_t *h_flag = reinterpret_cast<const int32_t *>(b->h_pin);
+    const float *h_mid = reinterpret_cast<const float *>(b->h_pin + 16);
     if (*h_flag) {   // muse_batch.go:38-41
         muse_batch_destroy(b);
         return fail(MUSE_ERR_STDDEV_ZERO, "Invalid input query, Standard deviation of zero");
     }
-    if (screen) {
+    if (b->screen_ok == -1) {
         b->a_mid = h_mid[1];
         b->x_mid = cf{h_mid[2], h_mid[3]};
         b->screen_ok = 1;
     }
+    return MUSE_OK;
+}
+
+extern "C" void muse_batch_destroy(muse_batch *b);
+
+extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out) {
+    muse_batch *b = nullptr;
+    int rc = batch_create_queue(ctx, g, ref, ref_len, &b);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        muse_batch_destroy(b);
+        return fail(MUSE_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    }
+    rc = batch_create_finish(b);
+    if (rc) return rc;
     *out = b;
     return MUSE_OK;
 }
@@ -1684,16 +1710,25 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
         muse_batch *bs[QC];
         int64_t which[QC];
         int live = 0, rc = MUSE_OK;
-        for (int i = 0; i < nq && rc == MUSE_OK; i++) {
-            muse_batch *b = nullptr;
-            rc = muse_batch_create(ctx, g, refs + (size_t)(q0 + i) * (size_t)ref_len, ref_len, &b);
-            if (rc == MUSE_ERR_STDDEV_ZERO) {   // muse_batch.go:38-41: this query has no Batch; the others do
-                n_out[q0 + i] = -1;
-                rc = MUSE_OK;
+        muse_batch *made[QC];
+        int n_made = 0;
+        for (int i = 0; i < nq && rc == MUSE_OK; i++) {      // the references of the launch: queued back to back, ONE round trip
+            rc = batch_create_queue(ctx, g, refs + (size_t)(q0 + i) * (size_t)ref_len, ref_len, &made[n_made]);
+            if (rc == MUSE_OK) n_made++;
+        }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == MUSE_OK) rc = fail(MUSE_ERR_CUDA, "cudaStreamSynchronize failed");
+        for (int i = 0; i < n_made; i++) {
+            if (rc != MUSE_OK) {
+                muse_batch_destroy(made[i]);
                 continue;
             }
-            if (rc == MUSE_OK) {
-                bs[live] = b;
+            const int rf = batch_create_finish(made[i]);
+            if (rf == MUSE_ERR_STDDEV_ZERO) {   // muse_batch.go:38-41: this query has no Batch; the others do
+                n_out[q0 + i] = -1;
+            } else if (rf != MUSE_OK) {
+                rc = rf;
+            } else {
+                bs[live] = made[i];
                 which[live++] = q0 + i;
             }
         }

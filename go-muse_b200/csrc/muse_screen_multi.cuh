@@ -4,7 +4,7 @@
 // go-muse builds one Batch per reference (muse_batch.go:23-52), so Q queries stream the store Q times and
 // transform every series Q times.  Nothing about a series' spectrum depends on the reference: here a warp
 // loads its row and runs the forward FFT_1024 ONCE, keeps the 1024 magnitudes |2Y_k| in registers (as the 16
-// mirror pairs + the middle bin of muse_screen.cuh) and the spectrum itself in a per-warp shared-memory stash,
+// mirror pairs + the middle bin of muse_screen.cuh) and the spectrum itself in shared memory (the warp's row buffer),
 // and then walks the queries of the launch:
 //     U_q = (1/n) sum_f |Y_f| |X_q,f| / std * (1 + 1e-5) + slack      (16 packed FMAs against the query's weights,
 //                                                                       which sit in shared memory for the whole launch)
@@ -35,17 +35,21 @@ struct MultiQuery {
     float *out_U;         // [count] upper bound on the score for this query
 };
 
+#ifndef MUSE_MULTI_WARPS
+#define MUSE_MULTI_WARPS 10   // measured (16 queries x 1 M series): 7 warps + separate stash 8.04 ms, 12 warps 7.93 ms, 10 warps 7.32 ms
+#endif
 struct ScreenMultiCfg {
     using G = Geo<10, 5>;
-    static constexpr int MAX_WARPS = 8;         // 256 threads x up to 255 registers: the second stage holds two spectra and the magnitudes
+    static constexpr int MAX_WARPS = MUSE_MULTI_WARPS;   // 168 registers per thread, no spills
     static constexpr int QC = 16;               // queries per launch (their weights: 64 KB of shared memory)
     static constexpr int NREF = ScreenWarpCfg::NREF;
     static constexpr size_t SMEM_BUDGET = 227 * 1024;
     static constexpr size_t EX_BYTES = ScreenWarpCfg::EX_BYTES;
     static constexpr size_t STASH_BYTES = (size_t)G::M * sizeof(cf);
     static constexpr size_t W_BYTES = (size_t)QC * (G::M / 2) * sizeof(cf) + 128;      // weights + A[M/2] per query
-    static size_t row_bytes(int N) { return ScreenWarpCfg::row_bytes(N); }
-    static size_t warp_bytes(int N) { return row_bytes(N) + STASH_BYTES; }
+    // one buffer per warp, three uses in turn: the row (bulk copy), the forward FFT exchange, the spectrum stash
+    static size_t row_bytes(int N) { const size_t r = ScreenWarpCfg::row_bytes(N); return r > STASH_BYTES ? r : STASH_BYTES; }
+    static size_t warp_bytes(int N) { return row_bytes(N); }
     static int warps(int N) {
         const size_t w = (SMEM_BUDGET - NREF * EX_BYTES - W_BYTES) / warp_bytes(N);
         return (int)(w > MAX_WARPS ? MAX_WARPS : w);
@@ -84,7 +88,7 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
     unsigned char *buf = smem_raw + (size_t)w * warp_bytes;
     const cd *rowc = reinterpret_cast<const cd *>(buf);
     cf *sm = reinterpret_cast<cf *>(buf);                       // forward exchange: the row buffer itself
-    cf *stash = reinterpret_cast<cf *>(buf + row_bytes);        // the series' spectrum, slot j of lane t at [32 j + t]
+    cf *stash = reinterpret_cast<cf *>(buf);                    // ... and then the series' spectrum, slot j of lane t at [32 j + t]
     unsigned char *refbase = smem_raw + (size_t)nwarps * warp_bytes;
     cf *sA = reinterpret_cast<cf *>(refbase + (size_t)C::NREF * C::EX_BYTES);     // [nq][512] (A[k], A[M-k])
     float *sAmid = reinterpret_cast<float *>(sA + (size_t)C::QC * (M / 2));       // [nq] A[M/2]
@@ -144,13 +148,10 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
         __syncwarp();
         fft_pass_load<10, 5, 1, float>(v, sm, t);
         __syncwarp();
-        if (t == 0 && next < count) {
-            asm volatile("" ::"r"(__float_as_uint(v[P - 1].y)) : "memory");
-            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
-        }
         Dft<P, float>::run(v);                          // v[Perm(j)] = Z[t + 32*j]
 
-        // ---- the spectrum goes to the stash (every lane reads back only what it wrote: no barrier) ----
+        // ---- the spectrum goes to the stash: the same buffer once more (the exchange has been read, __syncwarp above;
+        //      every lane reads back only what it wrote) ----
 #pragma unroll
         for (int j = 0; j < P; j++) stash[32 * j + t] = v[Perm<P>::at(j)];
 
@@ -304,6 +305,14 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
             if (t == q) my_U = U;
         }
         if (my_out) my_out[pos] = my_U;
+        // the stash is no longer needed: hand the buffer to the copy engine for the warp's next row.  (No prefetch under
+        // the transform as in 5.2: a separate stash costs 8 KB per warp, i.e. 7 warps per SM instead of 10 - 12, and this
+        // kernel is bound by latency hiding, not by DRAM.)
+        __syncwarp();
+        if (t == 0 && next < count) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
+        }
     }
 }
 
