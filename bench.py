@@ -175,25 +175,23 @@ def run_c5(args, mb, torch, dist, rank, local_rank, world, mode):
         refs[q] += 0.1 * (rng.random(N) - 0.5)
 
     def step():
-        out = mb.multi_run(store, refs, [], args.max_lag, top_n, args.threshold, 0, mode=mode)
+        sc, lg, ix, n_out = mb.multi_run(store, refs, [], args.max_lag, top_n, args.threshold, 0, mode=mode, raw=True)
         if world == 1:
-            return out
-        # fixed-size records per query: (score, lag, global index), padded with score -1
-        rec = np.full((Q, top_n, 3), -1.0)
-        for q, o in enumerate(out):
-            k = len(o[0])
-            rec[q, :k, 0], rec[q, :k, 1], rec[q, :k, 2] = o[0], o[1], o[2]
+            return [(sc[q, :n_out[q]], lg[q, :n_out[q]], ix[q, :n_out[q]]) for q in range(Q)]
+        # fixed-size records per query: (score, lag, global index), padded with score -1; one all-gather, then the
+        # per-query merge (score desc, index asc: results.go:81-85) for all queries at once
+        valid = np.arange(top_n)[None, :] < n_out[:, None]
+        rec = np.stack([np.where(valid, sc, -1.0), lg.astype(np.float64), ix.astype(np.float64)], axis=-1)
         mine = torch.from_numpy(rec).cuda(non_blocking=True)
         allr = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
         dist.all_gather_into_tensor(allr, mine)
-        allr = allr.cpu().numpy()
-        merged = []
-        for q in range(Q):
-            r = allr[:, q].reshape(-1, 3)
-            r = r[r[:, 0] >= 0]
-            order = np.lexsort((r[:, 2], -r[:, 0]))[:top_n]     # score desc, index asc (results.go:81-85)
-            merged.append((r[order, 0], r[order, 1].astype(np.int64), r[order, 2].astype(np.int64)))
-        return merged
+        # shards hold ascending global indices and each shard's list is already (score desc, index asc): a STABLE
+        # sort by score over the rank-ordered concatenation breaks ties by index
+        r = allr.permute(1, 0, 2, 3).reshape(Q, world * top_n, 3)
+        order = torch.sort(-r[..., 0], dim=-1, stable=True).indices[:, :top_n]
+        r = torch.gather(r, 1, order[..., None].expand(-1, -1, 3)).cpu().numpy()
+        k = (r[..., 0] >= 0).sum(axis=1)
+        return [(r[q, :k[q], 0], r[q, :k[q], 1].astype(np.int64), r[q, :k[q], 2].astype(np.int64)) for q in range(Q)]
 
     def barrier():
         if world > 1:

@@ -389,9 +389,11 @@ def merge_partials(parts: np.ndarray, max_lag: int, top_n: int, threshold: float
 
 
 def multi_run(store: "DeviceStore", refs, key_cols: Sequence[int], max_lag: int, top_n: int, threshold: float,
-              sign_filter: int = 0, mode: int = MODE_AUTO):
+              sign_filter: int = 0, mode: int = MODE_AUTO, raw: bool = False):
     """muse_multi_run: every row of refs as a NewBatch + Run against the resident store.  Returns one
-    (scores, lags, series_idx) triple per reference, None where the reference has zero std."""
+    (scores, lags, series_idx) triple per reference, None where the reference has zero std; raw=True returns the
+    call's own outputs instead: (scores[Q, top_n], lags[Q, top_n], series_idx[Q, top_n], n_out[Q]), n_out -1 for such
+    a reference."""
     R = np.ascontiguousarray(refs, dtype=np.float64)
     assert R.ndim == 2
     Q, cap = R.shape[0], max(1, int(top_n))
@@ -403,6 +405,8 @@ def multi_run(store: "DeviceStore", refs, key_cols: Sequence[int], max_lag: int,
     _check(lib().muse_multi_run(store.ctx.h, store.h, _d(R), Q, R.shape[1], kc.ctypes.data_as(_ip32) if kc.size else None,
                                 kc.size, max_lag, top_n, threshold, sign_filter, mode, _d(sc), lg.ctypes.data_as(_ip64),
                                 ix.ctypes.data_as(_ip64), n_out.ctypes.data_as(_ip64)))
+    if raw:
+        return sc[:Q], lg[:Q], ix[:Q], n_out[:Q]
     return [None if n_out[q] < 0 else (sc[q, :n_out[q]].copy(), lg[q, :n_out[q]].copy(), ix[q, :n_out[q]].copy())
             for q in range(Q)]
 
