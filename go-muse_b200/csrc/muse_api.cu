@@ -91,6 +91,7 @@ struct RunScratch {
     float4 *sx_f;                     // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
     float *d_mid;                     // [0] std-zero flag of the reference (as float bits), [1] A[M/2], [2..3] Xt[M/2] in fp32
     cudaEvent_t ev[4];
+    cudaStream_t aux;                 // the batch's own stream: the tails of the queries of a multi-query launch run side by side
 };
 
 struct muse_ctx {
@@ -130,7 +131,10 @@ struct muse_batch : RunScratch {
     int timing_pending;    // the last run was queued without a final synchronisation (muse_batch_run_partial_device)
     int fused_run;         // 1: score_fused, 2: score_fused_grouped (d_counters[2] = exact list length, [3] = refined)
     int prescreened;       // d_U and the cut-off state were filled by score_screen_multi_kernel: the next fused run starts at its tail
+    int use_aux;           // queue this batch's work on its own stream (RunScratch::aux) instead of the context's
 };
+
+static inline cudaStream_t bstream(const muse_batch *b) { return b->use_aux ? b->aux : b->ctx->stream; }
 
 struct DeviceGuard {
     int prev;
@@ -173,6 +177,7 @@ static void scratch_free(RunScratch &r) {
     cudaFree(r.d_ref); cudaFree(r.Xt); cudaFree(r.twM); cudaFree(r.twn);
     cudaFree(r.twp_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.d_mid);
     for (int i = 0; i < 4; i++) if (r.ev[i]) cudaEventDestroy(r.ev[i]);
+    if (r.aux) cudaStreamDestroy(r.aux);
     if (r.h_pin) cudaFreeHost(r.h_pin);
     memset(&r, 0, sizeof(r));
 }
@@ -566,7 +571,7 @@ __global__ void screen_tables_kernel(const cd *__restrict__ Xt, int M, const flo
 // Twiddle tables of FFT length n (they depend on n alone): filled when the scratch set was last used for another n.
 static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     const int64_t n = b->n, M = n / 2;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     if (b->d_ref_cap < ld) {
         cudaFree(b->d_ref);
         b->d_ref = nullptr;
@@ -749,7 +754,7 @@ static void free_scratch(muse_batch *b) {
 extern "C" void muse_batch_destroy(muse_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
-    cudaStreamSynchronize(b->ctx->stream);
+    cudaStreamSynchronize(bstream(b));
     {   // the store-sized scratch goes back to the context (at most 4 sets are kept)
         std::lock_guard<std::mutex> lk(b->ctx->mu);
         if (b->ctx->pool.size() < MUSE_SCRATCH_POOL) {
@@ -808,7 +813,7 @@ static int score_exact_all(muse_batch *b, int signed_scores, const int32_t *idx,
     p.out_score = b->d_score;
     p.out_lag = b->d_lag;
     if (count > 0) {
-        CU(launch_exact<MODE_SCORE>(b->log2m, p, b->ctx->stream));
+        CU(launch_exact<MODE_SCORE>(b->log2m, p, bstream(b)));
         b->timing.n_launches++;
     }
     return MUSE_OK;
@@ -824,9 +829,9 @@ extern "C" int muse_batch_score_all(muse_batch *b, int32_t signed_scores, double
     const int64_t S = b->g->size;
     rc = score_exact_all(b, signed_scores, nullptr, S);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(scores, b->d_score, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, b->ctx->stream));
-    CU(cudaMemcpyAsync(lags, b->d_lag, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, b->ctx->stream));
-    CU(cudaStreamSynchronize(b->ctx->stream));
+    CU(cudaMemcpyAsync(scores, b->d_score, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, bstream(b)));
+    CU(cudaMemcpyAsync(lags, b->d_lag, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToHost, bstream(b)));
+    CU(cudaStreamSynchronize(bstream(b)));
     return MUSE_OK;
 }
 
@@ -848,11 +853,11 @@ extern "C" int muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, 
     p.twn = b->twn;
     p.out_score = d_cc;
     p.out_flag = b->d_flag;
-    CU(launch_exact<MODE_CC>(b->log2m, p, b->ctx->stream));
+    CU(launch_exact<MODE_CC>(b->log2m, p, bstream(b)));
     int32_t flag = 0;
-    CU(cudaMemcpyAsync(cc, d_cc, sizeof(double) * (size_t)b->n, cudaMemcpyDeviceToHost, b->ctx->stream));
-    CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, b->ctx->stream));
-    CU(cudaStreamSynchronize(b->ctx->stream));
+    CU(cudaMemcpyAsync(cc, d_cc, sizeof(double) * (size_t)b->n, cudaMemcpyDeviceToHost, bstream(b)));
+    CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, bstream(b)));
+    CU(cudaStreamSynchronize(bstream(b)));
     cudaFree(d_cc);
     if (std_zero) *std_zero = flag;
     return MUSE_OK;
@@ -920,7 +925,7 @@ static int setup_group_table(muse_batch *b, const RunArgs &a, KeyCols &kc, Group
     gt.gmax = b->d_gmax;
     gt.gidx = b->d_gidx;
     gt.hkeys = b->d_hkeys;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     CU(cudaMemsetAsync(gt.gmax, 0, sizeof(unsigned long long) * (size_t)slots, st));
     CU(cudaMemsetAsync(gt.gidx, 0x7f, sizeof(int32_t) * (size_t)slots, st));
     if (!gt.dense) CU(cudaMemsetAsync(gt.hkeys, 0, sizeof(unsigned long long) * (size_t)slots, st));
@@ -937,7 +942,7 @@ static int run_fused_overflow(muse_batch *b, int64_t n_exact, bool refill);
 static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t limit, std::vector<Rec> &recs) {
     muse_group *g = b->g;
     const int64_t S = g->size;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     recs.clear();
     if (S == 0) return MUSE_OK;
     const unsigned blocks = (unsigned)((S + 255) / 256);
@@ -1148,7 +1153,7 @@ static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t m
     int rc = refresh_row_stats(b->g);
     if (rc) return rc;
     sp.row_stat = b->g->row_stat;
-    init_cut_kernel<<<(4 + MUSE_CUT_WORDS + 255) / 256, 256, 0, b->ctx->stream>>>(b->d_cut, cut0);
+    init_cut_kernel<<<(4 + MUSE_CUT_WORDS + 255) / 256, 256, 0, bstream(b)>>>(b->d_cut, cut0);
     CU(cudaGetLastError());
     const int64_t n = b->n, pad = n - b->N;
     if (max_lag < 0) max_lag = -1;                          // nothing passes |lag| <= max_lag
@@ -1192,7 +1197,7 @@ extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t m
     if (rc) return rc;
     const int64_t S = b->g->size;
     if (S == 0) return MUSE_OK;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     ScreenParams sp = screen_params(b);
     if (refine) {
         rc = ensure_lower(b);
@@ -1217,7 +1222,7 @@ extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t m
 // MUSE_EXACT_UB series and skips what the list does not hold.
 static int score_fused(muse_batch *b, const RunArgs &a) {
     const int64_t S = b->g->size;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     ScreenParams sp = screen_params(b);
     const float thr_lo = a.threshold > 0 ? (float)a.threshold * 0.999999f : 0.f;   // never above the fp64 threshold
     int rc = MUSE_OK;
@@ -1247,7 +1252,7 @@ static int score_fused(muse_batch *b, const RunArgs &a) {
 // exactly as in an all-exact run (every other member is provably below its group's representative).
 static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
     const int64_t S = b->g->size;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     ScreenParams sp = screen_params(b);
     int rc = ensure_lower(b);
     if (rc) return rc;
@@ -1286,7 +1291,7 @@ static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
 static int run_fused_overflow(muse_batch *b, int64_t n_exact, bool refill) {
     const int64_t S = b->g->size;
     if (refill) {
-        CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, b->ctx->stream));
+        CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, bstream(b)));
         return score_exact_all(b, 0, b->d_list, n_exact);
     }
     if (n_exact <= std::min<int64_t>(S, MUSE_EXACT_UB)) return MUSE_OK;
@@ -1299,7 +1304,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     memset(&b->timing, 0, sizeof(b->timing));
     b->fused_run = 0;
     b->timing_pending = 0;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     CU(cudaEventRecord(b->ev[0], st));
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
     // screening needs: a kernel for this FFT size, an ungrouped unsigned run, a sign filter that
@@ -1334,7 +1339,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
 }
 
 static int finish_timing(muse_batch *b) {
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     CU(cudaEventRecord(b->ev[3], st));
     CU(cudaEventSynchronize(b->ev[3]));
     cudaEventElapsedTime(&b->timing.total_ms, b->ev[0], b->ev[3]);
@@ -1359,7 +1364,7 @@ static int device_topn_queue(muse_batch *b, const RunArgs &a) {
     muse_partial *d_rec = reinterpret_cast<muse_partial *>(b->d_skey);      // free scratch in this path
     int rc = queue_topn_records(b, a, d_rec, a.top_n);
     if (rc) return rc;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     CU(cudaMemcpyAsync(b->h_pin + 64, d_rec, sizeof(muse_partial) * (size_t)a.top_n, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(b->ev[3], st));
     return MUSE_OK;
@@ -1417,7 +1422,7 @@ extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t
         if (top_n * 4 <= b->scratch_cap) {
             rc = device_topn_queue(b, a);
             if (rc) return rc;
-            CU(cudaStreamSynchronize(b->ctx->stream));
+            CU(cudaStreamSynchronize(bstream(b)));
             return device_topn_finish(b, a, scores, lags, series_idx, n_out);
         }
     }
@@ -1466,7 +1471,7 @@ static int queue_topn_records(muse_batch *b, const RunArgs &a_in, muse_partial *
     int rc = run_scores(b, a);
     if (rc) return rc;
     const int64_t S = b->g->size;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 2, st));
     if (S > 0) {
         FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
@@ -1514,7 +1519,7 @@ static int host_keys(muse_batch *b, const RunArgs &a, const std::vector<Rec> &re
     keys.resize(recs.size());
     muse_group *g = b->g;
     const int bits = 64 / a.n_key_cols;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     std::vector<int32_t> ids(recs.size() * (size_t)a.n_key_cols);
     if (recs.size() > 4096) {
         std::vector<int32_t> col((size_t)g->size);
@@ -1735,15 +1740,24 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
         bool queued = false;
         if (rc == MUSE_OK && one_pass && live > 1) {
             rc = screen_multi(ctx, bs, live, max_lag, top_n, threshold);
-            // the tails of all queries of the launch are queued back to back; ONE synchronisation for the lot
-            for (int i = 0; i < live && rc == MUSE_OK; i++) {
+            // the tails of the queries are independent and small (a few thousand series each): every batch queues its
+            // tail on its own stream behind the multi-query kernel, so they share the GPU instead of taking turns
+            cudaEvent_t screened = nullptr;
+            cudaError_t e = cudaEventCreateWithFlags(&screened, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(screened, ctx->stream);
+            for (int i = 0; i < live && rc == MUSE_OK && e == cudaSuccess; i++) {
+                muse_batch *b = bs[i];
+                if (!b->aux) e = cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(b->aux, screened, 0);
+                if (e != cudaSuccess) break;
+                b->use_aux = 1;
                 RunArgs a{nullptr, 0, max_lag, top_n, threshold, sign_filter, MUSE_MODE_SCREEN, 0};
-                rc = device_topn_queue(bs[i], a);
+                rc = device_topn_queue(b, a);
             }
-            if (rc == MUSE_OK) {
-                cudaError_t e = cudaStreamSynchronize(ctx->stream);
-                if (e != cudaSuccess) rc = fail(MUSE_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
-            }
+            for (int i = 0; i < live; i++)
+                if (bs[i]->use_aux && cudaStreamSynchronize(bs[i]->aux) != cudaSuccess && e == cudaSuccess) e = cudaErrorUnknown;
+            if (screened) cudaEventDestroy(screened);
+            if (e != cudaSuccess && rc == MUSE_OK) rc = fail(MUSE_ERR_CUDA, "muse_multi_run: %s", cudaGetErrorString(e));
             queued = rc == MUSE_OK;
         }
         for (int i = 0; i < live; i++) {
@@ -1929,7 +1943,7 @@ extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t 
     rc = run_scores(b, a);
     if (rc) return rc;
     const int64_t S = b->g->size;
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = bstream(b);
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 2, st));
     if (S > 0) {
         FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
