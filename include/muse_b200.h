@@ -189,10 +189,14 @@ int  muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t max_lag, fl
  * return value; KAT support).  *std_zero is set when xcorr.go:165-168 applies. */
 int  muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, int32_t *std_zero);
 
-/* Many reference queries against ONE resident store: n_refs x (NewBatch + Batch.Run) (muse_batch.go:23-52,
- * :99-130) in one call.  refs: host rows [n_refs][ref_len]; outputs: row q of scores / lags / series_idx
+/* Many reference queries against ONE resident store: what n_refs x (NewBatch + Batch.Run) (muse_batch.go:23-52,
+ * :99-130) return, in one call.  refs: host rows [n_refs][ref_len]; outputs: row q of scores / lags / series_idx
  * (capacity top_n each row) and n_out[q] = results of query q, or -1 when reference q has std == 0
- * (muse_batch.go:38-41: NewBatch fails for that query only).  Arguments as muse_batch_run_ex. */
+ * (muse_batch.go:38-41: NewBatch fails for that query only).  Arguments as muse_batch_run_ex.
+ * For FFT length 2048, ungrouped, unsigned runs over >= 16384 series the store is read and every series
+ * transformed ONCE per 16 references (score_screen_multi_kernel: per-query bounds, second stage and running
+ * cut-off; each query then finishes on the exact fp64 kernel like a single run) -- results identical to the
+ * separate runs; other shapes are served as separate batches on the resident store. */
 int  muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len,
                     const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag, int64_t top_n, double threshold,
                     int32_t sign_filter, int32_t mode,
