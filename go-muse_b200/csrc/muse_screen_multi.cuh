@@ -16,7 +16,7 @@
 // bounds is that of muse_screen.cuh (the same operations on the same values; only the order of the 33-term
 // accumulation differs, which the 1e-5 relative slack covers 30 times over).
 //
-// Cost per (series, query): 16 LDS.64 + 16 FFMA2 + a 5-step butterfly ~ 60 warp instructions (four queries at a
+// Cost per (series, query): 8 LDS.128 + 16 FFMA2 + a 5-step butterfly ~ 50 warp instructions (four queries at a
 // time, so that their dependency chains overlap), against ~1000 for the row's load + transform, which is paid
 // once per launch instead of once per query.
 #pragma once
@@ -104,9 +104,12 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
         mbar_init(bar, 1);
         if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)N * 8u, bar);
     }
+    // weights of query q for the mirror pairs k = t + 32 j: the pairs of slots j = 2 j2 and 2 j2 + 1 share one 16-byte
+    // entry [q][j2][t] (one LDS.128 per two packed FMAs)
     for (int i = threadIdx.x; i < nq * (M / 2); i += blockDim.x) {
-        const float4 s = queries[i >> 9].sw[i & (M / 2 - 1)];
-        sA[i] = cf{s.z, s.w};
+        const int q = i >> 9, k = i & (M / 2 - 1), j = k >> 5, tt = k & 31;
+        const float4 s = queries[q].sw[k];
+        sA[((q * (P / 4) + (j >> 1)) * 32 + tt) * 2 + (j & 1)] = cf{s.z, s.w};
     }
     if ((int)threadIdx.x < nq) sAmid[threadIdx.x] = queries[threadIdx.x].a_mid;
     // lane q looks after query q: its cut-off word and its row of bounds
@@ -192,12 +195,13 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int qi = q + i < nq ? q + i : nq - 1;
-                const cf *Aq = sA + (size_t)qi * (M / 2) + t;
+                const float4 *Aq = reinterpret_cast<const float4 *>(sA) + (size_t)qi * (M / 4) + t;
                 cf a0{0.f, 0.f}, a1{0.f, 0.f};
 #pragma unroll
-                for (int j = 0; j < P / 2; j += 2) {
-                    a0 = pfma(mg[j], Aq[32 * j], a0);
-                    a1 = pfma(mg[j + 1], Aq[32 * (j + 1)], a1);
+                for (int j2 = 0; j2 < P / 4; j2++) {
+                    const float4 wq = Aq[32 * j2];
+                    a0 = pfma(mg[2 * j2], cf{wq.x, wq.y}, a0);
+                    a1 = pfma(mg[2 * j2 + 1], cf{wq.z, wq.w}, a1);
                 }
                 acc4[i] = fmaf(mg_mid, sAmid[qi], (a0.x + a0.y) + (a1.x + a1.y));
             }
