@@ -40,9 +40,11 @@ static int fail(int code, const char *fmt, ...) {
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess)                                                                     \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError(); /* reported here: must not resurface in a later cudaGetLastError() check */ \
             return fail(e_ == cudaErrorMemoryAllocation ? MUSE_ERR_OUT_OF_MEMORY : MUSE_ERR_CUDA,  \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
     } while (0)
 
 extern "C" const char *muse_last_error(void) { return g_err; }
@@ -1885,6 +1887,8 @@ extern "C" int muse_exchange_create(muse_ctx *ctx, int32_t rank, int32_t world, 
 extern "C" int muse_exchange_ipc_handle(muse_exchange *x, void *handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     if (!x || !handle64) return fail(MUSE_ERR_INVALID_ARG, "muse_exchange_ipc_handle: NULL argument");
+    if (getenv("MUSE_B200_NO_IPC"))      // test hook: behave like a box where CUDA IPC is closed (callers fall back to the all-gather path)
+        return fail(MUSE_ERR_UNSUPPORTED, "CUDA IPC disabled by MUSE_B200_NO_IPC");
     CU(cudaSetDevice(x->ctx->device));
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, x->base));
