@@ -581,6 +581,23 @@ def NewGroup(name: str) -> Group:
     return Group(name)
 
 
+def _go_float(f: float) -> str:
+    """encoding/json's float64 formatting: shortest digits that round-trip, %f form for 1e-6 <= |f| < 1e21, else
+    %e form with a one- or two-digit exponent cleaned up as Go does (1e-07 -> 1e-7)."""
+    from decimal import Decimal
+    if f == 0:
+        return "-0" if str(f).startswith("-") else "0"
+    d = Decimal(repr(f))
+    if 1e-6 <= abs(f) < 1e21:
+        t = format(d, "f")
+        return t.rstrip("0").rstrip(".") if "." in t else t
+    sign, digits, exp = d.as_tuple()
+    ds = "".join(map(str, digits)).rstrip("0") or "0"
+    e10 = exp + len(digits) - 1
+    mant = ds[0] + ("." + ds[1:] if len(ds) > 1 else "")
+    return "%s%se%s%d" % ("-" if sign else "", mant, "-" if e10 < 0 else "+", abs(e10))
+
+
 class Score:
     """scores.go:11-15."""
 
@@ -602,7 +619,7 @@ class Score:
         if self.PercentScore != self.PercentScore or abs(self.PercentScore) == float("inf"):
             raise ValueError("json: unsupported value: %r" % self.PercentScore)     # as encoding/json
         return '{"labels":%s,"lag":%d,"percentScore":%s}' % ("{}" if self.Labels is not None else "null", self.Lag,
-                                                           json.dumps(float(self.PercentScore)))
+                                                           _go_float(float(self.PercentScore)))
 
 
 class Results:

@@ -142,3 +142,19 @@ def test_merge_partials_against_a_model():
         assert sc.tolist() == [float(p["score"]) for p in keep]
 
     check()
+
+
+def test_score_json_is_what_encoding_json_writes():
+    # scores.go:11-15: field order labels / lag / percentScore; *Labels has only unexported fields (labels.go:14-17),
+    # so encoding/json writes {} for a non-nil pointer and null for nil
+    import json
+    import muse_b200 as mb
+    s = mb.Score(mb.NewLabels({"graph": "g1", "host": "h1"}), -3, 0.75)
+    assert s.MarshalJSON() == '{"labels":{},"lag":-3,"percentScore":0.75}'
+    assert mb.Score(None, 0, 1.0).MarshalJSON() == '{"labels":null,"lag":0,"percentScore":1}'      # Go writes 1, not 1.0
+    assert mb.Score(None, 2, 2.5e-7).MarshalJSON() == '{"labels":null,"lag":2,"percentScore":2.5e-7}'  # and e-7, not e-07
+    assert json.loads(s.MarshalJSON())["percentScore"] == 0.75
+    assert s.to_json()["labels"] == {"graph": "g1", "host": "h1"}
+    import pytest
+    with pytest.raises(ValueError):
+        mb.Score(None, 0, float("nan")).MarshalJSON()      # json: unsupported value: NaN
