@@ -158,3 +158,19 @@ def test_score_json_is_what_encoding_json_writes():
     import pytest
     with pytest.raises(ValueError):
         mb.Score(None, 0, float("nan")).MarshalJSON()      # json: unsupported value: NaN
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    # bench.py --impl reference needs no GPU (the C oracle on the host cores): the JSON line the driver parses
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--series", "3000",
+                        "--cpu-sample", "3000", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "series-samples/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
