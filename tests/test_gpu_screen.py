@@ -325,3 +325,49 @@ def test_one_pass_multi_query_run_equals_exact_runs(ctx, N):
     assert np.max(np.abs(sc - wsc), initial=0) <= 1e-9
     np.testing.assert_array_equal(lg, wlg)
     np.testing.assert_array_equal(ix, wix)
+
+
+def test_multi_query_randomised_against_separate_runs(ctx):
+    # random shapes around the one-pass path's edges: query counts 2 .. 35 (chunks of 16 with remainders of 0, 1, 2),
+    # store sizes that do not divide by the warps of a block, top_n from 1 to a quarter of the store, thresholds from
+    # 0 to beyond every score, windows from 0 to all lags.  Reference: the same queries as separate screened batches
+    # (themselves pinned to the all-exact run by the tests above).
+    rng = np.random.default_rng(2026)
+    for case in range(8):
+        N = int(rng.choice([1026, 1200, 1440, 1800, 2046, 2048]))
+        S = int(rng.integers(16384, 23000))
+        Q = int(rng.choice([2, 15, 16, 17, 18, 32, 33, 35]))
+        Y = _adversarial(rng, S, N)
+        refs = np.zeros((Q, N))
+        for q in range(Q):
+            kind = q % 4
+            if kind == 0:
+                m, w = int(rng.integers(10, N - 30)), int(rng.integers(2, 25))
+                refs[q, m:m + w] = rng.uniform(0.5, 5)
+            elif kind == 1:
+                refs[q] = np.sin(2 * np.pi * np.arange(N) / rng.uniform(5, 200))
+            elif kind == 2:
+                refs[q] = Y[int(rng.integers(0, S))] if rng.random() < 0.5 else rng.standard_normal(N)
+            else:
+                refs[q] = 0.01 * np.arange(N) * rng.uniform(-1, 1)
+            refs[q] += 0.05 * (rng.random(N) - 0.5)
+        if Q > 4:
+            refs[3] = 1.25                                     # constant: this query alone fails
+        max_lag = int(rng.choice([0, 7, 60, N // 2, N]))
+        top_n = int(rng.choice([1, 10, 100, S // 4]))
+        thr = float(rng.choice([0.0, 0.2, 0.5, 0.9, 1.5]))
+        store = mb.DeviceStore(ctx, N, 0, S)
+        store.append(Y)
+        got = mb.multi_run(store, refs, [], max_lag, top_n, thr, mode=mb.MODE_SCREEN)
+        for q in range(Q):
+            try:
+                b = mb.DeviceBatch(ctx, store, refs[q])
+            except mb.MuseError as e:
+                assert e.code == mb.MUSE_ERR_STDDEV_ZERO and got[q] is None
+                continue
+            want = b.run([], max_lag, top_n, thr, mode=mb.MODE_SCREEN)
+            b.close()
+            assert got[q] is not None
+            for g, w_ in zip(got[q], want):
+                np.testing.assert_array_equal(g, w_, err_msg="case %d query %d N %d S %d Q %d" % (case, q, N, S, Q))
+        store.close()
