@@ -104,6 +104,8 @@ struct muse_ctx {
     std::mutex mu;
     std::vector<RunScratch> pool;   // scratch sets of destroyed batches, reused by the next muse_batch_create
     void *d_multi_q;                // query table of score_screen_multi_kernel (ScreenMultiCfg::QC entries)
+    double *d_multi_refs;           // [QC][d_multi_ld] reference rows of a multi-query launch, pad columns kept zero
+    int64_t d_multi_ld, d_multi_n;
 };
 
 struct muse_group {
@@ -137,6 +139,12 @@ struct muse_batch : RunScratch {
 };
 
 static inline cudaStream_t bstream(const muse_batch *b) { return b->use_aux ? b->aux : b->ctx->stream; }
+// timing events of a run: not recorded for the batches of a multi-query launch (nobody reads their timings, and five
+// calls per query are a fifth of what the host issues for one)
+#define TIMING_EVENT(b, i, st)                             \
+    do {                                                   \
+        if (!(b)->use_aux) CU(cudaEventRecord((b)->ev[i], st)); \
+    } while (0)
 
 struct DeviceGuard {
     int prev;
@@ -189,6 +197,7 @@ extern "C" void muse_ctx_destroy(muse_ctx *c) {
     cudaSetDevice(c->device);
     for (RunScratch &r : c->pool) scratch_free(r);
     cudaFree(c->d_multi_q);
+    cudaFree(c->d_multi_refs);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -627,7 +636,10 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
 // NewBatch in two halves, so that the references of a multi-query launch share ONE round trip: queue = everything
 // up to the copies of the std-zero flag and the middle-bin values into the batch's pinned mailbox; finish (after the
 // stream has been synchronised) = the error of muse_batch.go:38-41 (the batch is destroyed) or the by-value parameters.
-static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out) {
+// d_ref_row != NULL: the reference row is already on the device, zero-padded to the slab's row pitch (muse_multi_run
+// uploads the references of a launch with one copy).
+static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out,
+                              const double *d_ref_row = nullptr) {
     if (!ctx || !g || !ref || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_create: NULL argument");
     if (g->ctx != ctx) return fail(MUSE_ERR_INVALID_ARG, "group belongs to another context");
     if (ref_len != g->N)   // muse_batch.go:24-28
@@ -678,13 +690,14 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
         b->h_pin_bytes = (size_t)4 << 20;
         CU(cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault));
     }
-    CU(cudaMemsetAsync(b->d_sel, 0, sizeof(SelectState), st));
-    CU(cudaMemsetAsync(b->d_ref, 0, sizeof(double) * (size_t)g->ld, st));
-    CU(cudaMemcpyAsync(b->d_ref, ref, sizeof(double) * (size_t)ref_len, cudaMemcpyHostToDevice, st));
+    if (!d_ref_row) {      // (the select state is cleared where it is used)
+        CU(cudaMemsetAsync(b->d_ref, 0, sizeof(double) * (size_t)g->ld, st));
+        CU(cudaMemcpyAsync(b->d_ref, ref, sizeof(double) * (size_t)ref_len, cudaMemcpyHostToDevice, st));
+    }
     // X on the device through the same forward path the series take
     ExactParams p;
     memset(&p, 0, sizeof(p));
-    p.slab = b->d_ref;
+    p.slab = d_ref_row ? d_ref_row : b->d_ref;
     p.ld = g->ld;
     p.count = 1;
     p.N = (int)ref_len;
@@ -1236,7 +1249,7 @@ static int score_fused(muse_batch *b, const RunArgs &a) {
         CU(launch_screen(b, sp, st));
         b->timing.n_launches += 2;
     }
-    CU(cudaEventRecord(b->ev[1], st));
+    TIMING_EVENT(b, 1, st);
     if (!a.list_only) CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "cannot be in the result"
     const unsigned blocks = (unsigned)((S + 255) / 256);
     survivors_cut_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, b->d_cut, b->d_list, b->d_counters + 2);
@@ -1307,7 +1320,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     b->fused_run = 0;
     b->timing_pending = 0;
     cudaStream_t st = bstream(b);
-    CU(cudaEventRecord(b->ev[0], st));
+    TIMING_EVENT(b, 0, st);
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
     // screening needs: a kernel for this FFT size, an ungrouped unsigned run, a sign filter that
     // unsigned scores can pass, and a store big enough to be worth two extra round trips
@@ -1329,7 +1342,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
         b->fused_run = 1;
         rc = score_fused(b, a);
         if (rc) return rc;
-        CU(cudaEventRecord(b->ev[2], st));
+        TIMING_EVENT(b, 2, st);
         return MUSE_OK;
     }
     b->timing.mode = MUSE_MODE_EXACT;
@@ -1368,7 +1381,7 @@ static int device_topn_queue(muse_batch *b, const RunArgs &a) {
     if (rc) return rc;
     cudaStream_t st = bstream(b);
     CU(cudaMemcpyAsync(b->h_pin + 64, d_rec, sizeof(muse_partial) * (size_t)a.top_n, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(b->ev[3], st));
+    TIMING_EVENT(b, 3, st);
     return MUSE_OK;
 }
 
@@ -1383,6 +1396,7 @@ static int device_topn_finish(muse_batch *b, const RunArgs &a, double *scores, i
             series_idx[k] = h_rec[k].series_idx;
         }
         *n_out = k;
+        if (b->use_aux) return MUSE_OK;            // a query of a multi-query launch: no timing events were recorded
         muse_timing t;
         return muse_batch_last_timing(b, &t);      // settles timing_pending (events are complete)
     }
@@ -1499,8 +1513,8 @@ static int queue_topn_records(muse_batch *b, const RunArgs &a_in, muse_partial *
     CU(cudaGetLastError());
     // statistics and the end-of-run event are picked up by muse_batch_last_timing
     CU(cudaMemcpyAsync(b->h_pin, b->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(b->ev[3], st));
-    b->timing_pending = 1;
+    TIMING_EVENT(b, 3, st);
+    b->timing_pending = b->use_aux ? 0 : 1;
     return MUSE_OK;
 }
 
@@ -1719,8 +1733,25 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
         int live = 0, rc = MUSE_OK;
         muse_batch *made[QC];
         int n_made = 0;
-        for (int i = 0; i < nq && rc == MUSE_OK; i++) {      // the references of the launch: queued back to back, ONE round trip
-            rc = batch_create_queue(ctx, g, refs + (size_t)(q0 + i) * (size_t)ref_len, ref_len, &made[n_made]);
+        // the references of the launch: ONE upload (rows at the slab's pitch, pad columns zero), then queued back to
+        // back, ONE round trip
+        if (ref_len == g->N && (ctx->d_multi_ld != g->ld || ctx->d_multi_n != g->N)) {
+            cudaFree(ctx->d_multi_refs);
+            ctx->d_multi_refs = nullptr;
+            ctx->d_multi_ld = ctx->d_multi_n = 0;
+            CU(cudaMalloc(&ctx->d_multi_refs, sizeof(double) * (size_t)QC * (size_t)g->ld));
+            CU(cudaMemsetAsync(ctx->d_multi_refs, 0, sizeof(double) * (size_t)QC * (size_t)g->ld, ctx->stream));
+            ctx->d_multi_ld = g->ld;
+            ctx->d_multi_n = g->N;
+        }
+        const bool rows_on_device = ref_len == g->N;
+        if (rows_on_device)
+            CU(cudaMemcpy2DAsync(ctx->d_multi_refs, sizeof(double) * (size_t)g->ld, refs + (size_t)q0 * (size_t)ref_len,
+                                 sizeof(double) * (size_t)ref_len, sizeof(double) * (size_t)ref_len, (size_t)nq,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        for (int i = 0; i < nq && rc == MUSE_OK; i++) {
+            rc = batch_create_queue(ctx, g, refs + (size_t)(q0 + i) * (size_t)ref_len, ref_len, &made[n_made],
+                                    rows_on_device ? ctx->d_multi_refs + (size_t)i * (size_t)g->ld : nullptr);
             if (rc == MUSE_OK) n_made++;
         }
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == MUSE_OK) rc = fail(MUSE_ERR_CUDA, "cudaStreamSynchronize failed");
