@@ -69,7 +69,7 @@ func (g *Group) Length() int { return g.n }
 // Add registers time series; errors mirror go-muse group.go:31-56.
 func (g *Group) Add(series ...*Series) error {
 	for _, s := range series {
-		if len(s.labels.Keys()) == 0 {
+		if len(s.lab.Keys()) == 0 {
 			return fmt.Errorf("Invalid Series with no labels, %v", s)
 		}
 		uid := s.UID()
@@ -96,7 +96,7 @@ func (g *Group) FilterByLabelValues(labels *Labels) []*Series {
 	want := labels.ID(append([]string(nil), keys...))
 	var out []*Series
 	for _, s := range g.series {
-		if s.labels.ID(append([]string(nil), keys...)) == want {
+		if s.lab.ID(append([]string(nil), keys...)) == want {
 			out = append(out, s)
 		}
 	}
@@ -112,7 +112,7 @@ func (g *Group) syncDevice() error {
 	}
 	keySet := map[string]struct{}{}
 	for _, s := range g.series {
-		for _, k := range s.labels.Keys() {
+		for _, k := range s.lab.Keys() {
 			keySet[k] = struct{}{}
 		}
 	}
@@ -148,12 +148,12 @@ func (g *Group) syncDevice() error {
 	rows := make([]float64, 0, len(add)*g.n)
 	ids := make([]int32, len(add)*nk)
 	for i, s := range add {
-		rows = append(rows, s.y...)
+		rows = append(rows, s.vals...)
 		for c := 0; c < nk; c++ {
 			ids[i*nk+c] = -1
 		}
 		for c, k := range g.cols {
-			if v, ok := s.labels.Get(k); ok {
+			if v, ok := s.lab.Get(k); ok {
 				d := g.dict[k]
 				id, seen := d[v]
 				if !seen {
