@@ -562,9 +562,10 @@ static int screen_log2p(int log2m) { return log2m >= 10 ? 5 : (log2m == 9 ? 4 : 
 // mirror pair (k, M-k), k < M/2, with the split twiddle exp(-2*pi*i*k/n); the two reference coefficients of the
 // second stage; and A[M/2], Xt[M/2] for the host (kernel parameters).
 __global__ void screen_tables_kernel(const cd *__restrict__ Xt, int M, const float2 *__restrict__ swtw, float4 *__restrict__ sw,
-                                     float4 *__restrict__ sx, float *__restrict__ mid) {
+                                     float4 *__restrict__ sx, float *__restrict__ mid, const int32_t *__restrict__ std_zero) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > M / 2) return;
+    if (k == 0) mid[0] = __int_as_float(*std_zero);      // the reference's std-zero flag rides along: one copy to the host
     const cd a = Xt[k], c = Xt[M - k];
     if (k == M / 2) {
         mid[1] = __double2float_ru(hypot(a.x, a.y) * 2.0);
@@ -709,23 +710,24 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
     b->screen_ok = 0;
     const bool screen = b->tab_screen && !(b->N & 1);
     if (screen) {
-        screen_tables_kernel<<<(unsigned)((M / 2 + 1 + 255) / 256), 256, 0, st>>>(b->Xt, (int)M, b->swtw, b->sw_f, b->sx_f, b->d_mid);
+        screen_tables_kernel<<<(unsigned)((M / 2 + 1 + 255) / 256), 256, 0, st>>>(b->Xt, (int)M, b->swtw, b->sw_f, b->sx_f, b->d_mid, b->d_flag);
         CU(cudaGetLastError());
     }
     // one round trip: the std-zero flag of the reference and the two middle-bin values the kernels take by value
     int32_t *h_flag = reinterpret_cast<int32_t *>(b->h_pin);
     float *h_mid = reinterpret_cast<float *>(b->h_pin + 16);
-    CU(cudaMemcpyAsync(h_flag, b->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (screen) CU(cudaMemcpyAsync(h_mid, b->d_mid, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
+    if (screen) CU(cudaMemcpyAsync(h_mid, b->d_mid, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));      // [0] carries the flag
+    else CU(cudaMemcpyAsync(h_flag, b->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     b->screen_ok = screen ? -1 : 0;      // -1: pending until batch_create_finish
     *out = b;
     return MUSE_OK;
 }
 
 static int batch_create_finish(muse_batch *b) {
-    const int32_t *h_flag = reinterpret_cast<const int32_t *>(b->h_pin);
     const float *h_mid = reinterpret_cast<const float *>(b->h_pin + 16);
-    if (*h_flag) {   // muse_batch.go:38-41
+    int32_t flag;
+    memcpy(&flag, b->screen_ok == -1 ? static_cast<const void *>(h_mid) : static_cast<const void *>(b->h_pin), sizeof(flag));
+    if (flag) {   // muse_batch.go:38-41
         muse_batch_destroy(b);
         return fail(MUSE_ERR_STDDEV_ZERO, "Invalid input query, Standard deviation of zero");
     }
@@ -1190,6 +1192,7 @@ static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t m
 __global__ void survivors_cut_kernel(const float *__restrict__ U, int64_t S, const unsigned *__restrict__ cut_bits,
                                      int32_t *__restrict__ out, unsigned long long *n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) n[1] = *reinterpret_cast<const unsigned long long *>(cut_bits + 2);      // the refined count rides along (counters[3])
     const float lo = __uint_as_float(*cut_bits);
     const bool take = i < S && U[i] >= lo;
     const unsigned mask = __ballot_sync(0xffffffffu, take);
@@ -1256,7 +1259,6 @@ static int score_fused(muse_batch *b, const RunArgs &a) {
     b->timing.n_launches++;
     rc = score_exact_all(b, 0, b->d_list, std::min<int64_t>(S, MUSE_EXACT_UB), b->d_counters + 2);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(b->d_counters + 3, b->d_cut + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     return MUSE_OK;
 }
 
@@ -1488,7 +1490,7 @@ static int queue_topn_records(muse_batch *b, const RunArgs &a_in, muse_partial *
     if (rc) return rc;
     const int64_t S = b->g->size;
     cudaStream_t st = bstream(b);
-    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 2, st));
+    // counters[0..1] (candidates, selected) are still zero: run_scores cleared all four and ungrouped scoring writes only [2..3]
     if (S > 0) {
         FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
         Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
@@ -1979,7 +1981,7 @@ extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t 
     if (rc) return rc;
     const int64_t S = b->g->size;
     cudaStream_t st = bstream(b);
-    CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 2, st));
+    // counters[0..1] (candidates, selected) are still zero: run_scores cleared all four and ungrouped scoring writes only [2..3]
     if (S > 0) {
         FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
         Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
