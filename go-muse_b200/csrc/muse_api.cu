@@ -1683,8 +1683,7 @@ static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag,
     cudaStream_t st = ctx->stream;
     std::vector<MultiQuery> hq((size_t)nq);
     ScreenParams sp0;
-    float thr_lo = threshold > 0 ? (float)threshold * 0.999999f : 0.f;
-    if (getenv("MUSE_MULTI_BOUNDS_ONLY")) thr_lo = INFINITY;      // timing probe only (tools/c5_probe.py): no second stage, empty results
+    const float thr_lo = threshold > 0 ? (float)threshold * 0.999999f : 0.f;
     for (int q = 0; q < nq; q++) {
         muse_batch *b = bs[q];
         int rc = ensure_scratch(b);
