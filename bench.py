@@ -36,9 +36,10 @@ SEED = 20261018
 
 def workload(args):
     if args.workload == "c4":
-        name = ("C4 (weak-scaled share): %d series x %d fp64 samples per GPU, maxLag=%d, topN=%d, threshold=%g, grouped by "
-                "[graph, host] (100 series per group; BASELINE.json configs[3])"
-                % (args.series, args.length, args.max_lag, args.top_n, args.threshold))
+        name = ("C4 (%s): %d series x %d fp64 samples per GPU, maxLag=%d, topN=%d, threshold=%g, %s (BASELINE.json configs[3])"
+                % ("full size" if args.series * max(1, args.gpus) >= 10_000_000 else "weak-scaled share", args.series, args.length,
+                   args.max_lag, args.top_n, args.threshold,
+                   "ungrouped" if args.ungrouped else "grouped by [graph, host] (100 series per group)"))
     else:
         name = ("C3: %d series x %d fp64 samples per GPU, maxLag=%d, topN=%d, threshold=%g, ungrouped "
                 "(BASELINE.json configs[2])" % (args.series, args.length, args.max_lag, args.top_n, args.threshold))
@@ -46,7 +47,7 @@ def workload(args):
         "workload": name,
         "series_per_gpu": args.series, "series_len": args.length, "fft_len": int(2 ** int(np.ceil(np.log2(args.length)))),
         "max_lag": args.max_lag, "top_n": args.top_n, "threshold": args.threshold,
-        "group_by": ["graph", "host"] if args.workload == "c4" else None,
+        "group_by": ["graph", "host"] if args.workload == "c4" and not args.ungrouped else None,
         "mode": args.mode,
         "l2": "inputs (%.2f GB per GPU) are far larger than the 126 MB L2; no flush needed" % (args.series * args.length * 8 / 1e9),
     }
@@ -121,24 +122,17 @@ def cpu_arm(args, Y, ref, steps, warmup, nthreads):
     return S * N / dt, dt * 1e3
 
 
-def host_sample(args, n_rows):
-    import muse_b200 as mb
-    Y = np.empty((n_rows, args.length))
-    for i in range(n_rows):
-        Y[i] = mb.synth_row(SEED, i, args.length)
-    return Y
-
-
 def run_reference(args):
+    """The reference arm maps nothing but oracle/: rows and reference come from oracle/synth_gen.c (the same
+    counter-based generator as the device's, bit for bit), the timed loop is oracle/muse_oracle.c."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import muse_b200 as mb
     from oracle import c_oracle as co
     cores = co.max_threads()
     n_rows = min(args.series, args.cpu_sample)
-    Y = host_sample(args, n_rows)
-    ref = mb.synth_reference(SEED, args.length)
+    Y = co.synth_rows(SEED, 0, n_rows, args.length)
+    ref = co.synth_reference(SEED, args.length)
     value, ms = cpu_arm(args, Y, ref, args.steps, args.warmup, cores)
     sample = "first %d of the %d series of the workload per step (bounded so the run ends in minutes)" % (n_rows, args.series)
     line = {
@@ -253,6 +247,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: NCCL all-gather instead of the peer-memory push")
+    ap.add_argument("--ungrouped", action="store_true", help="--workload c4: Run(nil) instead of Run([graph, host])")
+    ap.add_argument("--data", default="mix", choices=["mix", "rect"],
+                    help="mix: rect / line / noise rows (the benchmark); rect: every row a rect of the reference's width "
+                         "(adversarial for the screening: nearly every score lies within the slack of the cut-off)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --series per GPU (the metric's configuration); strong: --series in total, sharded over the GPUs")
     args = ap.parse_args()
     dflt = {"c3": (1_000_000, 1440, 60), "c4": (1_250_000, 10080, 240), "c5": (1_000_000, 1440, 60)}[args.workload]
     args.series = args.series if args.series is not None else dflt[0]
@@ -293,7 +293,7 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)          # library kernels and NCCL deps on one stream: one event bracket
     S, N = args.series, args.length
-    grouped = args.workload == "c4"
+    grouped = args.workload == "c4" and not args.ungrouped
     store = mb.DeviceStore(ctx, N, 3 if grouped else 2, S)
     store.append_synthetic(S, SEED, rank * S)
     store.set_global_offset(rank * S)
@@ -428,8 +428,8 @@ def main():
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "kernel": "score_exact_kernel" if used_mode == "exact" else
-                              ("score_screen_warp_kernel" if 1024 < N <= 2048 else "score_screen_block_kernel" if N > 2048
-                               else "score_screen_kernel"),
+                              ("score_screen_warp_kernel" if 1024 < N <= 2048 else "score_screen_big_kernel" if N > 2048
+                               else "score_screen_block_kernel"),
                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                     "frac_of_nominal_8TBps": achieved / 8000.0}
         cpu = None

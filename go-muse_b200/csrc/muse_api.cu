@@ -10,14 +10,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include "../../include/muse_b200.h"
-#include "muse_exact.cuh"
-#include "muse_screen_block.cuh"
-#include "muse_screen_multi.cuh"
+#include "muse_launch.h"
 #include "muse_select.cuh"
 #include "muse_synth.cuh"
 #include "muse_xcorr.cuh"
@@ -57,6 +57,7 @@ extern "C" const char *muse_version(void) { return "muse_b200 0.1 (sm_100a)"; }
 // per-context pool across muse_batch_create / muse_batch_destroy, because cudaMalloc / cudaFree /
 // cudaHostAlloc of these cost milliseconds to seconds (measured: a NewBatch + Run + destroy cycle per
 // request spent 3 s in cudaFree/cudaFreeHost once in four) while the run itself takes 2.7 ms.
+#define MUSE_MAX_LABEL_KEYS 64   // label-key columns of a store (the facade adds one all-absent column)
 #define MUSE_SCRATCH_POOL 20   // scratch sets kept per context: a multi-query launch has ScreenMultiCfg::QC batches alive at once
 struct RunScratch {
     int64_t scratch_cap;
@@ -69,6 +70,7 @@ struct RunScratch {
     float *d_U;
     int32_t *d_list;
     float *d_L;                       // lower bounds (grouped screened runs, diagnostic entry point)
+    signed char *d_W;                 // grouped screened runs: lag-window verdict of every refined series (ScreenParams::out_W)
     int64_t d_L_cap;
     unsigned char *h_pin;             // pinned mailbox for the small device->host results
     size_t h_pin_bytes;
@@ -88,6 +90,7 @@ struct RunScratch {
     double *d_ref;                    // padded copy of the reference row
     cd *Xt, *twM, *twn;
     cf *twp_f;                        // fp32 screening pass: per-pass twiddles
+    cf *twi_f;                        // n = 4096 .. 16384: twiddles of the transposed inverse (muse_screen_big.cuh)
     float2 *swtw;                     // split twiddles exp(-2*pi*i*k/n), k < M/2, fp32
     float4 *sw_f;                     // fused kernels: (twn, A[k], A[M-k]) per k < M/2
     float4 *sx_f;                     // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
@@ -103,6 +106,8 @@ struct muse_ctx {
     cudaStream_t own_stream;   // created with the context
     std::mutex mu;
     std::vector<RunScratch> pool;   // scratch sets of destroyed batches, reused by the next muse_batch_create
+    unsigned char *h_stage[3];      // pinned staging ring for rows that arrive in pageable host memory (muse_group_append)
+    cudaEvent_t stage_ev[3];
     void *d_multi_q;                // query table of score_screen_multi_kernel (ScreenMultiCfg::QC entries)
     double *d_multi_refs;           // [QC][d_multi_ld] reference rows of a multi-query launch, pad columns kept zero
     int64_t d_multi_ld, d_multi_n;
@@ -116,7 +121,7 @@ struct muse_group {
     double *slab;       // [cap][ld]
     int nkeys;
     int32_t *labels;    // [nkeys][cap]
-    int32_t max_id[16];
+    int32_t max_id[MUSE_MAX_LABEL_KEYS];
     int64_t global_offset;
     RowStat *row_stat;          // [cap] screening: fp64 mean and fp32 1/std of each row (filled lazily up to stats_upto)
     int64_t stats_cap, stats_upto;
@@ -181,11 +186,11 @@ static void scratch_free(RunScratch &r) {
     cudaFree(r.d_score); cudaFree(r.d_lag); cudaFree(r.d_slot);
     cudaFree(r.d_ckey); cudaFree(r.d_skey); cudaFree(r.d_cidx); cudaFree(r.d_sidx);
     cudaFree(r.d_clag); cudaFree(r.d_slag);
-    cudaFree(r.d_U); cudaFree(r.d_list); cudaFree(r.d_L);
+    cudaFree(r.d_U); cudaFree(r.d_list); cudaFree(r.d_L); cudaFree(r.d_W);
     cudaFree(r.d_gmax); cudaFree(r.d_hkeys); cudaFree(r.d_gidx);
     cudaFree(r.d_flag); cudaFree(r.d_counters); cudaFree(r.d_sel); cudaFree(r.d_cut);
     cudaFree(r.d_ref); cudaFree(r.Xt); cudaFree(r.twM); cudaFree(r.twn);
-    cudaFree(r.twp_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.d_mid);
+    cudaFree(r.twp_f); cudaFree(r.twi_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.d_mid);
     for (int i = 0; i < 4; i++) if (r.ev[i]) cudaEventDestroy(r.ev[i]);
     if (r.aux) cudaStreamDestroy(r.aux);
     if (r.h_pin) cudaFreeHost(r.h_pin);
@@ -196,6 +201,10 @@ extern "C" void muse_ctx_destroy(muse_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (RunScratch &r : c->pool) scratch_free(r);
+    for (int i = 0; i < 3; i++) {
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
     cudaFree(c->d_multi_q);
     cudaFree(c->d_multi_refs);
     cudaStreamDestroy(c->own_stream);
@@ -236,21 +245,48 @@ static int group_reserve(muse_group *g, int64_t want) {
     ncap = std::max<int64_t>(ncap, 16);
     double *nslab = nullptr;
     int32_t *nlab = nullptr;
-    CU(cudaMalloc(&nslab, sizeof(double) * (size_t)ncap * (size_t)g->ld));
-    if (g->nkeys > 0) CU(cudaMalloc(&nlab, sizeof(int32_t) * (size_t)ncap * (size_t)g->nkeys));
-    if (g->size > 0) {
-        CU(cudaMemcpyAsync(nslab, g->slab, sizeof(double) * (size_t)g->size * (size_t)g->ld, cudaMemcpyDeviceToDevice,
-                           g->ctx->stream));
-        for (int k = 0; k < g->nkeys; k++)
-            CU(cudaMemcpyAsync(nlab + (size_t)k * ncap, g->labels + (size_t)k * g->cap, sizeof(int32_t) * (size_t)g->size,
-                               cudaMemcpyDeviceToDevice, g->ctx->stream));
-        CU(cudaStreamSynchronize(g->ctx->stream));
+    RowStat *nstat = nullptr;
+    auto bail = [&](int code) {
+        cudaFree(nslab);
+        cudaFree(nlab);
+        cudaFree(nstat);
+        return code;
+    };
+    cudaError_t e = cudaMalloc(&nslab, sizeof(double) * (size_t)ncap * (size_t)g->ld);
+    if (e == cudaSuccess && g->nkeys > 0) e = cudaMalloc(&nlab, sizeof(int32_t) * (size_t)ncap * (size_t)g->nkeys);
+    if (e == cudaSuccess) e = cudaMalloc(&nstat, sizeof(RowStat) * (size_t)ncap);
+    if (e == cudaSuccess && g->size > 0) {
+        e = cudaMemcpyAsync(nslab, g->slab, sizeof(double) * (size_t)g->size * (size_t)g->ld, cudaMemcpyDeviceToDevice, g->ctx->stream);
+        for (int k = 0; k < g->nkeys && e == cudaSuccess; k++)
+            e = cudaMemcpyAsync(nlab + (size_t)k * ncap, g->labels + (size_t)k * g->cap, sizeof(int32_t) * (size_t)g->size,
+                                cudaMemcpyDeviceToDevice, g->ctx->stream);
+        if (e == cudaSuccess && g->stats_upto > 0)
+            e = cudaMemcpyAsync(nstat, g->row_stat, sizeof(RowStat) * (size_t)g->stats_upto, cudaMemcpyDeviceToDevice, g->ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g->ctx->stream);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return bail(fail(e == cudaErrorMemoryAllocation ? MUSE_ERR_OUT_OF_MEMORY : MUSE_ERR_CUDA, "growing the store to %lld series: %s",
+                         (long long)ncap, cudaGetErrorString(e)));
     }
     if (g->slab) cudaFree(g->slab);
     if (g->labels) cudaFree(g->labels);
+    if (g->row_stat) cudaFree(g->row_stat);
     g->slab = nslab;
     g->labels = nlab;
+    g->row_stat = nstat;
     g->cap = ncap;
+    g->stats_cap = ncap;
+    return MUSE_OK;
+}
+
+// RowStat of rows [first, first + count): the batched mean / sample-std kernel of the z-normalisation (xcorr.go:84-95),
+// queued right behind the copy that brought the rows in, so that no Run ever pays a separate pass over the slab.
+static int queue_row_stats(muse_group *g, int64_t first, int64_t count) {
+    if (count <= 0) return MUSE_OK;
+    const unsigned grid = (unsigned)std::min<int64_t>((count + 7) / 8, (int64_t)g->ctx->sm_count * 16);
+    row_stats_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, (int)g->N, first, count, g->row_stat);
+    CU(cudaGetLastError());
     return MUSE_OK;
 }
 
@@ -260,7 +296,8 @@ extern "C" int muse_group_create(muse_ctx *ctx, int64_t series_len, int32_t n_la
     if (series_len < 2)
         return fail(MUSE_ERR_INVALID_ARG, "series length %lld: the sample std needs at least 2 samples (xcorr.go:88)",
                     (long long)series_len);
-    if (n_label_keys < 0 || n_label_keys > 16) return fail(MUSE_ERR_INVALID_ARG, "n_label_keys %d not in [0,16]", n_label_keys);
+    if (n_label_keys < 0 || n_label_keys > MUSE_MAX_LABEL_KEYS)
+        return fail(MUSE_ERR_INVALID_ARG, "n_label_keys %d not in [0,%d]", n_label_keys, MUSE_MAX_LABEL_KEYS);
     CU(cudaSetDevice(ctx->device));
     muse_group *g = new muse_group();
     memset(g, 0, sizeof(*g));
@@ -268,7 +305,7 @@ extern "C" int muse_group_create(muse_ctx *ctx, int64_t series_len, int32_t n_la
     g->N = series_len;
     g->ld = (series_len + 15) / 16 * 16;
     g->nkeys = n_label_keys;
-    for (int k = 0; k < 16; k++) g->max_id[k] = -1;
+    for (int k = 0; k < MUSE_MAX_LABEL_KEYS; k++) g->max_id[k] = -1;
     int rc = group_reserve(g, std::max<int64_t>(capacity_hint, 16));
     if (rc != MUSE_OK) {
         delete g;
@@ -287,6 +324,74 @@ extern "C" void muse_group_destroy(muse_group *g) {
     delete g;
 }
 
+// Pageable host rows -> slab through a ring of three pinned buffers: MUSE_STAGE_THREADS host threads copy chunk c into
+// buffer c % 3 while chunk c - 1 is on the wire (at most two DMA copies outstanding, so a buffer is free again when its
+// turn comes).  The chunk size is a whole number of rows.
+#define MUSE_STAGE_BYTES ((size_t)64 << 20)
+static int append_staged(muse_group *g, const double *rows, int64_t n_series) {
+    muse_ctx *c = g->ctx;
+    cudaStream_t st = c->stream;
+    for (int i = 0; i < 3; i++) {
+        if (!c->h_stage[i]) CU(cudaHostAlloc((void **)&c->h_stage[i], MUSE_STAGE_BYTES, cudaHostAllocDefault));
+        if (!c->stage_ev[i]) CU(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    }
+    const size_t row_bytes = sizeof(double) * (size_t)g->N;
+    if (row_bytes > MUSE_STAGE_BYTES) return fail(MUSE_ERR_UNSUPPORTED, "a row of %zu bytes exceeds the staging buffer", row_bytes);
+    const int64_t rows_per_chunk = (int64_t)(MUSE_STAGE_BYTES / row_bytes);
+    const int64_t n_chunks = (n_series + rows_per_chunk - 1) / rows_per_chunk;
+    unsigned hw = std::thread::hardware_concurrency();
+    const char *env = getenv("MUSE_STAGE_THREADS");
+    int n_threads = env ? atoi(env) : (int)std::min<unsigned>(hw ? hw : 4u, 12u);
+    if (n_threads < 1) n_threads = 1;
+    if ((size_t)n_series * row_bytes < ((size_t)8 << 20)) n_threads = 1;      // small appends: not worth the threads
+    std::vector<std::atomic<int>> done((size_t)n_chunks);
+    for (auto &d : done) d.store(0, std::memory_order_relaxed);
+    std::atomic<int64_t> writable(std::min<int64_t>(n_chunks, 2));      // chunks whose buffer may be filled
+    std::atomic<bool> abort_flag(false);
+    auto worker = [&](int w) {
+        for (int64_t ch = 0; ch < n_chunks; ch++) {
+            if (abort_flag.load(std::memory_order_relaxed)) return;
+            while (writable.load(std::memory_order_acquire) <= ch) {
+                if (abort_flag.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            const int64_t r0 = ch * rows_per_chunk, nr = std::min<int64_t>(rows_per_chunk, n_series - r0);
+            const size_t bytes = (size_t)nr * row_bytes;
+            const size_t lo = bytes * (size_t)w / (size_t)n_threads / 64 * 64, hi = (w + 1 == n_threads) ? bytes : bytes * (size_t)(w + 1) / (size_t)n_threads / 64 * 64;
+            if (hi > lo) memcpy(c->h_stage[ch % 3] + lo, reinterpret_cast<const unsigned char *>(rows) + (size_t)r0 * row_bytes + lo, hi - lo);
+            done[(size_t)ch].fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < n_threads; w++) pool.emplace_back(worker, w);
+    cudaError_t e = cudaSuccess;
+    // the calling thread is worker 0 and the one that talks to the device
+    for (int64_t ch = 0; ch < n_chunks && e == cudaSuccess; ch++) {
+        const int64_t r0 = ch * rows_per_chunk, nr = std::min<int64_t>(rows_per_chunk, n_series - r0);
+        {
+            const size_t bytes = (size_t)nr * row_bytes;
+            const size_t hi = (n_threads == 1) ? bytes : bytes / (size_t)n_threads / 64 * 64;
+            if (hi > 0) memcpy(c->h_stage[ch % 3], reinterpret_cast<const unsigned char *>(rows) + (size_t)r0 * row_bytes, hi);
+            done[(size_t)ch].fetch_add(1, std::memory_order_release);
+        }
+        while (done[(size_t)ch].load(std::memory_order_acquire) < n_threads) std::this_thread::yield();
+        double *dst = g->slab + (size_t)(g->size + r0) * g->ld;
+        if (g->ld == g->N) e = cudaMemcpyAsync(dst, c->h_stage[ch % 3], (size_t)nr * row_bytes, cudaMemcpyHostToDevice, st);
+        else e = cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)g->ld, c->h_stage[ch % 3], row_bytes, row_bytes, (size_t)nr, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev[ch % 3], st);
+        if (e == cudaSuccess && ch >= 1) e = cudaEventSynchronize(c->stage_ev[(ch - 1) % 3]);      // buffer (ch + 2) % 3 is free again
+        writable.store(ch + 3, std::memory_order_release);
+    }
+    if (e != cudaSuccess) abort_flag.store(true);
+    writable.store(n_chunks + 3, std::memory_order_release);
+    for (auto &t : pool) t.join();
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(MUSE_ERR_CUDA, "staged host->device copy failed: %s", cudaGetErrorString(e));
+    }
+    return MUSE_OK;
+}
+
 extern "C" int muse_group_append(muse_group *g, const double *rows, int64_t n_series, int64_t series_len,
                                  const int32_t *label_ids) {
     if (!g || (!rows && n_series > 0)) return fail(MUSE_ERR_INVALID_ARG, "muse_group_append: NULL argument");
@@ -301,7 +406,17 @@ extern "C" int muse_group_append(muse_group *g, const double *rows, int64_t n_se
     int rc = group_reserve(g, g->size + n_series);
     if (rc != MUSE_OK) return rc;
     cudaStream_t st = g->ctx->stream;
-    if (g->ld == g->N) {   // rows are already at the slab's pitch: one flat copy (a pitched copy of 10^6 rows is not always at DMA rate)
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, rows) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    (void)cudaGetLastError();
+    if (!pinned) {
+        // pageable rows (a Go slice, a numpy array): a direct cudaMemcpyAsync stages them through the driver's single
+        // bounce buffer at a fraction of the link rate -> chunks are copied into a pinned ring by several host threads
+        // while the previous chunk is on the wire
+        rc = append_staged(g, rows, n_series);
+        if (rc != MUSE_OK) return rc;
+    } else if (g->ld == g->N) {   // rows are already at the slab's pitch: one flat copy (a pitched copy of 10^6 rows is not always at DMA rate)
         CU(cudaMemcpyAsync(g->slab + (size_t)g->size * g->ld, rows, sizeof(double) * (size_t)g->N * (size_t)n_series,
                            cudaMemcpyHostToDevice, st));
     } else {
@@ -326,8 +441,11 @@ extern "C" int muse_group_append(muse_group *g, const double *rows, int64_t n_se
             CU(cudaStreamSynchronize(st));   // col is reused
         }
     }
+    rc = queue_row_stats(g, g->size, n_series);
+    if (rc != MUSE_OK) return rc;
     CU(cudaStreamSynchronize(st));
     g->size += n_series;
+    g->stats_upto = g->size;
     return MUSE_OK;
 }
 
@@ -347,11 +465,11 @@ __global__ void transpose_labels_kernel(const int32_t *src, int64_t n, int nkeys
 static int refresh_max_ids(muse_group *g, int64_t off, int64_t n) {
     if (g->nkeys == 0 || n == 0) return MUSE_OK;
     int32_t *d = nullptr;
-    CU(cudaMalloc(&d, sizeof(int32_t) * 16));
-    CU(cudaMemsetAsync(d, 0xff, sizeof(int32_t) * 16, g->ctx->stream));
+    CU(cudaMalloc(&d, sizeof(int32_t) * MUSE_MAX_LABEL_KEYS));
+    CU(cudaMemsetAsync(d, 0xff, sizeof(int32_t) * MUSE_MAX_LABEL_KEYS, g->ctx->stream));
     for (int k = 0; k < g->nkeys; k++)
         max_id_kernel<<<256, 256, 0, g->ctx->stream>>>(g->labels + (size_t)k * g->cap + off, n, d + k);
-    int32_t h[16];
+    int32_t h[MUSE_MAX_LABEL_KEYS];
     CU(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, g->ctx->stream));
     CU(cudaStreamSynchronize(g->ctx->stream));
     cudaFree(d);
@@ -382,23 +500,56 @@ extern "C" int muse_group_append_device(muse_group *g, const double *d_rows, int
         rc = refresh_max_ids(g, g->size, n_series);
         if (rc != MUSE_OK) return rc;
     }
+    rc = queue_row_stats(g, g->size, n_series);
+    if (rc != MUSE_OK) return rc;
     CU(cudaStreamSynchronize(st));
     g->size += n_series;
+    g->stats_upto = g->size;
     return MUSE_OK;
 }
 
-// one block per series row; coalesced 8-byte stores
-__global__ void synth_rows_kernel(double *slab, int64_t ld, int64_t N, int64_t row0, int64_t n_series, uint64_t seed,
-                                  int64_t first_index, int32_t *lab0, int32_t *lab1) {
+// one block per series row; coalesced 8-byte stores.  The row's RowStat (row_stats_kernel's sums about the first
+// sample) is accumulated while the samples are generated: a synthetic store never needs a pass of its own for them.
+__global__ void __launch_bounds__(256)
+synth_rows_kernel(double *slab, int64_t ld, int64_t N, int64_t row0, int64_t n_series, uint64_t seed,
+                  int64_t first_index, int32_t *lab0, int32_t *lab1, RowStat *stat) {
+    __shared__ double red[2][8];
     for (int64_t r = blockIdx.x; r < n_series; r += gridDim.x) {
         const int64_t gi = first_index + r;
         const SynthSeries sp = synth_params(seed, gi, N);
         double *row = slab + (size_t)(row0 + r) * ld;
-        for (int64_t t = threadIdx.x; t < ld; t += blockDim.x) row[t] = t < N ? synth_value(seed, gi, sp, t) : 0.0;
+        const double pivot = synth_value(seed, gi, sp, 0);
+        double s1 = 0.0, s2 = 0.0;
+        for (int64_t t = threadIdx.x; t < ld; t += blockDim.x) {
+            const double v = t < N ? synth_value(seed, gi, sp, t) : 0.0;
+            row[t] = v;
+            if (t < N) {
+                const double x = v - pivot;
+                s1 += x;
+                s2 = fma(x, x, s2);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = s1;
+            red[1][threadIdx.x >> 5] = s2;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
+            s1 = s2 = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+                s1 += red[0][w];
+                s2 += red[1][w];
+            }
+            stat[row0 + r] = make_row_stat(pivot, s1, s2, (int)N);
             if (lab0) lab0[row0 + r] = (int32_t)(gi / 1000);
             if (lab1) lab1[row0 + r] = (int32_t)(gi % 1000);
         }
+        __syncthreads();
     }
 }
 
@@ -414,9 +565,10 @@ extern "C" int muse_group_append_synthetic(muse_group *g, int64_t n_series, uint
     if (g->nkeys > 2)
         CU(cudaMemsetAsync(g->labels + (size_t)2 * g->cap, 0, sizeof(int32_t) * (size_t)g->cap * (size_t)(g->nkeys - 2), g->ctx->stream));
     const unsigned grid = (unsigned)std::min<int64_t>(n_series, (int64_t)g->ctx->sm_count * 16);
-    synth_rows_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, g->N, g->size, n_series, seed, first_index, l0, l1);
+    synth_rows_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, g->N, g->size, n_series, seed, first_index, l0, l1, g->row_stat);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(g->ctx->stream));
+    g->stats_upto = g->size + n_series;
     if (g->nkeys >= 1) g->max_id[0] = std::max<int32_t>(g->max_id[0], (int32_t)((first_index + n_series - 1) / 1000));
     if (g->nkeys >= 2) g->max_id[1] = std::max<int32_t>(g->max_id[1], (int32_t)std::min<int64_t>(999, first_index + n_series - 1));
     for (int k = 2; k < g->nkeys; k++) g->max_id[k] = std::max(g->max_id[k], 0);
@@ -480,7 +632,7 @@ extern "C" int muse_group_clear(muse_group *g) {
     CU(cudaStreamSynchronize(g->ctx->stream));
     g->size = 0;
     g->stats_upto = 0;
-    for (int k = 0; k < 16; k++) g->max_id[k] = -1;
+    for (int k = 0; k < MUSE_MAX_LABEL_KEYS; k++) g->max_id[k] = -1;
     return MUSE_OK;
 }
 
@@ -504,45 +656,6 @@ extern "C" int muse_group_read_row(muse_group *g, int64_t local_index, double *o
 }
 
 // ------------------------------------------------------------------------------------
-// exact kernel dispatch
-// ------------------------------------------------------------------------------------
-template <int LOG2M, int LOG2P, int MODE, int MINB>
-static cudaError_t launch_exact_cfg(const ExactParams &p, cudaStream_t st) {
-    using C = ExactCfg<LOG2M, LOG2P>;
-    auto kern = score_exact_kernel<LOG2M, LOG2P, MODE, MINB>;
-    if (C::SMEM > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return e;
-    }
-    const int64_t blocks = (p.count + C::SPB - 1) / C::SPB;
-    kern<<<(unsigned)blocks, C::TB, C::SMEM, st>>>(p);
-    return cudaGetLastError();
-}
-
-// points per thread of the exact kernel for each FFT size (also fixes the twiddle layout)
-static int exact_log2p(int log2m) { return log2m < 4 ? log2m : 4; }
-
-template <int LOG2M, int MODE>
-static cudaError_t launch_exact_t(const ExactParams &p, cudaStream_t st) {
-    constexpr int LOG2P = LOG2M < 4 ? LOG2M : 4;
-    // 512 resident threads per SM = a 128-register cap: measured best on B200 at n = 2048
-    // (16 warps/SM, 12.3 ms per 1M series vs 15.5 ms uncapped at 8 warps/SM; profiles/r01_tune_exact.txt)
-    constexpr int MINB = 512 / ExactCfg<LOG2M, LOG2P>::TB > 0 ? 512 / ExactCfg<LOG2M, LOG2P>::TB : 1;
-    return launch_exact_cfg<LOG2M, LOG2P, MODE, MINB>(p, st);
-}
-
-template <int MODE>
-static cudaError_t launch_exact(int log2m, const ExactParams &p, cudaStream_t st) {
-    switch (log2m) {
-#define MUSE_CASE(L) case L: return launch_exact_t<L, MODE>(p, st);
-        MUSE_CASE(0) MUSE_CASE(1) MUSE_CASE(2) MUSE_CASE(3) MUSE_CASE(4) MUSE_CASE(5) MUSE_CASE(6)
-        MUSE_CASE(7) MUSE_CASE(8) MUSE_CASE(9) MUSE_CASE(10) MUSE_CASE(11) MUSE_CASE(12) MUSE_CASE(13)
-#undef MUSE_CASE
-    }
-    return cudaErrorInvalidValue;
-}
-
-// ------------------------------------------------------------------------------------
 // batch
 // ------------------------------------------------------------------------------------
 static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 <= v < 2^29
@@ -554,6 +667,7 @@ static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 
 // fp32 tables of the screening kernel; leaves screen_ok = 0 when the shape has no screening kernel
 // n = 512 .. 16384: kernels with the fused fp32 second stage (warp kernel at 2048, block kernel elsewhere)
 static int screen_is_fused(int log2m) { return log2m >= 8 && log2m <= 13; }
+static int screen_is_big(int log2m) { return log2m >= 11 && log2m <= 13; }      // muse_screen_big.cuh
 static int screen_log2m_supported(int log2m) { return screen_is_fused(log2m); }
 static int screen_log2p(int log2m) { return log2m >= 10 ? 5 : (log2m == 9 ? 4 : 3); }
 
@@ -593,9 +707,9 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     if (!b->d_mid) CU(cudaMalloc(&b->d_mid, sizeof(float) * 4));
     const bool want_screen = screen_log2m_supported(b->log2m);
     if (b->tab_n == n && (b->tab_screen || !want_screen)) return MUSE_OK;
-    cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
+    cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
     b->Xt = b->twM = b->twn = nullptr;
-    b->twp_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
+    b->twp_f = b->twi_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
     b->tab_n = 0;
     b->tab_screen = 0;
     const long double PI2 = 6.283185307179586476925286766559005768L;
@@ -612,9 +726,17 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     CU(cudaMalloc(&b->twn, sizeof(cd) * (size_t)(M / 2 + 1)));
     CU(cudaMemcpyAsync(b->twM, twM.data(), sizeof(cd) * twM.size(), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b->twn, twn.data(), sizeof(cd) * (size_t)(M / 2 + 1), cudaMemcpyHostToDevice, st));
-    std::vector<cf> twp;
+    std::vector<cf> twp, twi;
     std::vector<float2> swtw;
     if (want_screen) {
+        if (screen_is_big(b->log2m)) {
+            twi.resize((size_t)((1 << (b->log2m - 10)) - 1) * 1024 + 31 * 32);
+            fill_big_inverse_twiddles(b->log2m, twi.data(), [&](long long num, long long den) {
+                return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
+            });
+            CU(cudaMalloc(&b->twi_f, sizeof(cf) * twi.size()));
+            CU(cudaMemcpyAsync(b->twi_f, twi.data(), sizeof(cf) * twi.size(), cudaMemcpyHostToDevice, st));
+        }
         twp.resize((size_t)M + 64);
         fill_pass_twiddles(b->log2m, screen_log2p(b->log2m), twp.data(), [&](long long num, long long den) {
             return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
@@ -706,7 +828,7 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
     p.twn = b->twn;
     p.out_X = b->Xt;
     p.out_flag = b->d_flag;
-    CU(launch_exact<MODE_REF>(b->log2m, p, st));
+    CU(launch_exact(MODE_REF, b->log2m, p, st));
     b->screen_ok = 0;
     const bool screen = b->tab_screen && !(b->N & 1);
     if (screen) {
@@ -830,7 +952,7 @@ static int score_exact_all(muse_batch *b, int signed_scores, const int32_t *idx,
     p.out_score = b->d_score;
     p.out_lag = b->d_lag;
     if (count > 0) {
-        CU(launch_exact<MODE_SCORE>(b->log2m, p, bstream(b)));
+        CU(launch_exact(MODE_SCORE, b->log2m, p, bstream(b)));
         b->timing.n_launches++;
     }
     return MUSE_OK;
@@ -870,7 +992,7 @@ extern "C" int muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, 
     p.twn = b->twn;
     p.out_score = d_cc;
     p.out_flag = b->d_flag;
-    CU(launch_exact<MODE_CC>(b->log2m, p, bstream(b)));
+    CU(launch_exact(MODE_CC, b->log2m, p, bstream(b)));
     int32_t flag = 0;
     CU(cudaMemcpyAsync(cc, d_cc, sizeof(double) * (size_t)b->n, cudaMemcpyDeviceToHost, bstream(b)));
     CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, bstream(b)));
@@ -904,18 +1026,45 @@ struct Rec {
     int32_t lag() const { return (lagsgn - (lagsgn & 1)) / 2; }
 };
 
+// Key bits per group-by column.  64 / ncols each when every column's cardinality fits: that packing does not depend on the
+// store, so the shards of a multi-GPU run merge on it.  Otherwise ceil(log2(cardinality)) of THIS store's columns, which
+// any number of keys up to MUSE_MAX_KEY_COLS can use as long as the widths sum to at most 64 bits (*rank_independent = 0).
+static int key_bits(const muse_group *g, const int32_t *key_cols, int n_key_cols, int *bits, int *rank_independent) {
+    if (n_key_cols > MUSE_MAX_KEY_COLS) return fail(MUSE_ERR_UNSUPPORTED, "grouping by more than %d label keys", MUSE_MAX_KEY_COLS);
+    const int fixed = 64 / n_key_cols;
+    bool fits = true;
+    int total = 0;
+    for (int c = 0; c < n_key_cols; c++) {
+        const int col = key_cols[c];
+        if (col < 0 || col >= g->nkeys) return fail(MUSE_ERR_INVALID_ARG, "key column %d not in [0,%d)", col, g->nkeys);
+        const int64_t card = (int64_t)g->max_id[col] + 2;      // ids -1 .. max_id -> values 0 .. max_id + 1
+        int w = 1;
+        while (w < 63 && (1LL << w) < card) w++;
+        bits[c] = w;
+        total += w;
+        if (fixed < 64 && card > (1LL << fixed)) fits = false;
+    }
+    if (fits) {
+        for (int c = 0; c < n_key_cols; c++) bits[c] = fixed;
+        if (rank_independent) *rank_independent = 1;
+        return MUSE_OK;
+    }
+    if (total > 64)
+        return fail(MUSE_ERR_UNSUPPORTED, "the label cardinalities of the %d group-by keys need %d key bits (at most 64)", n_key_cols, total);
+    if (rank_independent) *rank_independent = 0;
+    return MUSE_OK;
+}
+
 static int setup_group_table(muse_batch *b, const RunArgs &a, KeyCols &kc, GroupTable &gt) {
     muse_group *g = b->g;
-    if (a.n_key_cols > 4) return fail(MUSE_ERR_UNSUPPORTED, "grouping by more than 4 label keys");
+    int rc = key_bits(g, a.key_cols, a.n_key_cols, kc.bits, nullptr);
+    if (rc) return rc;
     kc.ncols = a.n_key_cols;
-    kc.bits = 64 / a.n_key_cols;
     long double prod = 1;
     for (int c = 0; c < a.n_key_cols; c++) {
         const int col = a.key_cols[c];
-        if (col < 0 || col >= g->nkeys) return fail(MUSE_ERR_INVALID_ARG, "key column %d not in [0,%d)", col, g->nkeys);
         kc.col[c] = g->labels + (size_t)col * g->cap;
         const int64_t card = (int64_t)g->max_id[col] + 2;
-        if (kc.bits < 64 && card > (1LL << kc.bits)) return fail(MUSE_ERR_UNSUPPORTED, "label cardinality %lld does not fit %d key bits", (long long)card, kc.bits);
         gt.radix[c] = card;
         prod *= (long double)card;
     }
@@ -1053,85 +1202,33 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
     return MUSE_OK;
 }
 
-template <int NZ>
-static cudaError_t launch_screen_warp_nz(const ScreenParams &p, int sm_count, cudaStream_t st) {
-    using C = ScreenWarpCfg;
-    auto kern = score_screen_warp_kernel<NZ>;
-    const int warps = C::warps(p.N);
-    const size_t wb = C::warp_bytes(p.N);
-    const size_t smem = C::smem_bytes(p.N);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int64_t blocks = (p.count + warps - 1) / warps;      // persistent: one block per SM
-    if (blocks > sm_count) blocks = sm_count;
-    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(p, (unsigned)wb, (unsigned)C::row_bytes(p.N));
-    return cudaGetLastError();
-}
-
-// n = 2048: one instantiation per number of non-zero rows of 32 complex slots (N = 1026 .. 2048)
-static cudaError_t launch_screen_warp(const ScreenParams &p, int sm_count, cudaStream_t st) {
-    switch (ScreenWarpCfg::nz(p.N)) {
-#define MUSE_NZ_CASE(z) case z: return launch_screen_warp_nz<z>(p, sm_count, st);
-        MUSE_NZ_CASE(17) MUSE_NZ_CASE(18) MUSE_NZ_CASE(19) MUSE_NZ_CASE(20) MUSE_NZ_CASE(21) MUSE_NZ_CASE(22)
-        MUSE_NZ_CASE(23) MUSE_NZ_CASE(24) MUSE_NZ_CASE(25) MUSE_NZ_CASE(26) MUSE_NZ_CASE(27) MUSE_NZ_CASE(28)
-        MUSE_NZ_CASE(29) MUSE_NZ_CASE(30) MUSE_NZ_CASE(31) MUSE_NZ_CASE(32)
-#undef MUSE_NZ_CASE
-    }
-    return cudaErrorInvalidValue;
-}
-
-template <int LOG2M, int MINB>
-static cudaError_t launch_screen_block(const ScreenParams &p, int sm_count, cudaStream_t st) {
-    using C = ScreenBlockCfg<LOG2M>;
-    auto kern = score_screen_block_kernel<LOG2M, MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, C::SMEM);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    const int64_t blocks = std::min<int64_t>(p.count, (int64_t)sm_count * per_sm);     // persistent: grid-stride over the series
-    kern<<<(unsigned)blocks, C::T, C::SMEM, st>>>(p);
-    return cudaGetLastError();
-}
-
 static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cudaStream_t st) {
-    switch (b->log2m) {
-        case 13: return launch_screen_block<13, 2>(p, b->ctx->sm_count, st);
-        case 12: return launch_screen_block<12, 4>(p, b->ctx->sm_count, st);
-        case 11: return launch_screen_block<11, 8>(p, b->ctx->sm_count, st);
-        case 10: return launch_screen_warp(p, b->ctx->sm_count, st);
-        case 9: return launch_screen_block<9, 16>(p, b->ctx->sm_count, st);
-        case 8: return launch_screen_block<8, 16>(p, b->ctx->sm_count, st);
-    }
-    return cudaErrorInvalidValue;
+    if (b->log2m == 10) return launch_screen_warp(p, b->ctx->sm_count, st);
+    if (screen_is_big(b->log2m)) return launch_screen_big(b->log2m, p, b->ctx->sm_count, st);
+    return launch_screen_block(b->log2m, p, b->ctx->sm_count, st);
 }
 
 static int ensure_lower(muse_batch *b) {
     const int64_t S = b->g->size;
     if (!b->d_L || b->d_L_cap < S) {
         cudaFree(b->d_L);
+        cudaFree(b->d_W);
         b->d_L = nullptr;
+        b->d_W = nullptr;
+        b->d_L_cap = 0;
         CU(cudaMalloc(&b->d_L, sizeof(float) * (size_t)S));
+        CU(cudaMalloc(&b->d_W, (size_t)S));
         b->d_L_cap = S;
     }
     return MUSE_OK;
 }
 
-// Per-row statistics of the store (RowStat), computed once for rows appended since the last screened run.
+// Per-row statistics of the store (RowStat): the ingest paths queue them behind the copy that brings the rows in
+// (queue_row_stats, synth_rows_kernel); this is the safety net for rows that arrived any other way.
 static int refresh_row_stats(muse_group *g) {
-    if (g->stats_cap < g->cap) {
-        if (g->row_stat) cudaFree(g->row_stat);
-        g->row_stat = nullptr;
-        CU(cudaMalloc(&g->row_stat, sizeof(RowStat) * (size_t)g->cap));
-        g->stats_cap = g->cap;
-        g->stats_upto = 0;
-    }
     if (g->stats_upto < g->size) {
-        const int64_t count = g->size - g->stats_upto;
-        const unsigned grid = (unsigned)std::min<int64_t>((count + 7) / 8, (int64_t)g->ctx->sm_count * 16);
-        row_stats_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, (int)g->N, g->stats_upto, count, g->row_stat);
-        CU(cudaGetLastError());
+        int rc = queue_row_stats(g, g->stats_upto, g->size - g->stats_upto);
+        if (rc) return rc;
         g->stats_upto = g->size;
     }
     return MUSE_OK;
@@ -1149,6 +1246,7 @@ static ScreenParams screen_params(muse_batch *b) {
     sp.a_mid = b->a_mid;
     sp.out_U = b->d_U;
     sp.sx = b->sx_f;
+    sp.twi = b->twi_f;
     sp.x_mid = b->x_mid;
     sp.row_stat = b->g->row_stat;
     sp.cut_bits = b->d_cut;
@@ -1275,12 +1373,10 @@ static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
     if (rc) return rc;
     sp.out_L = b->d_L;
     sp.grouped = 1;
-    rc = arm_refinement(b, sp, 0.f, 0, 0x7fffffff, 0.0);         // cut-off 0 that never rises: refine everything
+    // a member below the threshold cannot be the representative of a group that passes results.go:46-52
+    const float thr_lo = a.threshold > 0 ? (float)a.threshold * 0.999999f : 0.f;
+    rc = arm_refinement(b, sp, thr_lo, a.max_lag, 0x7fffffff, 0.0);      // a cut-off that never rises
     if (rc) return rc;
-    CU(launch_screen(b, sp, st));
-    b->timing.n_launches += 2;
-    CU(cudaEventRecord(b->ev[1], st));
-    CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "not its group's representative"
     GroupTable gt;
     memset(&gt, 0, sizeof(gt));
     KeyCols kc;
@@ -1288,9 +1384,24 @@ static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
     rc = setup_group_table(b, a, kc, gt);
     if (rc) return rc;
     const unsigned blocks = (unsigned)((S + 255) / 256);
-    group_lower_bound_kernel<<<blocks, 256, 0, st>>>(gt, kc, b->d_L, S, b->d_slot);
-    group_contenders_kernel<<<blocks, 256, 0, st>>>(gt, b->d_U, S, b->d_slot, b->d_list, b->d_counters + 2);
+    const bool running = screen_is_big(b->log2m);      // the kernel itself keeps each group's best lower bound
+    if (running) {
+        group_slots_kernel<<<blocks, 256, 0, st>>>(gt, kc, S, b->d_slot);
+        sp.slot_of = b->d_slot;
+        sp.group_L = gt.gmax;
+        sp.out_W = b->d_W;
+        b->timing.n_launches++;
+    }
+    CU(launch_screen(b, sp, st));
     b->timing.n_launches += 2;
+    TIMING_EVENT(b, 1, st);
+    CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, st));      // NaN = "not its group's representative"
+    if (!running) {
+        group_lower_bound_kernel<<<blocks, 256, 0, st>>>(gt, kc, b->d_L, S, b->d_slot);
+        b->timing.n_launches++;
+    }
+    group_contenders_kernel<<<blocks, 256, 0, st>>>(gt, b->d_U, S, b->d_slot, thr_lo, b->d_list, b->d_counters + 2);
+    b->timing.n_launches++;
     CU(cudaGetLastError());
     unsigned long long *h_n = reinterpret_cast<unsigned long long *>(b->h_pin);
     CU(cudaMemcpyAsync(h_n, b->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1336,7 +1447,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
         b->fused_run = 2;          // statistics as a fused run; its exact list is already complete
         rc = score_fused_grouped(b, a);
         if (rc) return rc;
-        CU(cudaEventRecord(b->ev[2], st));
+        TIMING_EVENT(b, 2, st);
         return MUSE_OK;
     }
     if (screen) {
@@ -1350,19 +1461,32 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     b->timing.mode = MUSE_MODE_EXACT;
     rc = score_exact_all(b, a.signed_scores, nullptr, b->g->size);
     if (rc) return rc;
-    CU(cudaEventRecord(b->ev[1], st));
-    CU(cudaEventRecord(b->ev[2], st));
+    TIMING_EVENT(b, 1, st);
+    TIMING_EVENT(b, 2, st);
     return MUSE_OK;
 }
 
+// Elapsed times between the run's events.  The batches of a multi-query launch record none (TIMING_EVENT), so there is
+// nothing to read for them; a failed query of an event must not stay behind as the runtime's last error.
+static void read_timing_events(muse_batch *b) {
+    float *out[4] = {&b->timing.total_ms, &b->timing.score_ms, &b->timing.rescore_ms, &b->timing.select_ms};
+    const int from[4] = {0, 0, 1, 2}, to[4] = {3, 1, 2, 3};
+    for (int i = 0; i < 4; i++)
+        if (cudaEventElapsedTime(out[i], b->ev[from[i]], b->ev[to[i]]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            *out[i] = 0.f;
+        }
+}
+
 static int finish_timing(muse_batch *b) {
+    if (b->use_aux) {      // a query of a multi-query launch: no events were recorded for this run
+        CU(cudaStreamSynchronize(bstream(b)));
+        return MUSE_OK;
+    }
     cudaStream_t st = bstream(b);
     CU(cudaEventRecord(b->ev[3], st));
     CU(cudaEventSynchronize(b->ev[3]));
-    cudaEventElapsedTime(&b->timing.total_ms, b->ev[0], b->ev[3]);
-    cudaEventElapsedTime(&b->timing.score_ms, b->ev[0], b->ev[1]);
-    cudaEventElapsedTime(&b->timing.rescore_ms, b->ev[1], b->ev[2]);
-    cudaEventElapsedTime(&b->timing.select_ms, b->ev[2], b->ev[3]);
+    read_timing_events(b);
     return MUSE_OK;
 }
 
@@ -1536,7 +1660,11 @@ static int host_keys(muse_batch *b, const RunArgs &a, const std::vector<Rec> &re
     // canonical group key of each record's series (labels fetched per record)
     keys.resize(recs.size());
     muse_group *g = b->g;
-    const int bits = 64 / a.n_key_cols;
+    int bits[MUSE_MAX_KEY_COLS], rank_independent = 0;
+    int rc = key_bits(g, a.key_cols, a.n_key_cols, bits, &rank_independent);
+    if (rc) return rc;
+    if (!rank_independent)
+        return fail(MUSE_ERR_UNSUPPORTED, "shard partials need group keys of at most %d bits per column (64 / %d keys)", 64 / a.n_key_cols, a.n_key_cols);
     cudaStream_t st = bstream(b);
     std::vector<int32_t> ids(recs.size() * (size_t)a.n_key_cols);
     if (recs.size() > 4096) {
@@ -1557,7 +1685,7 @@ static int host_keys(muse_batch *b, const RunArgs &a, const std::vector<Rec> &re
         uint64_t key = 0;
         for (int c = 0; c < a.n_key_cols; c++) {
             const uint64_t v = (uint64_t)(ids[i * a.n_key_cols + c] + 1);
-            key = bits == 64 ? v : ((key << bits) | v);
+            key = bits[c] >= 64 ? v : ((key << bits[c]) | v);
         }
         keys[i] = key;
     }
@@ -1651,31 +1779,6 @@ extern "C" int muse_merge_partials(const muse_partial *parts, int64_t n_parts, i
 // row statistics and the run scratch (context pool) are shared, results of query q land in row q of the
 // outputs.  Every query still streams the slab once (HBM-bound, 2.3 ms per 1 M x 1440 series); the multi-query
 // bound pass that reads the slab once for ALL queries is DESIGN.md section 8's next step.
-template <int NZ>
-static cudaError_t launch_screen_multi_nz(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st) {
-    using C = ScreenMultiCfg;
-    auto kern = score_screen_multi_kernel<NZ>;
-    const int warps = C::warps(p.N);
-    const size_t smem = C::smem_bytes(p.N);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int64_t blocks = (p.count + warps - 1) / warps;      // persistent: one block per SM
-    if (blocks > sm_count) blocks = sm_count;
-    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(p, d_queries, nq, (unsigned)C::warp_bytes(p.N), (unsigned)C::row_bytes(p.N));
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_screen_multi(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st) {
-    switch (ScreenWarpCfg::nz(p.N)) {
-#define MUSE_NZ_CASE(z) case z: return launch_screen_multi_nz<z>(p, d_queries, nq, sm_count, st);
-        MUSE_NZ_CASE(17) MUSE_NZ_CASE(18) MUSE_NZ_CASE(19) MUSE_NZ_CASE(20) MUSE_NZ_CASE(21) MUSE_NZ_CASE(22)
-        MUSE_NZ_CASE(23) MUSE_NZ_CASE(24) MUSE_NZ_CASE(25) MUSE_NZ_CASE(26) MUSE_NZ_CASE(27) MUSE_NZ_CASE(28)
-        MUSE_NZ_CASE(29) MUSE_NZ_CASE(30) MUSE_NZ_CASE(31) MUSE_NZ_CASE(32)
-#undef MUSE_NZ_CASE
-    }
-    return cudaErrorInvalidValue;
-}
-
 // Up to ScreenMultiCfg::QC queries in ONE pass over the slab: every batch gets its cut-off state armed, the
 // multi-query kernel fills each batch's bounds (d_U) and cut-off, and each batch is marked `prescreened` so that
 // its next fused run starts at the tail (survivors -> exact fp64 kernel -> filter -> top-N).
@@ -2039,10 +2142,7 @@ extern "C" int muse_batch_last_timing(const muse_batch *cb, muse_timing *out) {
     if (b->timing_pending) {     // a device-side run (muse_batch_run_partial_device): finish its bookkeeping now
         CU(cudaSetDevice(b->ctx->device));
         CU(cudaEventSynchronize(b->ev[3]));
-        cudaEventElapsedTime(&b->timing.total_ms, b->ev[0], b->ev[3]);
-        cudaEventElapsedTime(&b->timing.score_ms, b->ev[0], b->ev[1]);
-        cudaEventElapsedTime(&b->timing.rescore_ms, b->ev[1], b->ev[2]);
-        cudaEventElapsedTime(&b->timing.select_ms, b->ev[2], b->ev[3]);
+        read_timing_events(b);
         const unsigned long long *h_n = reinterpret_cast<const unsigned long long *>(b->h_pin);
         if (b->fused_run) {
             b->timing.n_rescored = (int64_t)h_n[2];

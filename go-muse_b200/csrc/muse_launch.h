@@ -1,0 +1,27 @@
+// muse_launch.h -- host-side launchers of the templated score kernels.  Each family of instantiations is its own
+// translation unit (kernels_*.cu) so that the library builds in parallel; muse_api.cu sees only these entry points.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "muse_exact.cuh"
+#include "muse_screen_big.cuh"
+#include "muse_screen_block.cuh"
+#include "muse_screen_multi.cuh"
+
+namespace muse {
+
+// score_exact_kernel<log2m, ., mode> (muse_exact.cuh); log2m = log2(n/2) in 0 .. 13
+cudaError_t launch_exact(int mode, int log2m, const ExactParams &p, cudaStream_t st);
+// points per thread of the exact kernel for each FFT size (fixes the twiddle layout of ExactParams::twM)
+inline int exact_log2p(int log2m) { return log2m < 4 ? log2m : 4; }
+
+// fp32 screening + fused second stage: warp kernel (n = 2048), block kernel (n = 512, 1024, 4096 .. 16384)
+cudaError_t launch_screen_warp(const ScreenParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_screen_block(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st);
+// n = 4096 .. 16384 (muse_screen_big.cuh)
+cudaError_t launch_screen_big(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st);
+// the same pass for up to ScreenMultiCfg::QC reference queries at once (n = 2048)
+cudaError_t launch_screen_multi(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st);
+
+}  // namespace muse

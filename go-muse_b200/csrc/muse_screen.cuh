@@ -24,6 +24,9 @@
 // 1e-12 and 1e+12 amplitudes, trends) and records the smallest observed margin.
 #pragma once
 
+#include <vector_functions.h>   // float4 / make_float4 (host builds of the emulators too)
+#include <vector_types.h>
+
 #include "muse_score.cuh"
 
 namespace muse {
@@ -79,6 +82,11 @@ struct ScreenParams {
     float thr;            // threshold rounded up to fp32 (a lower bound must reach it to count)
     int grouped;          // grouped run: every series is refined, bounds ignore the window, no cut-off
     float *out_U;         // [count] upper bound on the score (already clamped to <= 1 + slack)
+    // ---- muse_screen_big.cuh ----
+    const cf *twi;        // fp32 twiddles of the transposed inverse (fill_big_inverse_twiddles)
+    const int64_t *slot_of;           // grouped runs: group-table slot of every series
+    unsigned long long *group_L;      // grouped runs: [slots] running best lower bound of each group (float bits, low word)
+    signed char *out_W;   // grouped runs: [count] 1 = peak certainly inside the lag window, -1 = certainly outside, 0 = undecided
 };
 
 #if defined(__CUDACC__)
@@ -209,10 +217,25 @@ __device__ __forceinline__ float refine_decide(float U, float s_in, float s_out,
     return fminf(U, u32);
 }
 
+#if defined(__CUDACC__)
+// RowStat from the sums s1 = sum (y - pivot), s2 = sum (y - pivot)^2 of a row of N samples.
+__device__ __forceinline__ RowStat make_row_stat(double pivot, double s1, double s2, int N) {
+    const double mean = pivot + s1 / N;
+    const double var = (s2 - s1 * s1 / N) / (N - 1);
+    const bool ok = var >= (double)MUSE_SCREEN_VAR_MIN && var <= (double)MUSE_SCREEN_VAR_MAX &&
+                    mean * mean <= MUSE_SCREEN_OFFSET_MAX * MUSE_SCREEN_OFFSET_MAX * var;      // false for NaN / Inf
+    RowStat r;
+    r.mean = mean;
+    r.rstd = ok ? (float)(1.0 / sqrt(var)) : __int_as_float(0x7fc00000);
+    r.pad = 0u;
+    return r;
+}
+#endif
+
 // RowStat of rows first .. first+count-1.  One warp per row; sums are taken about the row's first sample so
 // that the one-pass variance does not cancel (|row[0] - mean| <= sqrt(N-1) * std, so the cancellation costs at
 // most a factor N of the 1e-16).
-__global__ void row_stats_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
+static __global__ void row_stats_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
                                  RowStat *__restrict__ stat) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -231,17 +254,7 @@ __global__ void row_stats_kernel(const double *__restrict__ slab, int64_t ld, in
             s1 += __shfl_xor_sync(0xffffffffu, s1, off);
             s2 += __shfl_xor_sync(0xffffffffu, s2, off);
         }
-        if (lane == 0) {
-            const double mean = pivot + s1 / N;
-            const double var = (s2 - s1 * s1 / N) / (N - 1);
-            const bool ok = var >= (double)MUSE_SCREEN_VAR_MIN && var <= (double)MUSE_SCREEN_VAR_MAX &&
-                            mean * mean <= MUSE_SCREEN_OFFSET_MAX * MUSE_SCREEN_OFFSET_MAX * var;      // false for NaN / Inf
-            RowStat r;
-            r.mean = mean;
-            r.rstd = ok ? (float)(1.0 / sqrt(var)) : __int_as_float(0x7fc00000);
-            r.pad = 0u;
-            stat[first + i] = r;
-        }
+        if (lane == 0) stat[first + i] = make_row_stat(pivot, s1, s2, N);
     }
 }
 

@@ -24,17 +24,19 @@ __device__ __forceinline__ unsigned long long score_bits(double s) {
 // Canonical group key of series i from its label ids: (id+1) packed in 64/ncols bits per
 // column (id < 0 -> 0: "label absent", all such series share a group as labels.go:61-65
 // skips absent keys).  Rank independent, so shards can be merged on it.
+#define MUSE_MAX_KEY_COLS 16
 struct KeyCols {
-    const int32_t *col[4];
+    const int32_t *col[MUSE_MAX_KEY_COLS];
     int ncols;
-    int bits;   // 64 / ncols
+    int bits[MUSE_MAX_KEY_COLS];   // key bits of each column: 64 / ncols each when every cardinality fits (rank independent),
+                                   // else ceil(log2(cardinality)) per column of THIS store (sum <= 64)
 };
 
 __device__ __forceinline__ unsigned long long canonical_key(const KeyCols &kc, int64_t i) {
     unsigned long long key = 0;
     for (int c = 0; c < kc.ncols; c++) {
         const unsigned long long v = (unsigned long long)(kc.col[c][i] + 1);
-        key = (kc.bits == 64) ? v : ((key << kc.bits) | v);
+        key = (kc.bits[c] >= 64) ? v : ((key << kc.bits[c]) | v);
     }
     return key;
 }
@@ -47,7 +49,7 @@ struct GroupTable {
     unsigned long long *hkeys;  // [slots] hash mode: canonical key + 1 (0 = empty)
     int64_t slots;              // power of two in hash mode
     int dense;                  // 1: dense index
-    int64_t radix[4];           // dense: cardinality (max id + 2) per column
+    int64_t radix[MUSE_MAX_KEY_COLS];   // dense: cardinality (max id + 2) per column
 };
 
 __device__ __forceinline__ int64_t table_slot(const GroupTable &gt, const KeyCols &kc, int64_t i) {
@@ -82,6 +84,12 @@ __global__ void group_max_kernel(GroupTable gt, KeyCols kc, const double *__rest
     if (sc == sc) atomicMax(&gt.gmax[s], score_bits(sc));
 }
 
+// slot of every series in the group table (hash mode: inserts the key)
+__global__ void group_slots_kernel(GroupTable gt, KeyCols kc, int64_t S, int64_t *__restrict__ slot_of) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) slot_of[i] = table_slot(gt, kc, i);
+}
+
 // Grouped screening: slot per series + atomicMax of the fp32 LOWER bounds of the members' scores
 // (float bits in the low word of gmax; non-negative floats order like their bit patterns).
 __global__ void group_lower_bound_kernel(GroupTable gt, KeyCols kc, const float *__restrict__ lower, int64_t S,
@@ -96,11 +104,13 @@ __global__ void group_lower_bound_kernel(GroupTable gt, KeyCols kc, const float 
 
 // ... and the members that can still be their group's representative: upper bound >= the group's
 // best lower bound (the true representative always qualifies, and so does every member that ties it)
+// A member whose upper bound is below thr_lo (<= the threshold) cannot be the representative of a group that passes
+// results.go:46-52 -- if it were, the whole group would fail -- so it is left out as well.
 __global__ void group_contenders_kernel(GroupTable gt, const float *__restrict__ upper, int64_t S,
-                                        const int64_t *__restrict__ slot_of, int32_t *__restrict__ out,
+                                        const int64_t *__restrict__ slot_of, float thr_lo, int32_t *__restrict__ out,
                                         unsigned long long *n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool take = i < S && upper[i] >= __uint_as_float((unsigned)gt.gmax[slot_of[i]]);
+    const bool take = i < S && upper[i] >= thr_lo && upper[i] >= __uint_as_float((unsigned)gt.gmax[slot_of[i]]);
     const unsigned mask = __ballot_sync(0xffffffffu, take);
     if (mask == 0u) return;
     const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;

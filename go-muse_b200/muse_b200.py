@@ -43,7 +43,10 @@ SignFilter_ANY = 0    # results.go:25
 DefaultLabel = "uid"  # labels.go:7
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
+# translation units of libmuse_b200.so: the C ABI and one file per family of kernel instantiations
+SOURCES = ["muse_api.cu", "kernels_exact.cu", "kernels_screen_warp.cu", "kernels_screen_block.cu",
+           "kernels_screen_big.cu", "kernels_screen_multi.cu", "kernels_bounds_tc.cu"]
 
 
 class MuseError(Exception):
@@ -69,18 +72,40 @@ PARTIAL_DTYPE = np.dtype([("group_key", "<u8"), ("score", "<f8"), ("series_idx",
                           ("lag", "<i4"), ("flags", "<i4")])
 
 
-def build(verbose: bool = False) -> str:
-    """Compile libmuse_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    src = os.path.join(_HERE, "csrc", "muse_api.cu")
-    deps = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
-    deps.append(os.path.join(_ROOT, "include", "muse_b200.h"))
-    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
-    return LIB_PATH
+def build(verbose: bool = False, out: Optional[str] = None, extra_flags: Sequence[str] = (), tag: str = "") -> str:
+    """Compile libmuse_b200.so for sm_100a with nvcc (cross-compiles without a GPU): one object per translation
+    unit, compiled side by side, then one link.  out / extra_flags / tag: a variant build for kernel A/B runs
+    (tools/build_variant.py; loaded with MUSE_B200_LIB)."""
+    from concurrent.futures import ThreadPoolExecutor
+    csrc = os.path.join(_HERE, "csrc")
+    lib_path = out or LIB_PATH
+    hdrs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(_ROOT, "include", "muse_b200.h"))
+    objdir = os.path.join(_ROOT, "build", "obj" + ("_" + tag if tag else ""))
+    os.makedirs(objdir, exist_ok=True)
+    srcs = [os.path.join(csrc, f) for f in SOURCES if os.path.exists(os.path.join(csrc, f))]
+    objs = [os.path.join(objdir, os.path.basename(f)[:-3] + ".o") for f in srcs]
+
+    def stale(target, deps):
+        return not os.path.exists(target) or any(os.path.getmtime(target) < os.path.getmtime(d) for d in deps)
+
+    def compile_one(pair):
+        src, obj = pair
+        if not stale(obj, [src] + hdrs):
+            return
+        cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(srcs), os.cpu_count() or 1))) as ex:
+        list(ex.map(compile_one, zip(srcs, objs)))
+    if stale(lib_path, objs):
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_path] + objs
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return lib_path
 
 
 _lib = None

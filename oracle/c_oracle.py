@@ -30,6 +30,10 @@ def lib():
         L.muse_oracle_batch_run.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, ip, C.c_int64, C.c_int64,
                                             C.c_int64, C.c_double, C.c_int, dp, ip, ip, ip, C.c_int]
         L.muse_oracle_max_threads.restype = C.c_int
+        L.muse_oracle_synth_rows.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, dp]
+        L.muse_oracle_synth_rows.restype = None
+        L.muse_oracle_synth_reference.argtypes = [C.c_uint64, C.c_int64, dp]
+        L.muse_oracle_synth_reference.restype = None
         _LIB = L
     return _LIB
 
@@ -40,6 +44,19 @@ def _d(a):
 
 def _i(a):
     return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def synth_rows(seed: int, first: int, count: int, N: int) -> np.ndarray:
+    """Rows first .. first+count-1 of the benchmark's synthetic store (synth_gen.c)."""
+    out = np.empty((count, N))
+    lib().muse_oracle_synth_rows(seed, first, count, N, _d(out))
+    return out
+
+
+def synth_reference(seed: int, N: int) -> np.ndarray:
+    out = np.empty(N)
+    lib().muse_oracle_synth_reference(seed, N, _d(out))
+    return out
 
 
 def max_threads() -> int:

@@ -105,6 +105,19 @@ def test_kernel_phases_on_cpu():
     assert "ALL OK" in out.stdout
 
 
+def test_big_kernel_phases_on_cpu():
+    """score_screen_big_kernel's phases (n = 4096 .. 16384: mirror-paired last pass, split and conj(Y)*X in
+    registers, transposed inverse) run thread by thread on the CPU against a double-precision FFT: the bound
+    sum |Y||X| / n and the maxima of |cc| inside and outside the lag window."""
+    import subprocess
+    exe = "/tmp/muse_emulate_big"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "go-muse_b200", "csrc"),
+                           "-I", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "cpp", "emulate_big.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count(" ok") == 8 and "FAIL" not in out.stdout
+
+
 def test_merge_partials_against_a_model():
     """muse_merge_partials against a direct Python model on random shard outputs: group max across shards
     BEFORE the filter (muse_batch.go:87-89), ties by lowest global series index, filter

@@ -111,6 +111,31 @@ def test_c4_shape_screened_run_is_the_exact_run(ctx):
     np.testing.assert_array_equal(s[1][:20], wlg)
 
 
+def test_c4_grouped_by_two_labels_is_the_exact_run_and_the_oracle(ctx):
+    # BASELINE.json configs[3] as benched: N = 10080, grouped by [graph, host] (100 series per group), maxLag 240, topN 100,
+    # on 100 k synthetic series: the screened run (running per-group lower bound, muse_batch.go:87-89) must be the all-exact
+    # run bit for bit, and both must be the oracle's answer (group.go:76-104 + muse_batch.go:56-93 + results.go:46-87)
+    S, N = 100_000, 10080
+    store = mb.DeviceStore(ctx, N, 3, S)
+    store.append_synthetic(S, SEED, 0)
+    store.set_synthetic_labels([10000, 100, 1], [1000, 100, 100])
+    ref = mb.synth_reference(SEED, N)
+    b = mb.DeviceBatch(ctx, store, ref)
+    e = b.run([0, 1], 240, 100, 0.5, mode=mb.MODE_EXACT)
+    s = b.run([0, 1], 240, 100, 0.5, mode=mb.MODE_AUTO)
+    t = b.timing()
+    assert t.mode == mb.MODE_SCREEN and t.n_rescored < 0.1 * S and t.n_refined < 0.6 * S
+    for x, y in zip(e, s):
+        np.testing.assert_array_equal(x, y)
+    print("C4 grouped, %d series: screened %.2f ms (%d refined, %d exact)" % (S, t.total_ms, t.n_refined, t.n_rescored))
+    Y = store.read_rows(0, S)
+    wsc, wlg, wix = co.batch_run(ref, Y, (np.arange(S) // 100).astype(np.int64), 240, 100, 0.5)
+    assert len(wsc) == len(s[0]) == 100
+    assert np.max(np.abs(s[0] - wsc)) <= 1e-9
+    np.testing.assert_array_equal(s[1], wlg)
+    np.testing.assert_array_equal(s[2], wix)
+
+
 def test_c2_benchmark_shape_matches_oracle(ctx):
     # muse_batch_test.go:137-190: 100 graphs x 50 hosts, N = 480, noise rows, Run(["graph"]), maxLag 10, topN 20, thr 0
     rng = np.random.default_rng(42)

@@ -326,6 +326,33 @@ def test_hash_group_table(ctx):
     assert np.max(np.abs(sc - wsc)) <= SCORE_TOL
 
 
+def test_group_by_six_keys(ctx):
+    # labels.go:54-73 takes any number of keys: six group-by columns (10 key bits each when packed evenly; one column
+    # of cardinality 5000 forces the per-column widths), against the oracle; 9 wide columns do not fit 64 bits -> an error
+    rng = np.random.default_rng(17)
+    S, N = 4000, 100
+    ref, Y = _siggen(rng, S, N)
+    cards = [7, 3, 5000, 2, 11, 4, 200000, 200000, 200000, 200000, 200000, 200000, 200000, 200000, 200000]
+    ids = np.stack([rng.integers(0, c, S) for c in cards], axis=1).astype(np.int32)
+    ids[::5, 2] = 17                       # real groups
+    ids[::5, :2] = 1
+    ids[3, 4] = -1                         # an absent label is a value of its own (labels.go:61-65)
+    store = mb.DeviceStore(ctx, N, len(cards), S)
+    store.append(Y, ids)
+    b = mb.DeviceBatch(ctx, store, ref)
+    for cols in ([0, 1, 2, 3, 4, 5], [0, 1, 3, 4, 5], [5, 4, 3, 2, 1, 0]):
+        key = {}
+        gids = np.array([key.setdefault(tuple(int(v) for v in row), len(key)) for row in ids[:, sorted(cols)]])
+        sc, lg, ix = b.run(cols, 100, 60, 0.0, mode=mb.MODE_EXACT)
+        wsc, wlg, wix = mo.batch_run_arrays(ref, Y, gids, 100, 60, 0.0)
+        np.testing.assert_array_equal(ix, wix)
+        np.testing.assert_array_equal(lg, wlg)
+        assert np.max(np.abs(sc - wsc)) <= SCORE_TOL
+    with pytest.raises(mb.MuseError) as ei:
+        b.run(list(range(6, 15)), 100, 60, 0.0, mode=mb.MODE_EXACT)
+    assert ei.value.code == mb.MUSE_ERR_UNSUPPORTED
+
+
 def test_synthetic_rows_identical_on_host_and_device(ctx):
     N, S, seed, first = 1440, 64, 20261018, 999_990
     store = mb.DeviceStore(ctx, N, 2, S)

@@ -53,3 +53,15 @@ def test_c_batch_run_matches_numpy():
             assert len(a[0]) == len(b[0])
             np.testing.assert_allclose(a[0], b[0], rtol=0, atol=1e-12)
             assert (a[1] == b[1]).all() and (a[2] == b[2]).all()
+
+
+def test_synthetic_generator_matches_the_library():
+    """oracle/synth_gen.c (what bench.py's reference arm generates its rows with) against the library's host-side
+    generator (muse_synth.cuh compiled for the host, itself checked against the device in test_gpu_parity.py)."""
+    import muse_b200 as mb
+    seed = 20261018
+    for N in (480, 1440, 10080):
+        rows = co.synth_rows(seed, 999_990, 24, N)
+        for k in range(24):
+            np.testing.assert_array_equal(rows[k], mb.synth_row(seed, 999_990 + k, N))
+        np.testing.assert_array_equal(co.synth_reference(seed, N), mb.synth_reference(seed, N))
