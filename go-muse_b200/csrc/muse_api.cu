@@ -108,6 +108,12 @@ struct muse_ctx {
     std::vector<RunScratch> pool;   // scratch sets of destroyed batches, reused by the next muse_batch_create
     unsigned char *h_stage[3];      // pinned staging ring for rows that arrive in pageable host memory (muse_group_append)
     cudaEvent_t stage_ev[3];
+    // multi-query bounds on the tensor cores (muse_bounds_tc.cuh): magnitudes of the store and weights of a launch's queries
+    unsigned char *tc_a, *tc_b;     // bf16 tiles: [S/128][16][16 KB] and [16][32 KB]
+    size_t tc_a_bytes;
+    float *tc_mid, *tc_amid;        // [S] |2Y_(M/2)| per series, [256] A_q[M/2] per query
+    int64_t tc_mid_cap;
+    void **tc_ptrs;                 // device: [256] sw tables, [256] bound arrays
     void *d_multi_q;                // query table of score_screen_multi_kernel (ScreenMultiCfg::QC entries)
     double *d_multi_refs;           // [QC][d_multi_ld] reference rows of a multi-query launch, pad columns kept zero
     int64_t d_multi_ld, d_multi_n;
@@ -205,6 +211,7 @@ extern "C" void muse_ctx_destroy(muse_ctx *c) {
         if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
         if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     }
+    cudaFree(c->tc_a); cudaFree(c->tc_b); cudaFree(c->tc_mid); cudaFree(c->tc_amid); cudaFree(c->tc_ptrs);
     cudaFree(c->d_multi_q);
     cudaFree(c->d_multi_refs);
     cudaStreamDestroy(c->own_stream);
@@ -730,8 +737,8 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     std::vector<float2> swtw;
     if (want_screen) {
         if (screen_is_big(b->log2m)) {
-            twi.resize((size_t)((1 << (b->log2m - 10)) - 1) * 1024 + 31 * 32);
-            fill_big_inverse_twiddles(b->log2m, twi.data(), [&](long long num, long long den) {
+            twi.resize((size_t)10 * (M / 32) + 31 * (M / 1024) + 1024 + 31 * 32);      // ScreenBigCfg::TW_TOTAL
+            fill_big_twiddles(b->log2m, twi.data(), [&](long long num, long long den) {
                 return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
             });
             CU(cudaMalloc(&b->twi_f, sizeof(cf) * twi.size()));
@@ -1812,6 +1819,93 @@ static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag,
     CU(launch_screen_multi(sp0, d_q, nq, ctx->sm_count, st));
     for (int q = 0; q < nq; q++) bs[q]->prescreened = 1;
     return MUSE_OK;
+}
+
+// The bounds of up to TcCfg::TN queries (batches bs[0 .. nq), FFT length 2048, tables built) against the whole store, as
+// one bf16 contraction on the tensor cores: magnitudes of every series -> tiles, the queries' weights -> tiles, GEMM with
+// the bound's epilogue into every batch's d_U.  Everything is queued on the context's stream.
+static int tc_bounds_queue(muse_ctx *ctx, muse_group *g, muse_batch **bs, int nq) {
+    const int64_t S = g->size;
+    cudaStream_t st = ctx->stream;
+    int rc = refresh_row_stats(g);
+    if (rc) return rc;
+    const size_t a_bytes = TcCfg::a_bytes(S);
+    if (ctx->tc_a_bytes < a_bytes) {
+        cudaFree(ctx->tc_a);
+        ctx->tc_a = nullptr;
+        ctx->tc_a_bytes = 0;
+        CU(cudaMalloc(&ctx->tc_a, a_bytes));
+        ctx->tc_a_bytes = a_bytes;
+    }
+    if (ctx->tc_mid_cap < S) {
+        cudaFree(ctx->tc_mid);
+        ctx->tc_mid = nullptr;
+        ctx->tc_mid_cap = 0;
+        CU(cudaMalloc(&ctx->tc_mid, sizeof(float) * (size_t)S));
+        ctx->tc_mid_cap = S;
+    }
+    if (!ctx->tc_b) CU(cudaMalloc(&ctx->tc_b, TcCfg::b_bytes()));
+    if (!ctx->tc_amid) CU(cudaMalloc(&ctx->tc_amid, sizeof(float) * TcCfg::TN));
+    if (!ctx->tc_ptrs) CU(cudaMalloc(&ctx->tc_ptrs, sizeof(void *) * 2 * TcCfg::TN));
+    void *h_ptrs[2 * TcCfg::TN];
+    float h_amid[TcCfg::TN];
+    memset(h_ptrs, 0, sizeof(h_ptrs));
+    memset(h_amid, 0, sizeof(h_amid));
+    for (int q = 0; q < nq; q++) {
+        rc = ensure_scratch(bs[q]);
+        if (rc) return rc;
+        h_ptrs[q] = bs[q]->sw_f;
+        h_ptrs[TcCfg::TN + q] = bs[q]->d_U;
+        h_amid[q] = bs[q]->a_mid;
+    }
+    // pageable sources: the copies have left the host buffers when the calls return
+    CU(cudaMemcpyAsync(ctx->tc_ptrs, h_ptrs, sizeof(h_ptrs), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->tc_amid, h_amid, sizeof(h_amid), cudaMemcpyHostToDevice, st));
+    ScreenParams sp = screen_params(bs[0]);
+    CU(launch_mag_tiles(sp, ctx->tc_a, ctx->tc_mid, ctx->sm_count, st));
+    CU(launch_weight_tiles(reinterpret_cast<const float4 *const *>(ctx->tc_ptrs), nq, ctx->tc_b, st));
+    TcBoundsParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.a_tiles = ctx->tc_a;
+    tp.b_tiles = ctx->tc_b;
+    tp.mid = ctx->tc_mid;
+    tp.amid = ctx->tc_amid;
+    tp.row_stat = g->row_stat;
+    tp.out_U = reinterpret_cast<float *const *>(ctx->tc_ptrs + TcCfg::TN);
+    tp.S = S;
+    tp.nq = nq;
+    CU(launch_bounds_tc(tp, st));
+    return MUSE_OK;
+}
+
+static bool tc_shape_ok(const muse_group *g, int64_t ref_len) {
+    return ref_len == g->N && (ref_len & 1) == 0 && next_pow2(ref_len) == 2048;
+}
+
+extern "C" int muse_multi_bounds_tc(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len, float *upper) {
+    if (!ctx || !g || !refs || !upper) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_bounds_tc: NULL argument");
+    if (n_refs < 1 || n_refs > TcCfg::TN) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_bounds_tc: 1 .. %d references", TcCfg::TN);
+    if (!tc_shape_ok(g, ref_len)) return fail(MUSE_ERR_UNSUPPORTED, "the tensor-core bounds exist for even series lengths of FFT length 2048");
+    CU(cudaSetDevice(ctx->device));
+    const int64_t S = g->size;
+    if (S == 0) return MUSE_OK;
+    std::vector<muse_batch *> bs;
+    int rc = MUSE_OK;
+    for (int64_t q = 0; q < n_refs && rc == MUSE_OK; q++) {
+        muse_batch *b = nullptr;
+        rc = muse_batch_create(ctx, g, refs + (size_t)q * (size_t)ref_len, ref_len, &b);
+        if (rc == MUSE_OK) bs.push_back(b);
+    }
+    if (rc == MUSE_OK) rc = tc_bounds_queue(ctx, g, bs.data(), (int)bs.size());
+    for (size_t q = 0; q < bs.size() && rc == MUSE_OK; q++)
+        if (cudaMemcpyAsync(upper + q * (size_t)S, bs[q]->d_U, sizeof(float) * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            rc = fail(MUSE_ERR_CUDA, "muse_multi_bounds_tc: copy failed");
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && rc == MUSE_OK) {
+        (void)cudaGetLastError();
+        rc = fail(MUSE_ERR_CUDA, "muse_multi_bounds_tc: %s", cudaGetErrorString(cudaPeekAtLastError()));
+    }
+    for (muse_batch *b : bs) muse_batch_destroy(b);
+    return rc;
 }
 
 extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len,

@@ -8,6 +8,7 @@
 #include "muse_screen_big.cuh"
 #include "muse_screen_block.cuh"
 #include "muse_screen_multi.cuh"
+#include "muse_bounds_tc.cuh"
 
 namespace muse {
 
@@ -23,5 +24,10 @@ cudaError_t launch_screen_block(int log2m, const ScreenParams &p, int sm_count, 
 cudaError_t launch_screen_big(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st);
 // the same pass for up to ScreenMultiCfg::QC reference queries at once (n = 2048)
 cudaError_t launch_screen_multi(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st);
+
+// many queries' bounds as one bf16 contraction on the tensor cores (muse_bounds_tc.cuh)
+cudaError_t launch_mag_tiles(const ScreenParams &p, unsigned char *a_tiles, float *mid, int sm_count, cudaStream_t st);
+cudaError_t launch_weight_tiles(const float4 *const *d_sw, int nq, unsigned char *b_tiles, cudaStream_t st);
+cudaError_t launch_bounds_tc(const TcBoundsParams &p, cudaStream_t st);
 
 }  // namespace muse

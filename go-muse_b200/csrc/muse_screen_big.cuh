@@ -46,20 +46,34 @@ struct ScreenBigCfg {
     // uses padR (one spare element per R)
     static constexpr int SM_ELEMS = M + (M >> LR) + 2;
     static constexpr size_t SMEM = (size_t)SM_ELEMS * 8;
-    // fp32 twiddles of the inverse: pass 0' W_M^(j*b) [(R-1) x 1024], pass 1' W_1024^(j*p) [31 x 32]
-    static constexpr int TWI1_OFF = (R - 1) * 1024;
-    static constexpr int TWI_TOTAL = TWI1_OFF + 31 * 32;
-    // forward per-pass tables (fill_pass_twiddles(LOG2M, 5)): pass 0 W_M^(j*t) [31 x T], pass 1 W_T^(j*p) [31 x T/32]
-    static constexpr int TWF1_OFF = 31 * T;
+    // fp32 twiddle tables of this kernel, ONE array (fill_big_twiddles), sized to stay L1-resident next to two blocks'
+    // exchange buffers (a full W_M^(j t) table is 64 KB at n = 16384 and every load of it went to L2):
+    //   forward pass 0: W_M^(j t) = W_M^(8 a t) * W_M^(b t), j = 8 a + b:   A [3 x T] (a = 1..3), B [7 x T] (b = 1..7)
+    //   forward pass 1: W_T^(j p) [31 x T/32]
+    //   inverse pass 0': W_M^b [1024], the higher powers W_M^(j b), j < R, by multiplication
+    //   inverse pass 1': W_1024^(j p) [31 x 32]
+    static constexpr int TWF0_OFF = 0;
+    static constexpr int TWF1_OFF = 10 * T;
+    static constexpr int TWI0_OFF = TWF1_OFF + 31 * (T / 32);
+    static constexpr int TWI1_OFF = TWI0_OFF + 1024;
+    static constexpr int TW_TOTAL = TWI1_OFF + 31 * 32;
 };
 
 template <typename TW, typename FN>
-inline void fill_big_inverse_twiddles(int log2m, TW *out, FN unit_root /* (num, den) -> TW */) {
-    const int R = 1 << (log2m - 10), M = 1 << log2m;
-    for (int j = 1; j < R; j++)
-        for (int b = 0; b < 1024; b++) out[(j - 1) * 1024 + b] = unit_root((long long)j * b, (long long)M);
+inline void fill_big_twiddles(int log2m, TW *out, FN unit_root /* (num, den) -> TW */) {
+    const int M = 1 << log2m, T = M / 32;
+    for (int a = 1; a < 4; a++)
+        for (int t = 0; t < T; t++) out[(a - 1) * T + t] = unit_root((long long)8 * a * t, (long long)M);
+    for (int b = 1; b < 8; b++)
+        for (int t = 0; t < T; t++) out[(3 + b - 1) * T + t] = unit_root((long long)b * t, (long long)M);
+    TW *p1 = out + 10 * T;
     for (int j = 1; j < 32; j++)
-        for (int p = 0; p < 32; p++) out[(R - 1) * 1024 + (j - 1) * 32 + p] = unit_root((long long)j * p, 1024LL);
+        for (int p = 0; p < T / 32; p++) p1[(j - 1) * (T / 32) + p] = unit_root((long long)j * p, (long long)T);
+    TW *i0 = p1 + 31 * (T / 32);
+    for (int b = 0; b < 1024; b++) i0[b] = unit_root((long long)b, (long long)M);
+    TW *i1 = i0 + 1024;
+    for (int j = 1; j < 32; j++)
+        for (int p = 0; p < 32; p++) i1[(j - 1) * 32 + p] = unit_root((long long)j * p, 1024LL);
 }
 
 MUSE_HD float big_sqrt(float x) {
@@ -86,14 +100,24 @@ MUSE_HD float4 big_load_f4(const float4 *p) {
 // ---- forward passes (Stockham, radix 32, 32, R) ------------------------------------------------------------
 // pass 0: inputs v[j] = z[t + T*j]; writes y[32 t + j] * W_M^(j t) (pad5)
 template <int LOG2M>
-MUSE_HD void big_fwd_pass0(cf *v, cf *sm, int t, const cf *twp) {
+MUSE_HD void big_fwd_pass0(cf *v, cf *sm, int t, const cf *tw) {
     using C = ScreenBigCfg<LOG2M>;
     Dft<32, float>::run(v);
     cf *dst = sm + 33 * t;
-    const cf *tw = twp + t;
+    const cf *twt = tw + C::TWF0_OFF + t;
+    cf wb[8];
+#pragma unroll
+    for (int b = 1; b < 8; b++) wb[b] = twt[(3 + b - 1) * C::T];
     dst[0] = v[Perm<32>::at(0)];
 #pragma unroll
-    for (int j = 1; j < 32; j++) dst[j] = cmul(v[Perm<32>::at(j)], tw[(j - 1) * C::T]);
+    for (int b = 1; b < 8; b++) dst[b] = cmul(v[Perm<32>::at(b)], wb[b]);
+#pragma unroll
+    for (int a = 1; a < 4; a++) {
+        const cf wa = twt[(a - 1) * C::T];
+        dst[8 * a] = cmul(v[Perm<32>::at(8 * a)], wa);
+#pragma unroll
+        for (int b = 1; b < 8; b++) dst[8 * a + b] = cmul(v[Perm<32>::at(8 * a + b)], cmul(wa, wb[b]));
+    }
 }
 // loads of passes whose butterfly is the thread itself: inputs t + T*j under pad5
 template <int LOG2M>
@@ -105,12 +129,12 @@ MUSE_HD void big_load_stride_t(cf *v, const cf *sm, int t) {
 }
 // pass 1: butterfly t: p = t / 32, q = t % 32; writes y[q + 1024 p + 32 j] * W_T^(j p) (pad5)
 template <int LOG2M>
-MUSE_HD void big_fwd_pass1(cf *v, cf *sm, int t, const cf *twp) {
+MUSE_HD void big_fwd_pass1(cf *v, cf *sm, int t, const cf *twb) {
     using C = ScreenBigCfg<LOG2M>;
     Dft<32, float>::run(v);
     const int p = t >> 5, q = t & 31;
     cf *dst = sm + q + 1056 * p;
-    const cf *tw = twp + C::TWF1_OFF + p;
+    const cf *tw = twb + C::TWF1_OFF + p;
     dst[0] = v[Perm<32>::at(0)];
 #pragma unroll
     for (int j = 1; j < 32; j++) dst[33 * j] = cmul(v[Perm<32>::at(j)], tw[(j - 1) * (C::T / 32)]);
@@ -266,8 +290,12 @@ MUSE_HD void big_inv_pass0(cf *v, cf *sm, int t, const cf *twi) {
             Dft<R, float>::run(w);
             cf *dst = sm + (R + 1) * b;
             dst[0] = w[Perm<R>::at(0)];
+            cf pw[R];                          // W_M^(j b): j = 1 from the table, the rest by products of depth <= 3
+            pw[1] = twi[C::TWI0_OFF + b];
 #pragma unroll
-            for (int j = 1; j < R; j++) dst[j] = cmul(w[Perm<R>::at(j)], twi[(j - 1) * 1024 + b]);
+            for (int j = 2; j < R; j++) pw[j] = cmul(pw[j / 2], pw[j - j / 2]);
+#pragma unroll
+            for (int j = 1; j < R; j++) dst[j] = cmul(w[Perm<R>::at(j)], pw[j]);
         }
     }
 }
@@ -373,11 +401,11 @@ score_screen_big_kernel(const ScreenParams prm) {
         }
 
         // ---- forward FFT_M; ends with Z in registers in mirror-paired order ----
-        big_fwd_pass0<LOG2M>(v, sm, t, prm.twp);
+        big_fwd_pass0<LOG2M>(v, sm, t, prm.twi);
         __syncthreads();
         big_load_stride_t<LOG2M>(v, sm, t);
         __syncthreads();
-        big_fwd_pass1<LOG2M>(v, sm, t, prm.twp);
+        big_fwd_pass1<LOG2M>(v, sm, t, prm.twi);
         __syncthreads();
         big_fwd_last<LOG2M>(v, sm, t);
 

@@ -151,6 +151,7 @@ ABI = {
     "muse_batch_run_partial_device": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32, _vp, C.c_int64]),
     "muse_multi_run": (C.c_int, [_vp, _vp, _dp, C.c_int64, C.c_int64, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double,
                                  C.c_int32, C.c_int32, _dp, _ip64, _ip64, _ip64]),
+    "muse_multi_bounds_tc": (C.c_int, [_vp, _vp, _dp, C.c_int64, C.c_int64, _vp]),
     "muse_xcorr": (C.c_int, [_vp, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int32, _dp, C.c_int64, _ip64, _ip64,
                              C.POINTER(C.c_double), _ip32]),
     "muse_exchange_create": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.POINTER(_vp)]),
@@ -434,6 +435,16 @@ def multi_run(store: "DeviceStore", refs, key_cols: Sequence[int], max_lag: int,
         return sc[:Q], lg[:Q], ix[:Q], n_out[:Q]
     return [None if n_out[q] < 0 else (sc[q, :n_out[q]].copy(), lg[q, :n_out[q]].copy(), ix[q, :n_out[q]].copy())
             for q in range(Q)]
+
+
+def multi_bounds_tc(store: "DeviceStore", refs) -> np.ndarray:
+    """muse_multi_bounds_tc: [Q, S] upper bounds of every series' score against every reference, computed as one bf16
+    contraction on the tensor cores (diagnostic)."""
+    R = np.ascontiguousarray(refs, dtype=np.float64)
+    assert R.ndim == 2
+    out = np.zeros((R.shape[0], max(store.size(), 1)), dtype=np.float32)
+    _check(lib().muse_multi_bounds_tc(store.ctx.h, store.h, _d(R), R.shape[0], R.shape[1], out.ctypes.data_as(_vp)))
+    return out[:, :store.size()]
 
 
 def xCorr(x, y, n: int, normalize: bool, ctx: Optional[Context] = None):

@@ -202,6 +202,13 @@ int  muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_
                     int32_t sign_filter, int32_t mode,
                     double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
 
+/* Diagnostic: the screening bounds of n_refs <= 256 reference queries against the whole store as ONE bf16 contraction on the
+ * tensor cores (tcgen05.mma, fp32 accumulation in TMEM; the first stage of muse_multi_run for FFT length 2048):
+ * upper[q * muse_group_size() + i] >= the score muse_batch_score_all gives series i against reference q (2.0 = undecided).
+ * What go-muse computes per reference with one Batch each (muse_batch.go:23-52, :56-93) is bounded here for all of them
+ * from one transform of every series. */
+int  muse_multi_bounds_tc(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len, float *upper);
+
 /* xCorr(x, y, n, normalize) of xcorr.go:102-153 for ANY n (the FFT kernels above exist for powers of
  * two; the reference's own KATs use n = 5): n' = max(n, x_len, y_len) (:104-106), optional z-normalisation
  * of both inputs (:108-127), LEADING zero pads (:128-129), cc[k] = sum_t xp[(t+k) mod n'] * yp[t], divided

@@ -78,13 +78,11 @@ static int run_case(int N, unsigned seed, int max_lag) {
         if (in) w_in = std::max(w_in, a); else w_out = std::max(w_out, a);
     }
     // ---- tables as the library builds them ----
-    std::vector<cf> twp((size_t)M + 64), twi(C::TWI_TOTAL);
-    fill_pass_twiddles(LOG2M, 5, twp.data(), [](long long num, long long den) {
+    std::vector<cf> twi(C::TW_TOTAL);
+    fill_big_twiddles(LOG2M, twi.data(), [](long long num, long long den) {
         return cf{(float)cosl(-2 * PI_L * num / den), (float)sinl(-2 * PI_L * num / den)};
     });
-    fill_big_inverse_twiddles(LOG2M, twi.data(), [](long long num, long long den) {
-        return cf{(float)cosl(-2 * PI_L * num / den), (float)sinl(-2 * PI_L * num / den)};
-    });
+    const std::vector<cf> &twp = twi;
     std::vector<float4> sw(M / 2), sx(M / 2);
     auto Xt = [&](int k) { return xt[k] / (2.0 * n); };
     for (int k = 0; k < M / 2; k++) {

@@ -167,9 +167,19 @@ def test_grouped_screened_run_equals_exact_run(ctx, N):
     # the point of it: far fewer fp64 scorings than series
     b.run([0], 60, 100, 0.5, mode=mb.MODE_SCREEN)
     assert b.timing().n_rescored < 0.6 * S
-    # sharded partials (F2: unfiltered group representatives) also come out of the screened path unchanged
+    # sharded partials (F2: unfiltered group representatives) out of the screened path: every group whose representative
+    # reaches the threshold is there unchanged; below it the screened path may name another member (or none) -- a member
+    # whose bound is under the threshold is never scored, and such a group fails results.go:46-52 after any merge
     pe = b.run_partial([0, 2], 60, 100, 0.5, mode=mb.MODE_EXACT)
     ps = b.run_partial([0, 2], 60, 100, 0.5, mode=mb.MODE_SCREEN)
+    np.testing.assert_array_equal(np.sort(pe[pe["score"] >= 0.5], order=["group_key"]), np.sort(ps[ps["score"] >= 0.5], order=["group_key"]))
+    assert np.all(np.isin(ps["group_key"], pe["group_key"])) and np.all(ps["score"][~np.isin(ps["series_idx"], pe["series_idx"])] < 0.5)
+    for top_n in (100, 5):
+        for x, y in zip(mb.merge_partials(pe, 60, top_n, 0.5), mb.merge_partials(ps, 60, top_n, 0.5)):
+            np.testing.assert_array_equal(x, y)
+    # threshold 0: nothing may be left out
+    pe = b.run_partial([0, 2], 60, 100, 0.0, mode=mb.MODE_EXACT)
+    ps = b.run_partial([0, 2], 60, 100, 0.0, mode=mb.MODE_SCREEN)
     np.testing.assert_array_equal(np.sort(pe, order=["group_key"]), np.sort(ps, order=["group_key"]))
 
 
