@@ -218,6 +218,8 @@ def run_c5(args, mb, torch, dist, rank, local_rank, world, mode):
             "config": {"workload": "C5: %d reference queries x %d series x %d fp64 samples, maxLag=%d, topN=%d, threshold=%g, "
                                    "ungrouped, store sharded by series over %d GPU(s)" % (Q, S_total, N, args.max_lag, top_n, args.threshold, world),
                        "queries": Q, "series_total": S_total, "series_len": N, "ms_per_query": ms / Q,
+                       "refined_pairs_per_step": mb.multi_last_stats(ctx)[0], "rescored_pairs_per_step": mb.multi_last_stats(ctx)[1],
+                       "bounds": "fp32" if os.environ.get("MUSE_MULTI_TC") == "0" else "bf16x2 tcgen05",
                        "l2": "each shard (%.2f GB) is far larger than the 126 MB L2" % ((hi - lo) * N * 8 / 1e9)},
             "clocks": clocks, "top": {"score": float(out[0][0][0]) if len(out[0][0]) else None, "n": int(len(out[0][0]))},
         }

@@ -1,4 +1,6 @@
 // kernels_exact.cu -- instantiations of score_exact_kernel (muse_exact.cuh) for every FFT length n = 2 .. 16384.
+#include <cstring>
+
 #include "muse_launch.h"
 
 namespace muse {
@@ -34,6 +36,21 @@ static cudaError_t launch_exact_m(int log2m, const ExactParams &p, cudaStream_t 
 #undef MUSE_CASE
     }
     return cudaErrorInvalidValue;
+}
+
+// n = 2048 only (the multi-query path): d_table[nq] parameter blocks in device memory, max_count = the largest count
+cudaError_t launch_exact_batch(int mode, const ExactParams *d_table, int nq, int64_t max_count, cudaStream_t st) {
+    constexpr int LOG2M = 10, LOG2P = 4;
+    using C = ExactCfg<LOG2M, LOG2P>;
+    constexpr int MINB = 512 / C::TB > 0 ? 512 / C::TB : 1;
+    ExactParams p;
+    memset(&p, 0, sizeof(p));
+    p.batch = d_table;
+    const dim3 grid((unsigned)((max_count + C::SPB - 1) / C::SPB), (unsigned)nq);
+    if (mode == MODE_SCORE) score_exact_kernel<LOG2M, LOG2P, MODE_SCORE, MINB, true><<<grid, C::TB, C::SMEM, st>>>(p);
+    else if (mode == MODE_REF) score_exact_kernel<LOG2M, LOG2P, MODE_REF, MINB, true><<<grid, C::TB, C::SMEM, st>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_exact(int mode, int log2m, const ExactParams &p, cudaStream_t st) {

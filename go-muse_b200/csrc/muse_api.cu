@@ -58,7 +58,8 @@ extern "C" const char *muse_version(void) { return "muse_b200 0.1 (sm_100a)"; }
 // cudaHostAlloc of these cost milliseconds to seconds (measured: a NewBatch + Run + destroy cycle per
 // request spent 3 s in cudaFree/cudaFreeHost once in four) while the run itself takes 2.7 ms.
 #define MUSE_MAX_LABEL_KEYS 64   // label-key columns of a store (the facade adds one all-absent column)
-#define MUSE_SCRATCH_POOL 20   // scratch sets kept per context: a multi-query launch has ScreenMultiCfg::QC batches alive at once
+#define MUSE_SCRATCH_POOL 272   // scratch sets kept per context: a multi-query launch has up to MUSE_MULTI_GROUP batches alive at once
+#define MUSE_MULTI_GROUP 256    // queries of one launch of the tensor-core multi-query path (== TcCfg::TN == RefineMultiCfg::QMAX)
 struct RunScratch {
     int64_t scratch_cap;
     double *d_score;
@@ -114,6 +115,10 @@ struct muse_ctx {
     float *tc_mid, *tc_amid;        // [S] |2Y_(M/2)| per series, [256] A_q[M/2] per query
     int64_t tc_mid_cap;
     void **tc_ptrs;                 // device: [256] sw tables, [256] bound arrays
+    unsigned *d_multi_next;         // work counter of refine_multi_kernel
+    unsigned char *d_mt, *h_mt;     // parameter tables and results of a multi-query launch (MultiTables), device and pinned host
+    int64_t mt_top_n;               // result records per query the two buffers were sized for
+    int64_t multi_refined, multi_rescored;      // totals of the last muse_multi_run (second stages, fp64 re-scorings)
     void *d_multi_q;                // query table of score_screen_multi_kernel (ScreenMultiCfg::QC entries)
     double *d_multi_refs;           // [QC][d_multi_ld] reference rows of a multi-query launch, pad columns kept zero
     int64_t d_multi_ld, d_multi_n;
@@ -213,6 +218,9 @@ extern "C" void muse_ctx_destroy(muse_ctx *c) {
     }
     cudaFree(c->tc_a); cudaFree(c->tc_b); cudaFree(c->tc_mid); cudaFree(c->tc_amid); cudaFree(c->tc_ptrs);
     cudaFree(c->d_multi_q);
+    cudaFree(c->d_multi_next);
+    cudaFree(c->d_mt);
+    if (c->h_mt) cudaFreeHost(c->h_mt);
     cudaFree(c->d_multi_refs);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -768,9 +776,23 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
 // stream has been synchronised) = the error of muse_batch.go:38-41 (the batch is destroyed) or the by-value parameters.
 // d_ref_row != NULL: the reference row is already on the device, zero-padded to the slab's row pitch (muse_multi_run
 // uploads the references of a launch with one copy).
-static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out,
-                              const double *d_ref_row = nullptr) {
-    if (!ctx || !g || !ref || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_create: NULL argument");
+extern "C" void muse_batch_destroy(muse_batch *b);
+
+// as CU, for code that owns a half-built batch `b`: it goes back to the pool before the error is returned
+#define CUB(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                              \
+            muse_batch_destroy(b);                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? MUSE_ERR_OUT_OF_MEMORY : MUSE_ERR_CUDA,  \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+
+// The batch object with its pooled scratch, the tables of its FFT length and its small allocations: nothing is launched.
+static int batch_alloc(muse_ctx *ctx, muse_group *g, int64_t ref_len, muse_batch **out) {
+    if (!ctx || !g || !out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_create: NULL argument");
     if (g->ctx != ctx) return fail(MUSE_ERR_INVALID_ARG, "group belongs to another context");
     if (ref_len != g->N)   // muse_batch.go:24-28
         return fail(MUSE_ERR_LENGTH_MISMATCH, "comparison group series (length %lld) does not have the same length as the reference (%lld)",
@@ -788,7 +810,6 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
     int l = 0;
     while ((1LL << l) < M) l++;
     b->log2m = l;
-    cudaStream_t st = ctx->stream;
     {   // scratch of an earlier batch on this context, if there is one: a set whose tables were filled for this FFT
         // length is preferred, then the largest (it fits most stores)
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -812,17 +833,34 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
         if (!b->ev[i] && cudaEventCreate(&b->ev[i]) != cudaSuccess) return bail(fail(MUSE_ERR_CUDA, "cudaEventCreate failed"));
     int rc = ensure_ref_tables(b, g->ld);
     if (rc) return bail(rc);
-    if (!b->d_flag) CU(cudaMalloc(&b->d_flag, sizeof(int32_t)));
-    if (!b->d_counters) CU(cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4));
-    if (!b->d_sel) CU(cudaMalloc(&b->d_sel, sizeof(SelectState)));
-    if (!b->d_cut) CU(cudaMalloc(&b->d_cut, sizeof(unsigned) * (4 + MUSE_CUT_WORDS)));
-    if (!b->h_pin) {
+    cudaError_t e = cudaSuccess;
+    if (!b->d_flag) e = cudaMalloc(&b->d_flag, sizeof(int32_t));
+    if (e == cudaSuccess && !b->d_counters) e = cudaMalloc(&b->d_counters, sizeof(unsigned long long) * 4);
+    if (e == cudaSuccess && !b->d_sel) e = cudaMalloc(&b->d_sel, sizeof(SelectState));
+    if (e == cudaSuccess && !b->d_cut) e = cudaMalloc(&b->d_cut, sizeof(unsigned) * (4 + MUSE_CUT_WORDS));
+    if (e == cudaSuccess && !b->h_pin) {
         b->h_pin_bytes = (size_t)4 << 20;
-        CU(cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault));
+        e = cudaHostAlloc((void **)&b->h_pin, b->h_pin_bytes, cudaHostAllocDefault);
     }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return bail(fail(e == cudaErrorMemoryAllocation ? MUSE_ERR_OUT_OF_MEMORY : MUSE_ERR_CUDA, "muse_batch_create: %s", cudaGetErrorString(e)));
+    }
+    *out = b;
+    return MUSE_OK;
+}
+
+static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out,
+                              const double *d_ref_row = nullptr) {
+    if (!ref) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_create: NULL argument");
+    muse_batch *b = nullptr;
+    int rc = batch_alloc(ctx, g, ref_len, &b);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int64_t M = b->n / 2;
     if (!d_ref_row) {      // (the select state is cleared where it is used)
-        CU(cudaMemsetAsync(b->d_ref, 0, sizeof(double) * (size_t)g->ld, st));
-        CU(cudaMemcpyAsync(b->d_ref, ref, sizeof(double) * (size_t)ref_len, cudaMemcpyHostToDevice, st));
+        CUB(cudaMemsetAsync(b->d_ref, 0, sizeof(double) * (size_t)g->ld, st));
+        CUB(cudaMemcpyAsync(b->d_ref, ref, sizeof(double) * (size_t)ref_len, cudaMemcpyHostToDevice, st));
     }
     // X on the device through the same forward path the series take
     ExactParams p;
@@ -835,18 +873,18 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
     p.twn = b->twn;
     p.out_X = b->Xt;
     p.out_flag = b->d_flag;
-    CU(launch_exact(MODE_REF, b->log2m, p, st));
+    CUB(launch_exact(MODE_REF, b->log2m, p, st));
     b->screen_ok = 0;
     const bool screen = b->tab_screen && !(b->N & 1);
     if (screen) {
         screen_tables_kernel<<<(unsigned)((M / 2 + 1 + 255) / 256), 256, 0, st>>>(b->Xt, (int)M, b->swtw, b->sw_f, b->sx_f, b->d_mid, b->d_flag);
-        CU(cudaGetLastError());
+        CUB(cudaGetLastError());
     }
     // one round trip: the std-zero flag of the reference and the two middle-bin values the kernels take by value
     int32_t *h_flag = reinterpret_cast<int32_t *>(b->h_pin);
     float *h_mid = reinterpret_cast<float *>(b->h_pin + 16);
-    if (screen) CU(cudaMemcpyAsync(h_mid, b->d_mid, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));      // [0] carries the flag
-    else CU(cudaMemcpyAsync(h_flag, b->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (screen) CUB(cudaMemcpyAsync(h_mid, b->d_mid, sizeof(float) * 4, cudaMemcpyDeviceToHost, st));      // [0] carries the flag
+    else CUB(cudaMemcpyAsync(h_flag, b->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     b->screen_ok = screen ? -1 : 0;      // -1: pending until batch_create_finish
     *out = b;
     return MUSE_OK;
@@ -868,7 +906,6 @@ static int batch_create_finish(muse_batch *b) {
     return MUSE_OK;
 }
 
-extern "C" void muse_batch_destroy(muse_batch *b);
 
 extern "C" int muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len, muse_batch **out) {
     muse_batch *b = nullptr;
@@ -1270,13 +1307,23 @@ __global__ void init_cut_kernel(unsigned *state, float cut0) {
     if (i < 4 + MUSE_CUT_WORDS) state[i] = (i == 0) ? __float_as_uint(cut0) : 0u;
 }
 
-static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t max_lag, int64_t top_n, double threshold) {
+// the same for the queries of a multi-query launch: blockIdx.y = query
+__global__ void init_cut_batch_kernel(unsigned *const *__restrict__ states, float cut0) {
+    unsigned *state = states[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 + MUSE_CUT_WORDS) state[i] = (i == 0) ? __float_as_uint(cut0) : 0u;
+}
+
+// skip_init: the cut-off state is armed by init_cut_batch_kernel for all the queries of a launch at once
+static int arm_refinement(muse_batch *b, ScreenParams &sp, float cut0, int64_t max_lag, int64_t top_n, double threshold, bool skip_init = false) {
     if (!screen_is_fused(b->log2m)) return MUSE_OK;
     int rc = refresh_row_stats(b->g);
     if (rc) return rc;
     sp.row_stat = b->g->row_stat;
-    init_cut_kernel<<<(4 + MUSE_CUT_WORDS + 255) / 256, 256, 0, bstream(b)>>>(b->d_cut, cut0);
-    CU(cudaGetLastError());
+    if (!skip_init) {
+        init_cut_kernel<<<(4 + MUSE_CUT_WORDS + 255) / 256, 256, 0, bstream(b)>>>(b->d_cut, cut0);
+        CU(cudaGetLastError());
+    }
     const int64_t n = b->n, pad = n - b->N;
     if (max_lag < 0) max_lag = -1;                          // nothing passes |lag| <= max_lag
     if (2 * max_lag >= n - 1) {                             // every lag is inside
@@ -1307,6 +1354,53 @@ __global__ void survivors_cut_kernel(const float *__restrict__ U, int64_t S, con
     if (lane == leader) base = atomicAdd(n, (unsigned long long)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (take) out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
+}
+
+// the batched tails of muse_multi_run: blockIdx.y = query (MultiTail, muse_select.cuh)
+__global__ void tail_reset_kernel(const MultiTail *__restrict__ tails, int nq) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq)
+        for (int i = 0; i < 4; i++) tails[q].counters[i] = 0ull;
+}
+__global__ void survivors_cut_batch_kernel(const MultiTail *__restrict__ tails, int64_t S) {
+    const MultiTail t = tails[blockIdx.y];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) t.counters[3] = *reinterpret_cast<const unsigned long long *>(t.cut + 2);
+    const float lo = __uint_as_float(*t.cut);
+    const bool take = i < S && t.U[i] >= lo;
+    const unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(t.counters + 2, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (take) t.list[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
+}
+// reference preparation of a launch's queries: screen_tables_kernel with blockIdx.y = query; the 4 floats of every query
+// (std-zero flag, A[M/2], Xt[M/2]) land in ONE array for one copy to the host
+struct TablesArgs {
+    const cd *Xt;
+    float4 *sw, *sx;
+    const int32_t *std_zero;
+};
+__global__ void screen_tables_batch_kernel(const TablesArgs *__restrict__ args, int M, const float2 *__restrict__ swtw, float *__restrict__ mids) {
+    const TablesArgs a = args[blockIdx.y];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > M / 2) return;
+    float *mid = mids + 4 * blockIdx.y;
+    if (k == 0) mid[0] = __int_as_float(*a.std_zero);
+    const cd x = a.Xt[k], c = a.Xt[M - k];
+    if (k == M / 2) {
+        mid[1] = __double2float_ru(hypot(x.x, x.y) * 2.0);
+        mid[2] = (float)x.x;
+        mid[3] = (float)x.y;
+        return;
+    }
+    const float wa = __double2float_ru(hypot(x.x, x.y) * (k == 0 ? 1.0 : 2.0));
+    const float wc = __double2float_ru(hypot(c.x, c.y) * (k == 0 ? 1.0 : 2.0));
+    const float2 w = swtw[k];
+    a.sw[k] = make_float4(w.x, w.y, wa, wc);
+    a.sx[k] = make_float4((float)x.x, (float)x.y, (float)c.x, (float)c.y);
 }
 
 extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t max_lag, float *upper, float *lower) {
@@ -1789,7 +1883,9 @@ extern "C" int muse_merge_partials(const muse_partial *parts, int64_t n_parts, i
 // Up to ScreenMultiCfg::QC queries in ONE pass over the slab: every batch gets its cut-off state armed, the
 // multi-query kernel fills each batch's bounds (d_U) and cut-off, and each batch is marked `prescreened` so that
 // its next fused run starts at the tail (survivors -> exact fp64 kernel -> filter -> top-N).
-static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag, int64_t top_n, double threshold) {
+static int tc_bounds_queue(muse_ctx *ctx, muse_group *g, muse_batch **bs, int nq);
+
+static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag, int64_t top_n, double threshold, bool tensor_cores) {
     cudaStream_t st = ctx->stream;
     std::vector<MultiQuery> hq((size_t)nq);
     ScreenParams sp0;
@@ -1813,10 +1909,19 @@ static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag,
     }
     // the query table lives with the context (stream-ordered reuse: copy and launch go down the same stream; a copy
     // from pageable memory has left the host buffer when the call returns), so nothing here waits for the kernel
-    if (!ctx->d_multi_q) CU(cudaMalloc(&ctx->d_multi_q, sizeof(MultiQuery) * (size_t)ScreenMultiCfg::QC));
+    if (!ctx->d_multi_q) CU(cudaMalloc(&ctx->d_multi_q, sizeof(MultiQuery) * (size_t)MUSE_MULTI_GROUP));
     MultiQuery *d_q = static_cast<MultiQuery *>(ctx->d_multi_q);
     CU(cudaMemcpyAsync(d_q, hq.data(), sizeof(MultiQuery) * (size_t)nq, cudaMemcpyHostToDevice, st));
-    CU(launch_screen_multi(sp0, d_q, nq, ctx->sm_count, st));
+    if (tensor_cores) {
+        // bounds of all queries as one bf16 contraction on the tensor cores, then ONE pass over the store for the second
+        // stages of all of them
+        int rc = tc_bounds_queue(ctx, bs[0]->g, bs, nq);
+        if (rc) return rc;
+        if (!ctx->d_multi_next) CU(cudaMalloc(&ctx->d_multi_next, sizeof(unsigned)));
+        CU(launch_refine_multi(sp0, d_q, nq, ctx->sm_count, ctx->d_multi_next, st));
+    } else {
+        CU(launch_screen_multi(sp0, d_q, nq, ctx->sm_count, st));
+    }
     for (int q = 0; q < nq; q++) bs[q]->prescreened = 1;
     return MUSE_OK;
 }
@@ -1882,6 +1987,229 @@ static bool tc_shape_ok(const muse_group *g, int64_t ref_len) {
     return ref_len == g->N && (ref_len & 1) == 0 && next_pow2(ref_len) == 2048;
 }
 
+// Layout of the per-launch tables of the tensor-core multi-query path (the same in device memory and in the pinned host
+// mirror): parameter blocks of the batched kernels, then the results that come back.
+struct MultiTables {
+    static constexpr int Q = MUSE_MULTI_GROUP;
+    static size_t off_ep() { return 0; }                                                  // ExactParams[Q]: reference spectra
+    static size_t off_ta() { return off_ep() + sizeof(ExactParams) * Q; }                 // TablesArgs[Q]
+    static size_t off_cut() { return off_ta() + sizeof(TablesArgs) * Q; }                 // unsigned*[Q]: cut-off states
+    static size_t off_tail() { return off_cut() + sizeof(void *) * Q; }                   // MultiTail[Q]
+    static size_t off_ep2() { return off_tail() + sizeof(MultiTail) * Q; }                // ExactParams[Q]: fp64 re-scoring
+    static size_t off_mids() { return off_ep2() + sizeof(ExactParams) * Q; }              // float[Q][4]
+    static size_t off_cnt() { return off_mids() + sizeof(float) * 4 * Q; }                // u64[Q][4]
+    static size_t off_recs() { return (off_cnt() + sizeof(unsigned long long) * 4 * Q + 255) / 256 * 256; }      // PartialRec[Q][top_n]
+    static size_t bytes(int64_t top_n) { return off_recs() + sizeof(PartialRec) * (size_t)Q * (size_t)std::max<int64_t>(top_n, 1); }
+};
+
+// One launch group (<= 256 references) of muse_multi_run on the tensor-core path, with ONE launch per stage for all its
+// queries: reference spectra and tables (batched fp64 kernel in MODE_REF, blockIdx.y = query), cut-off states, bounds
+// (bf16 contraction), second stages (one pass over the store), survivors, fp64 re-scoring, filter, top-N -- and two
+// round trips to the host: the std-zero flags after the preparation, the list lengths before the re-scoring.  A query
+// whose lists do not fit the device-side select finishes alone on the single-query path.
+static int multi_run_tc_group(muse_ctx *ctx, muse_group *g, const double *refs, int nq, int64_t ref_len, int64_t max_lag, int64_t top_n,
+                              double threshold, int32_t sign_filter, double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out) {
+    using MT = MultiTables;
+    const int64_t S = g->size;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->d_mt || ctx->mt_top_n < top_n) {
+        cudaFree(ctx->d_mt);
+        if (ctx->h_mt) cudaFreeHost(ctx->h_mt);
+        ctx->d_mt = ctx->h_mt = nullptr;
+        ctx->mt_top_n = 0;
+        CU(cudaMalloc(&ctx->d_mt, MT::bytes(top_n)));
+        CU(cudaHostAlloc((void **)&ctx->h_mt, MT::bytes(top_n), cudaHostAllocDefault));
+        ctx->mt_top_n = top_n;
+    }
+    unsigned char *d = ctx->d_mt, *h = ctx->h_mt;
+    if (ctx->d_multi_ld != g->ld || ctx->d_multi_n != g->N) {
+        cudaFree(ctx->d_multi_refs);
+        ctx->d_multi_refs = nullptr;
+        ctx->d_multi_ld = ctx->d_multi_n = 0;
+        CU(cudaMalloc(&ctx->d_multi_refs, sizeof(double) * (size_t)MUSE_MULTI_GROUP * (size_t)g->ld));
+        CU(cudaMemsetAsync(ctx->d_multi_refs, 0, sizeof(double) * (size_t)MUSE_MULTI_GROUP * (size_t)g->ld, st));
+        ctx->d_multi_ld = g->ld;
+        ctx->d_multi_n = g->N;
+    }
+    CU(cudaMemcpy2DAsync(ctx->d_multi_refs, sizeof(double) * (size_t)g->ld, refs, sizeof(double) * (size_t)ref_len,
+                         sizeof(double) * (size_t)ref_len, (size_t)nq, cudaMemcpyHostToDevice, st));
+    std::vector<muse_batch *> bs((size_t)nq, nullptr);
+    int rc = MUSE_OK;
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(st);
+        for (muse_batch *b : bs)
+            if (b) muse_batch_destroy(b);
+        return code;
+    };
+#define CUM(call)                                                                                                        \
+    do {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                         \
+        if (e_ != cudaSuccess) {                                                                                         \
+            (void)cudaGetLastError();                                                                                    \
+            return cleanup(fail(e_ == cudaErrorMemoryAllocation ? MUSE_ERR_OUT_OF_MEMORY : MUSE_ERR_CUDA, "%s failed: %s (%s:%d)", \
+                                #call, cudaGetErrorString(e_), __FILE__, __LINE__));                                      \
+        }                                                                                                                \
+    } while (0)
+
+    // ---- reference preparation: one launch per stage ----
+    ExactParams *h_ep = reinterpret_cast<ExactParams *>(h + MT::off_ep());
+    TablesArgs *h_ta = reinterpret_cast<TablesArgs *>(h + MT::off_ta());
+    unsigned **h_cut = reinterpret_cast<unsigned **>(h + MT::off_cut());
+    for (int i = 0; i < nq; i++) {
+        rc = batch_alloc(ctx, g, ref_len, &bs[(size_t)i]);
+        if (rc == MUSE_OK) rc = ensure_scratch(bs[(size_t)i]);
+        if (rc) return cleanup(rc);
+        muse_batch *b = bs[(size_t)i];
+        ExactParams &p = h_ep[i];
+        memset(&p, 0, sizeof(p));
+        p.slab = ctx->d_multi_refs + (size_t)i * (size_t)g->ld;
+        p.ld = g->ld;
+        p.count = 1;
+        p.N = (int)ref_len;
+        p.twM = b->twM;
+        p.twn = b->twn;
+        p.out_X = b->Xt;
+        p.out_flag = b->d_flag;
+        h_ta[i] = TablesArgs{b->Xt, b->sw_f, b->sx_f, b->d_flag};
+        h_cut[i] = b->d_cut;
+    }
+    const int64_t M = bs[0]->n / 2;
+    const float thr_lo = threshold > 0 ? (float)threshold * 0.999999f : 0.f;
+    CUM(cudaMemcpyAsync(d, h, MT::off_tail(), cudaMemcpyHostToDevice, st));
+    CUM(launch_exact_batch(MODE_REF, reinterpret_cast<const ExactParams *>(d + MT::off_ep()), nq, 1, st));
+    screen_tables_batch_kernel<<<dim3((unsigned)((M / 2 + 1 + 255) / 256), (unsigned)nq), 256, 0, st>>>(
+        reinterpret_cast<const TablesArgs *>(d + MT::off_ta()), (int)M, bs[0]->swtw, reinterpret_cast<float *>(d + MT::off_mids()));
+    init_cut_batch_kernel<<<dim3((4 + MUSE_CUT_WORDS + 255) / 256, (unsigned)nq), 256, 0, st>>>(
+        reinterpret_cast<unsigned *const *>(d + MT::off_cut()), thr_lo);
+    CUM(cudaGetLastError());
+    CUM(cudaMemcpyAsync(h + MT::off_mids(), d + MT::off_mids(), sizeof(float) * 4 * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CUM(cudaStreamSynchronize(st));
+    const float *h_mids = reinterpret_cast<const float *>(h + MT::off_mids());
+    std::vector<int> live;
+    for (int i = 0; i < nq; i++) {
+        int32_t flag;
+        memcpy(&flag, &h_mids[4 * i], sizeof(flag));
+        if (flag) {      // muse_batch.go:38-41: this query has no Batch; the others do
+            n_out[i] = -1;
+            continue;
+        }
+        muse_batch *b = bs[(size_t)i];
+        b->a_mid = h_mids[4 * i + 1];
+        b->x_mid = cf{h_mids[4 * i + 2], h_mids[4 * i + 3]};
+        b->screen_ok = 1;
+        n_out[i] = 0;
+        live.push_back(i);
+    }
+    const int nl = (int)live.size();
+    if (nl == 0) return cleanup(MUSE_OK);
+
+    // ---- bounds (tensor cores) and second stages (one pass over the store) ----
+    std::vector<muse_batch *> lb((size_t)nl);
+    std::vector<MultiQuery> hq((size_t)nl);
+    ScreenParams sp0;
+    for (int k = 0; k < nl; k++) {
+        muse_batch *b = lb[(size_t)k] = bs[(size_t)live[(size_t)k]];
+        ScreenParams sp = screen_params(b);
+        rc = arm_refinement(b, sp, thr_lo, max_lag, top_n, threshold, true);
+        if (rc) return cleanup(rc);
+        if (k == 0) sp0 = sp;
+        MultiQuery &m = hq[(size_t)k];
+        memset(&m, 0, sizeof(m));
+        m.sw = b->sw_f;
+        m.sx = b->sx_f;
+        m.x_mid = b->x_mid;
+        m.a_mid = b->a_mid;
+        m.cut = b->d_cut;
+        m.out_U = b->d_U;
+    }
+    if (!ctx->d_multi_q) CUM(cudaMalloc(&ctx->d_multi_q, sizeof(MultiQuery) * (size_t)MUSE_MULTI_GROUP));
+    if (!ctx->d_multi_next) CUM(cudaMalloc(&ctx->d_multi_next, sizeof(unsigned)));
+    MultiQuery *d_q = static_cast<MultiQuery *>(ctx->d_multi_q);
+    CUM(cudaMemcpyAsync(d_q, hq.data(), sizeof(MultiQuery) * (size_t)nl, cudaMemcpyHostToDevice, st));
+    rc = tc_bounds_queue(ctx, g, lb.data(), nl);
+    if (rc) return cleanup(rc);
+    CUM(launch_refine_multi(sp0, d_q, nl, ctx->sm_count, ctx->d_multi_next, st));
+
+    // ---- tails: survivors -> fp64 re-scoring -> filter -> top-N, one launch each ----
+    MultiTail *h_tail = reinterpret_cast<MultiTail *>(h + MT::off_tail());
+    ExactParams *h_ep2 = reinterpret_cast<ExactParams *>(h + MT::off_ep2());
+    unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(d + MT::off_cnt());
+    PartialRec *d_recs = reinterpret_cast<PartialRec *>(d + MT::off_recs());
+    const int64_t lim = std::min<int64_t>(S, MUSE_EXACT_UB);
+    for (int k = 0; k < nl; k++) {
+        muse_batch *b = lb[(size_t)k];
+        h_tail[k] = MultiTail{b->d_U, b->d_cut, b->d_list, d_cnt + 4 * k, b->d_score, b->d_lag, b->d_ckey, b->d_cidx, b->d_clag,
+                              d_recs + (size_t)k * (size_t)top_n};
+        ExactParams &p = h_ep2[k];
+        memset(&p, 0, sizeof(p));
+        p.slab = g->slab;
+        p.ld = g->ld;
+        p.count = lim;
+        p.count_ptr = d_cnt + 4 * k + 2;
+        p.idx = b->d_list;
+        p.N = (int)ref_len;
+        p.Xt = b->Xt;
+        p.twM = b->twM;
+        p.twn = b->twn;
+        p.out_score = b->d_score;
+        p.out_lag = b->d_lag;
+    }
+    CUM(cudaMemcpyAsync(d + MT::off_tail(), h + MT::off_tail(), MT::off_mids() - MT::off_tail(), cudaMemcpyHostToDevice, st));
+    const MultiTail *d_tail = reinterpret_cast<const MultiTail *>(d + MT::off_tail());
+    tail_reset_kernel<<<(nl + 255) / 256, 256, 0, st>>>(d_tail, nl);
+    survivors_cut_batch_kernel<<<dim3((unsigned)((S + 255) / 256), (unsigned)nl), 256, 0, st>>>(d_tail, S);
+    CUM(cudaGetLastError());
+    unsigned long long *h_cnt = reinterpret_cast<unsigned long long *>(h + MT::off_cnt());
+    CUM(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(unsigned long long) * 4 * (size_t)nl, cudaMemcpyDeviceToHost, st));
+    CUM(cudaStreamSynchronize(st));      // the list lengths size the next launches
+    int64_t max_len = 0;
+    for (int k = 0; k < nl; k++) max_len = std::max<int64_t>(max_len, std::min<int64_t>((int64_t)h_cnt[4 * k + 2], lim));
+    if (max_len > 0) {
+        CUM(launch_exact_batch(MODE_SCORE, reinterpret_cast<const ExactParams *>(d + MT::off_ep2()), nl, max_len, st));
+        FilterArgs f{max_lag, threshold, sign_filter, 1};
+        emit_listed_batch_kernel<<<dim3((unsigned)((max_len + 255) / 256), (unsigned)nl), 256, 0, st>>>(d_tail, (long long)lim, f);
+    }
+    partial_topn_batch_kernel<<<dim3(16, (unsigned)nl), 256, 0, st>>>(d_tail, (long long)top_n, (long long)g->global_offset, (long long)lim);
+    CUM(cudaGetLastError());
+    CUM(cudaMemcpyAsync(h + MT::off_recs(), d_recs, sizeof(PartialRec) * (size_t)nl * (size_t)top_n, cudaMemcpyDeviceToHost, st));
+    CUM(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(unsigned long long) * 4 * (size_t)nl, cudaMemcpyDeviceToHost, st));
+    CUM(cudaStreamSynchronize(st));
+    const muse_partial *h_recs = reinterpret_cast<const muse_partial *>(h + MT::off_recs());
+    for (int k = 0; k < nl; k++) {
+        const int i = live[(size_t)k];
+        const muse_partial *r = h_recs + (size_t)k * (size_t)top_n;
+        double *sc = scores + (size_t)i * (size_t)top_n;
+        int64_t *lg = lags + (size_t)i * (size_t)top_n, *ix = series_idx + (size_t)i * (size_t)top_n;
+        ctx->multi_rescored += (int64_t)h_cnt[4 * k + 2];
+        ctx->multi_refined += (int64_t)h_cnt[4 * k + 3];
+        if (r[0].flags == 2) {
+            // the list did not fit the device-side select (or the re-scoring launch): this query finishes alone, from its
+            // bounds and cut-off on the device (the fused run skips the screening of a prescreened batch)
+            muse_batch *b = lb[(size_t)k];
+            b->prescreened = 1;
+            rc = muse_batch_run_ex(b, nullptr, 0, max_lag, top_n, threshold, sign_filter, MUSE_MODE_SCREEN, 0, sc, lg, ix, n_out + i);
+            if (rc) return cleanup(rc);
+            continue;
+        }
+        int64_t c = 0;
+        for (; c < top_n && r[c].flags == 0; c++) {
+            sc[c] = r[c].score;
+            lg[c] = r[c].lag;
+            ix[c] = r[c].series_idx;
+        }
+        n_out[i] = c;
+    }
+#undef CUM
+    return cleanup(MUSE_OK);
+}
+
+extern "C" int muse_multi_last_stats(const muse_ctx *ctx, int64_t *n_refined, int64_t *n_rescored) {
+    if (!ctx || !n_refined || !n_rescored) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_last_stats: NULL argument");
+    *n_refined = ctx->multi_refined;
+    *n_rescored = ctx->multi_rescored;
+    return MUSE_OK;
+}
+
 extern "C" int muse_multi_bounds_tc(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_refs, int64_t ref_len, float *upper) {
     if (!ctx || !g || !refs || !upper) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_bounds_tc: NULL argument");
     if (n_refs < 1 || n_refs > TcCfg::TN) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_bounds_tc: 1 .. %d references", TcCfg::TN);
@@ -1923,13 +2251,24 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
     const bool one_pass = n_key_cols == 0 && mode != MUSE_MODE_EXACT && sign_filter != MUSE_SIGN_NEG && ref_len == g->N &&
                           (ref_len & 1) == 0 && next_pow2(ref_len) == 2048 && top_n > 0 && top_n <= 65536 &&
                           top_n * 4 <= g->size && (g->size >= 16384 || mode == MUSE_MODE_SCREEN) && n_refs > 1;
-    constexpr int QC = ScreenMultiCfg::QC;
+    // the bounds of a launch's queries: one bf16 contraction on the tensor cores for up to 256 queries at a time
+    // (MUSE_MULTI_TC=0: the fp32 kernel, 16 queries per pass over the store)
+    ctx->multi_refined = ctx->multi_rescored = 0;
+    const char *tc_env = getenv("MUSE_MULTI_TC");
+    const bool tensor_cores = one_pass && !(tc_env && atoi(tc_env) == 0);
+    const int QC = tensor_cores ? MUSE_MULTI_GROUP : ScreenMultiCfg::QC;
+    std::vector<muse_batch *> bs((size_t)QC), made((size_t)QC);
+    std::vector<int64_t> which((size_t)QC);
     for (int64_t q0 = 0; q0 < n_refs; q0 += QC) {
         const int nq = (int)std::min<int64_t>(QC, n_refs - q0);
-        muse_batch *bs[QC];
-        int64_t which[QC];
+        if (tensor_cores && nq > 1) {
+            int rct = multi_run_tc_group(ctx, g, refs + (size_t)q0 * (size_t)ref_len, nq, ref_len, max_lag, top_n, threshold, sign_filter,
+                                         scores + (size_t)q0 * (size_t)top_n, lags + (size_t)q0 * (size_t)top_n,
+                                         series_idx + (size_t)q0 * (size_t)top_n, n_out + q0);
+            if (rct) return rct;
+            continue;
+        }
         int live = 0, rc = MUSE_OK;
-        muse_batch *made[QC];
         int n_made = 0;
         // the references of the launch: ONE upload (rows at the slab's pitch, pad columns zero), then queued back to
         // back, ONE round trip
@@ -1937,8 +2276,8 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
             cudaFree(ctx->d_multi_refs);
             ctx->d_multi_refs = nullptr;
             ctx->d_multi_ld = ctx->d_multi_n = 0;
-            CU(cudaMalloc(&ctx->d_multi_refs, sizeof(double) * (size_t)QC * (size_t)g->ld));
-            CU(cudaMemsetAsync(ctx->d_multi_refs, 0, sizeof(double) * (size_t)QC * (size_t)g->ld, ctx->stream));
+            CU(cudaMalloc(&ctx->d_multi_refs, sizeof(double) * (size_t)MUSE_MULTI_GROUP * (size_t)g->ld));
+            CU(cudaMemsetAsync(ctx->d_multi_refs, 0, sizeof(double) * (size_t)MUSE_MULTI_GROUP * (size_t)g->ld, ctx->stream));
             ctx->d_multi_ld = g->ld;
             ctx->d_multi_n = g->N;
         }
@@ -1970,7 +2309,7 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
         }
         bool queued = false;
         if (rc == MUSE_OK && one_pass && live > 1) {
-            rc = screen_multi(ctx, bs, live, max_lag, top_n, threshold);
+            rc = screen_multi(ctx, bs.data(), live, max_lag, top_n, threshold, tensor_cores);
             // the tails of the queries are independent and small (a few thousand series each): every batch queues its
             // tail on its own stream behind the multi-query kernel, so they share the GPU instead of taking turns
             cudaEvent_t screened = nullptr;
@@ -1998,6 +2337,9 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
                 n_out[q] = 0;
                 rc = device_topn_finish(bs[i], a, scores + (size_t)q * (size_t)top_n, lags + (size_t)q * (size_t)top_n,
                                         series_idx + (size_t)q * (size_t)top_n, n_out + q);
+                const unsigned long long *h_n = reinterpret_cast<const unsigned long long *>(bs[i]->h_pin);
+                ctx->multi_rescored += (int64_t)h_n[2];
+                ctx->multi_refined += (int64_t)h_n[3];
             } else if (rc == MUSE_OK)
                 rc = muse_batch_run_ex(bs[i], key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter,
                                        bs[i]->prescreened ? MUSE_MODE_SCREEN : mode, 0,
@@ -2079,7 +2421,12 @@ struct muse_exchange {
     unsigned long long epoch;
     unsigned *d_done;
     int *d_status;
-    unsigned char *h_recs;            // pinned copy of the local records of one step
+    unsigned char *h_recs;            // pinned: the merged top_n records of one step, then the status word
+    // device-side merge of the gathered records (group max across shards, filter, top-N)
+    MergeState merge;
+    size_t merge_bytes;               // one allocation behind merge.hkeys
+    unsigned long long *d_nlocal;     // grouped runs: representatives of this shard
+    PartialRec *d_out;                // [capacity] merged top_n
 };
 
 static size_t exchange_bytes(int world, int64_t capacity) {
@@ -2105,7 +2452,30 @@ extern "C" int muse_exchange_create(muse_ctx *ctx, int32_t rank, int32_t world, 
     CU(cudaMemset(x->d_done, 0, sizeof(unsigned)));
     CU(cudaMalloc(&x->d_status, sizeof(int)));
     CU(cudaMemset(x->d_status, 0, sizeof(int)));
-    CU(cudaHostAlloc((void **)&x->h_recs, x->recs_bytes + 64, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void **)&x->h_recs, (size_t)capacity * sizeof(muse_partial) + 64, cudaHostAllocDefault));
+    {   // merge scratch: hash table of 2 x (records of all shards) slots, candidate arrays, counters, output records
+        const long long total = (long long)world * capacity;
+        long long slots = 1;
+        while (slots < 2 * total) slots <<= 1;
+        const size_t tab = sizeof(unsigned long long) * (size_t)slots;
+        const size_t bytes_m = 3 * tab + (size_t)total * (8 + 8 + 4) + 64 + (size_t)capacity * sizeof(PartialRec) + 64;
+        unsigned char *m = nullptr;
+        CU(cudaMalloc(&m, bytes_m));
+        CU(cudaMemset(m, 0, bytes_m));
+        x->merge_bytes = 3 * tab;
+        x->merge.hkeys = reinterpret_cast<unsigned long long *>(m);
+        x->merge.gmax = x->merge.hkeys + slots;
+        x->merge.gidx = x->merge.gmax + slots;
+        x->merge.slots = slots;
+        x->merge.ckey = x->merge.gidx + slots;
+        x->merge.cidx = reinterpret_cast<long long *>(x->merge.ckey + total);
+        x->merge.clag = reinterpret_cast<int32_t *>(x->merge.cidx + total);
+        unsigned char *tail = reinterpret_cast<unsigned char *>(x->merge.clag + total);
+        tail = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(tail) + 31) & ~(uintptr_t)31);
+        x->merge.counters = reinterpret_cast<unsigned long long *>(tail);
+        x->d_nlocal = x->merge.counters + 4;
+        x->d_out = reinterpret_cast<PartialRec *>(tail + 64);
+    }
     x->peer_base[rank] = x->base;
     x->opened = (world == 1);
     CU(cudaDeviceSynchronize());
@@ -2149,48 +2519,38 @@ extern "C" void muse_exchange_destroy(muse_exchange *x) {
     cudaFree(x->base);
     cudaFree(x->d_done);
     cudaFree(x->d_status);
+    cudaFree(x->merge.hkeys);
     if (x->h_recs) cudaFreeHost(x->h_recs);
     delete x;
 }
 
-// One multi-GPU step of an UNGROUPED run: scores, filter, the shard's top_n pushed into every rank's receive
-// buffer by the selection kernel itself (partial_topn_push_kernel), wait for all the peers' flags, one copy of
-// the gathered records to the host, merge.  Every rank returns the same global result.  MUSE_ERR_UNSUPPORTED
-// ("host path needed") when some shard's candidate list was too long for the device-side select: every rank
-// sees the same marker and can fall back together.
-extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t max_lag, int64_t top_n, double threshold,
-                                       int32_t sign_filter, int32_t mode, double *scores, int64_t *lags, int64_t *series_idx,
-                                       int64_t *n_out) {
+// One multi-GPU step: scores, then the shard's records stored straight into every rank's receive buffer over NVLink peer
+// memory by the kernel that produces them -- ungrouped: the filtered local top_n (partial_topn_push_kernel); grouped: every
+// group representative, unfiltered (group_records_push_kernel) --, wait for all the peers' flags, merge ON THE
+// DEVICE (group max across shards, filter, top-N) and copy only the top_n records to the host.  Every rank returns the same
+// global result.  MUSE_ERR_UNSUPPORTED ("host path needed") when a shard's list was too long for the device-side select or
+// for its slot: every rank sees the same marker and can fall back together.
+extern "C" int muse_batch_run_exchange_ex(muse_batch *b, muse_exchange *x, const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag,
+                                          int64_t top_n, double threshold, int32_t sign_filter, int32_t mode, double *scores, int64_t *lags,
+                                          int64_t *series_idx, int64_t *n_out) {
     int rc = check_batch(b);
     if (rc) return rc;
     if (!x || !n_out) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_exchange: NULL argument");
     if (x->ctx != b->ctx) return fail(MUSE_ERR_INVALID_ARG, "exchange belongs to another context");
     if (!x->opened) return fail(MUSE_ERR_INVALID_ARG, "muse_exchange_open_peers has not been called");
+    if (n_key_cols < 0 || (n_key_cols > 0 && !key_cols)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_exchange: bad key columns");
     if (top_n < 0) top_n = 0;
     if (top_n > x->capacity) return fail(MUSE_ERR_INVALID_ARG, "exchange capacity %lld < top_n %lld", (long long)x->capacity, (long long)top_n);
     if (top_n > 0 && (!scores || !lags || !series_idx)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_run_exchange: NULL output");
     CU(cudaSetDevice(b->ctx->device));
     *n_out = 0;
-    RunArgs a{nullptr, 0, max_lag, top_n, threshold, sign_filter, mode, 0};
-    a.list_only = 1;
+    const bool grouped = n_key_cols > 0;
+    RunArgs a{key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, 0};
+    a.list_only = grouped ? 0 : 1;
     rc = run_scores(b, a);
     if (rc) return rc;
     const int64_t S = b->g->size;
     cudaStream_t st = bstream(b);
-    // counters[0..1] (candidates, selected) are still zero: run_scores cleared all four and ungrouped scoring writes only [2..3]
-    if (S > 0) {
-        FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
-        Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
-        if (b->fused_run == 1) {
-            const int64_t lim = std::min<int64_t>(S, MUSE_EXACT_UB);
-            emit_listed_kernel<<<(unsigned)((lim + 255) / 256), 256, 0, st>>>(b->d_list, b->d_counters + 2, lim, b->d_score, b->d_lag, f, cand);
-        } else {
-            GroupTable gt;
-            memset(&gt, 0, sizeof(gt));
-            emit_candidates_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(gt, nullptr, b->d_score, b->d_lag, S, f, cand);
-        }
-        b->timing.n_launches++;
-    }
     x->epoch++;
     const int par = (int)(x->epoch & 1ull);
     ExchangePeers ex;
@@ -2203,16 +2563,66 @@ extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t 
     ex.rank = x->rank;
     ex.epoch = x->epoch;
     ex.done_blocks = x->d_done;
-    const long long exact_bound = b->fused_run == 1 ? (long long)std::min<int64_t>(S, MUSE_EXACT_UB) : -1;
-    const unsigned pblocks = (unsigned)std::min<int64_t>((std::max<int64_t>(S, 1) + 7) / 8, (int64_t)b->ctx->sm_count * 8);
-    partial_topn_push_kernel<<<pblocks, 256, 0, st>>>(b->d_ckey, b->d_cidx, b->d_clag, b->d_counters, (long long)top_n,
-                                                      (long long)b->g->global_offset, exact_bound, (long long)x->capacity, ex);
+    if (grouped) {
+        // group max and representative of THIS shard on the exact scores (as run_select does), then the push
+        GroupTable gt;
+        memset(&gt, 0, sizeof(gt));
+        KeyCols kc;
+        memset(&kc, 0, sizeof(kc));
+        int rank_independent = 0;
+        rc = key_bits(b->g, key_cols, n_key_cols, kc.bits, &rank_independent);
+        if (rc) return rc;
+        if (!rank_independent)
+            return fail(MUSE_ERR_UNSUPPORTED, "shards merge on group keys of at most %d bits per column (64 / %d keys)", 64 / n_key_cols, n_key_cols);
+        rc = setup_group_table(b, a, kc, gt);
+        if (rc) return rc;
+        const unsigned blocks = (unsigned)((std::max<int64_t>(S, 1) + 255) / 256);
+        if (S > 0) {
+            group_max_kernel<<<blocks, 256, 0, st>>>(gt, kc, b->d_score, S, b->d_slot);
+            group_rep_kernel<<<blocks, 256, 0, st>>>(gt, b->d_score, S, b->d_slot);
+        }
+        group_records_push_kernel<<<blocks, 256, 0, st>>>(gt, kc, b->d_slot, b->d_score, b->d_lag, (long long)S, (long long)b->g->global_offset,
+                                                          (long long)x->capacity, x->d_nlocal, ex);
+        b->timing.n_launches += 3;
+    } else {
+        // counters[0..1] (candidates, selected) are still zero: run_scores cleared all four and ungrouped scoring writes only [2..3]
+        if (S > 0) {
+            FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
+            Cand cand{b->d_ckey, b->d_cidx, b->d_clag, b->d_counters};
+            if (b->fused_run == 1) {
+                const int64_t lim = std::min<int64_t>(S, MUSE_EXACT_UB);
+                emit_listed_kernel<<<(unsigned)((lim + 255) / 256), 256, 0, st>>>(b->d_list, b->d_counters + 2, lim, b->d_score, b->d_lag, f, cand);
+            } else {
+                GroupTable gt;
+                memset(&gt, 0, sizeof(gt));
+                emit_candidates_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(gt, nullptr, b->d_score, b->d_lag, S, f, cand);
+            }
+            b->timing.n_launches++;
+        }
+        const long long exact_bound = b->fused_run == 1 ? (long long)std::min<int64_t>(S, MUSE_EXACT_UB) : -1;
+        const unsigned pblocks = (unsigned)std::min<int64_t>((std::max<int64_t>(S, 1) + 7) / 8, (int64_t)b->ctx->sm_count * 8);
+        partial_topn_push_kernel<<<pblocks, 256, 0, st>>>(b->d_ckey, b->d_cidx, b->d_clag, b->d_counters, (long long)top_n,
+                                                          (long long)b->g->global_offset, exact_bound, (long long)x->capacity, ex);
+        b->timing.n_launches++;
+    }
     // ~10 s at ~2 GHz: ranks may be a whole host->device upload apart, but a peer that never arrives must not hang the box
     exchange_wait_kernel<<<1, 32, 0, st>>>(ex.flags[x->rank], x->world, x->epoch, 20000000000ll, x->d_status);
-    b->timing.n_launches += 2;
+    // merge on the device: the hash table, candidate counter and status start from zero
+    CU(cudaMemsetAsync(x->merge.hkeys, 0, x->merge_bytes / 3 * 2, st));                       // keys and maxima
+    CU(cudaMemsetAsync(x->merge.gidx, 0xff, x->merge_bytes / 3, st));                         // representatives: +inf
+    CU(cudaMemsetAsync(x->merge.counters, 0, sizeof(unsigned long long) * 4, st));
+    const long long total = (long long)x->world * x->capacity;
+    const unsigned mblocks = (unsigned)((total + 255) / 256);
+    const PartialRec *recs_local = ex.recs[x->rank];
+    FilterArgs f{a.max_lag, a.threshold, a.sign_filter, 1};
+    merge_max_kernel<<<mblocks, 256, 0, st>>>(x->merge, recs_local, ex.flags[x->rank], x->world, (long long)x->capacity);
+    merge_rep_kernel<<<mblocks, 256, 0, st>>>(x->merge, recs_local, ex.flags[x->rank], x->world, (long long)x->capacity);
+    merge_emit_kernel<<<mblocks, 256, 0, st>>>(x->merge, recs_local, ex.flags[x->rank], x->world, (long long)x->capacity, f);
+    merged_topn_kernel<<<(unsigned)std::min<long long>((total + 7) / 8, (long long)b->ctx->sm_count * 8), 256, 0, st>>>(x->merge, (long long)top_n, x->d_out);
+    b->timing.n_launches += 5;
     CU(cudaGetLastError());
-    int *h_status = reinterpret_cast<int *>(x->h_recs + x->recs_bytes);
-    CU(cudaMemcpyAsync(x->h_recs, x->peer_base[x->rank] + (size_t)par * x->recs_bytes, x->recs_bytes, cudaMemcpyDeviceToHost, st));
+    int *h_status = reinterpret_cast<int *>(x->h_recs + (size_t)x->capacity * sizeof(muse_partial));
+    if (top_n > 0) CU(cudaMemcpyAsync(x->h_recs, x->d_out, sizeof(muse_partial) * (size_t)top_n, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_status, x->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(b->h_pin, b->d_counters, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(b->ev[3], st));
@@ -2223,11 +2633,22 @@ extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t 
         return fail(MUSE_ERR_CUDA, "muse_batch_run_exchange: a peer did not deliver its records within the time limit");
     }
     const muse_partial *recs = reinterpret_cast<const muse_partial *>(x->h_recs);
-    for (int r = 0; r < x->world; r++)
-        if (recs[(size_t)r * x->capacity].flags == 2)
-            return fail(MUSE_ERR_UNSUPPORTED, "host path needed: rank %d's candidate list was too long for the device-side select", r);
-    return muse_merge_partials(recs, (int64_t)x->world * x->capacity, max_lag, top_n, threshold, sign_filter, scores, lags,
-                               series_idx, n_out);
+    if (top_n > 0 && recs[0].flags == 2)
+        return fail(MUSE_ERR_UNSUPPORTED, "host path needed: a shard's record list was too long for the device-side select or merge");
+    int64_t k = 0;
+    for (; k < top_n && recs[k].flags == 0; k++) {
+        scores[k] = recs[k].score;
+        lags[k] = recs[k].lag;
+        series_idx[k] = recs[k].series_idx;
+    }
+    *n_out = k;
+    return MUSE_OK;
+}
+
+extern "C" int muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t max_lag, int64_t top_n, double threshold,
+                                       int32_t sign_filter, int32_t mode, double *scores, int64_t *lags, int64_t *series_idx,
+                                       int64_t *n_out) {
+    return muse_batch_run_exchange_ex(b, x, nullptr, 0, max_lag, top_n, threshold, sign_filter, mode, scores, lags, series_idx, n_out);
 }
 
 extern "C" int muse_batch_last_timing(const muse_batch *cb, muse_timing *out) {

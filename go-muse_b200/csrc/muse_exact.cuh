@@ -28,6 +28,7 @@ struct ExactParams {
     int32_t *out_lag;        // MODE_SCORE: [rows]
     cd *out_X;               // MODE_REF: Xt out (M+1)
     int32_t *out_flag;       // MODE_REF / MODE_CC: 1 when std == 0
+    const ExactParams *batch;   // BATCH instantiations: the parameters of query blockIdx.y (device memory); everything above unused
 };
 
 template <int LOG2M, int LOG2P>
@@ -115,9 +116,12 @@ __device__ __forceinline__ void fft_to_last(cd *v, cd *sm, int t, const cd *__re
     }
 }
 
-template <int LOG2M, int LOG2P, int MODE, int MINB = 1>
+// BATCH: one launch serves many queries, blockIdx.y picks the query's parameter block (muse_multi_run's reference
+// preparation and tails: one launch per stage instead of one per query)
+template <int LOG2M, int LOG2P, int MODE, int MINB = 1, bool BATCH = false>
 __global__ void __launch_bounds__(ExactCfg<LOG2M, LOG2P>::TB, MINB)
-score_exact_kernel(const ExactParams prm) {
+score_exact_kernel(const ExactParams prm0) {
+    const ExactParams prm = BATCH ? prm0.batch[blockIdx.y] : prm0;
     using G = Geo<LOG2M, LOG2P>;
     using C = ExactCfg<LOG2M, LOG2P>;
     constexpr int T = C::T, M = G::M, n = 2 * M;

@@ -14,6 +14,7 @@ namespace muse {
 
 // score_exact_kernel<log2m, ., mode> (muse_exact.cuh); log2m = log2(n/2) in 0 .. 13
 cudaError_t launch_exact(int mode, int log2m, const ExactParams &p, cudaStream_t st);
+cudaError_t launch_exact_batch(int mode, const ExactParams *d_table, int nq, int64_t max_count, cudaStream_t st);
 // points per thread of the exact kernel for each FFT size (fixes the twiddle layout of ExactParams::twM)
 inline int exact_log2p(int log2m) { return log2m < 4 ? log2m : 4; }
 
@@ -25,6 +26,8 @@ cudaError_t launch_screen_big(int log2m, const ScreenParams &p, int sm_count, cu
 // the same pass for up to ScreenMultiCfg::QC reference queries at once (n = 2048)
 cudaError_t launch_screen_multi(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st);
 
+// the second stage for up to RefineMultiCfg::QMAX queries with precomputed bounds (n = 2048)
+cudaError_t launch_refine_multi(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, unsigned *d_next, cudaStream_t st);
 // many queries' bounds as one bf16 contraction on the tensor cores (muse_bounds_tc.cuh)
 cudaError_t launch_mag_tiles(const ScreenParams &p, unsigned char *a_tiles, float *mid, int sm_count, cudaStream_t st);
 cudaError_t launch_weight_tiles(const float4 *const *d_sw, int nq, unsigned char *b_tiles, cudaStream_t st);

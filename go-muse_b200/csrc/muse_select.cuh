@@ -184,9 +184,9 @@ __global__ void emit_candidates_kernel(GroupTable gt, const int64_t *__restrict_
 
 // Emit candidates from a LIST of series (the fused path's exact list): entry i < min(*n_list, limit) is a
 // series with an exact score; the ones that pass results.go:46-52 are appended like emit_candidates_kernel does.
-__global__ void emit_listed_kernel(const int32_t *__restrict__ list, const unsigned long long *__restrict__ n_list,
-                                   long long limit, const double *__restrict__ score, const int32_t *__restrict__ lag,
-                                   FilterArgs f, Cand out) {
+__device__ __forceinline__ void emit_listed_body(const int32_t *__restrict__ list, const unsigned long long *__restrict__ n_list,
+                                                 long long limit, const double *__restrict__ score, const int32_t *__restrict__ lag,
+                                                 const FilterArgs &f, const Cand &out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long n = *n_list;
     bool emit = false;
@@ -212,6 +212,30 @@ __global__ void emit_listed_kernel(const int32_t *__restrict__ list, const unsig
     }
 }
 
+__global__ void emit_listed_kernel(const int32_t *__restrict__ list, const unsigned long long *__restrict__ n_list,
+                                   long long limit, const double *__restrict__ score, const int32_t *__restrict__ lag,
+                                   FilterArgs f, Cand out) {
+    emit_listed_body(list, n_list, limit, score, lag, f, out);
+}
+
+// Per-query pointers of the batched tails of muse_multi_run (one launch per stage, blockIdx.y = query).
+struct MultiTail {
+    const float *U;                 // [S] the query's bounds after the second stages
+    const unsigned *cut;            // the query's cut-off state ([0] final cut-off bits, [2..3] refined count)
+    int32_t *list;                  // series whose bound reaches the cut-off
+    unsigned long long *counters;   // [0] candidates, [1] selected, [2] list length, [3] refined
+    double *score;                  // [S] exact scores of the listed series
+    int32_t *lag;
+    unsigned long long *ckey;       // candidates
+    int32_t *cidx, *clag;
+    void *out;                      // PartialRec[top_n]: the query's result records
+};
+
+__global__ void emit_listed_batch_kernel(const MultiTail *__restrict__ tails, long long limit, FilterArgs f) {
+    const MultiTail t = tails[blockIdx.y];
+    emit_listed_body(t.list, t.counters + 2, limit, t.score, t.lag, f, Cand{t.ckey, t.cidx, t.clag, t.counters});
+}
+
 // ---- device-side top-N of a short candidate list, written as muse_partial records ------
 // Rank by counting: candidate i's position in the (|score| desc, index asc) order is the number of
 // candidates that come before it; those with a position < top_n write their own muse_partial
@@ -230,10 +254,9 @@ struct PartialRec {           // == muse_partial (include/muse_b200.h)
     int flags;
 };
 
-__global__ void __launch_bounds__(256)
-partial_topn_kernel(const unsigned long long *__restrict__ ckey, const int32_t *__restrict__ cidx,
-                    const int32_t *__restrict__ clag, const unsigned long long *__restrict__ counters, long long top_n,
-                    long long global_offset, long long exact_list_bound, PartialRec *__restrict__ out, long long capacity) {
+__device__ __forceinline__ void partial_topn_body(const unsigned long long *__restrict__ ckey, const int32_t *__restrict__ cidx,
+                                                  const int32_t *__restrict__ clag, const unsigned long long *__restrict__ counters, long long top_n,
+                                                  long long global_offset, long long exact_list_bound, PartialRec *__restrict__ out, long long capacity) {
     const unsigned long long n = counters[0];
     const bool overflow = n > MUSE_PARTIAL_RANK_CAP || (exact_list_bound >= 0 && counters[2] > (unsigned long long)exact_list_bound);
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,6 +295,18 @@ partial_topn_kernel(const unsigned long long *__restrict__ ckey, const int32_t *
             out[before] = PartialRec{(unsigned long long)gi, (ls & 1) ? -a : a, gi, (ls - (ls & 1)) / 2, 0};
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+partial_topn_kernel(const unsigned long long *__restrict__ ckey, const int32_t *__restrict__ cidx,
+                    const int32_t *__restrict__ clag, const unsigned long long *__restrict__ counters, long long top_n,
+                    long long global_offset, long long exact_list_bound, PartialRec *__restrict__ out, long long capacity) {
+    partial_topn_body(ckey, cidx, clag, counters, top_n, global_offset, exact_list_bound, out, capacity);
+}
+__global__ void __launch_bounds__(256)
+partial_topn_batch_kernel(const MultiTail *__restrict__ tails, long long top_n, long long global_offset, long long exact_list_bound) {
+    const MultiTail t = tails[blockIdx.y];
+    partial_topn_body(t.ckey, t.cidx, t.clag, t.counters, top_n, global_offset, exact_list_bound, static_cast<PartialRec *>(t.out), top_n);
 }
 
 // ---- the same top-N, pushed straight into every GPU's receive buffer over NVLink peer memory ------
@@ -350,7 +385,9 @@ partial_topn_push_kernel(const unsigned long long *__restrict__ ckey, const int3
     __syncthreads();
     if (!last) return;
     __threadfence_system();
-    if (threadIdx.x < ex.world) st_release_sys_u64(&ex.flags[threadIdx.x][ex.rank], ex.epoch);
+    // flag word: (epoch << 32) | records in the slot (the whole slot: it is padded), 0xffffffff = take the host path
+    const unsigned long long word = (ex.epoch << 32) | (overflow ? 0xffffffffull : (unsigned long long)capacity);
+    if (threadIdx.x < ex.world) st_release_sys_u64(&ex.flags[threadIdx.x][ex.rank], word);
     if (threadIdx.x == 0) *ex.done_blocks = 0u;
 }
 
@@ -361,7 +398,7 @@ __global__ void exchange_wait_kernel(const unsigned long long *flags, int world,
     bool ok = true;
     if (r < world) {
         const long long t0 = clock64();
-        while (ld_acquire_sys_u64(&flags[r]) < epoch) {
+        while ((ld_acquire_sys_u64(&flags[r]) >> 32) < epoch) {
             if (clock64() - t0 > timeout_cycles) {
                 ok = false;
                 break;
@@ -370,6 +407,152 @@ __global__ void exchange_wait_kernel(const unsigned long long *flags, int world,
         }
     }
     if (!ok) *status = 1;
+}
+
+// ---- grouped shards: every group representative (unfiltered) pushed to every GPU ------------------------
+// Flags carry (epoch << 32) | record count of the sender (0xffffffff: more representatives than the buffer holds).
+// One thread per series: the representative of its group (lowest index among the members holding the group max,
+// muse_batch.go:87-89) builds its muse_partial record -- the rank-independent group key included -- and stores it into
+// slot [rank] of every rank's receive buffer.
+__global__ void __launch_bounds__(256)
+group_records_push_kernel(GroupTable gt, KeyCols kc, const int64_t *__restrict__ slot_of, const double *__restrict__ score,
+                          const int32_t *__restrict__ lag, long long S, long long global_offset, long long capacity,
+                          unsigned long long *__restrict__ n_local, ExchangePeers ex) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) {
+        const double sc = score[i];
+        if (sc == sc && gt.gidx[slot_of[i]] == (int32_t)i) {
+            const unsigned long long pos = atomicAdd(n_local, 1ull);
+            if ((long long)pos < capacity) {
+                const long long gi = global_offset + i;
+                const PartialRec rec{canonical_key(kc, i), sc, gi, lag[i], 0};
+                for (int d = 0; d < ex.world; d++) ex.recs[d][(long long)ex.rank * capacity + (long long)pos] = rec;
+            }
+        }
+    }
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ex.done_blocks, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    const unsigned long long n = *n_local;
+    const unsigned long long word = (ex.epoch << 32) | (n > (unsigned long long)capacity ? 0xffffffffull : n);
+    if (threadIdx.x < ex.world) st_release_sys_u64(&ex.flags[threadIdx.x][ex.rank], word);
+    if (threadIdx.x == 0) {
+        *ex.done_blocks = 0u;
+        *n_local = 0ull;
+    }
+}
+
+// ---- merge of all shards' records on the device: group max across shards BEFORE the filter (muse_batch.go:87-89, ties ->
+// lowest global series index), filter (results.go:46-52), top-N (results.go:55-87); only top_n records go to the host ------
+struct MergeState {
+    unsigned long long *hkeys;     // [slots] group key + 1 (0 = empty)
+    unsigned long long *gmax;      // [slots] best |score| bits of the group
+    unsigned long long *gidx;      // [slots] lowest global series index among the records holding it
+    long long slots;               // power of two
+    unsigned long long *ckey;      // candidates: |score| bits
+    long long *cidx;               //             global series index
+    int32_t *clag;                 //             2 * lag + (score < 0)
+    unsigned long long *counters;  // [0] candidates, [1] status (1: some shard overflowed), [2] records seen
+};
+
+__device__ __forceinline__ long long merge_slot(const MergeState &m, unsigned long long group_key) {
+    const unsigned long long key = group_key + 1ull;
+    unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+    long long s = (long long)(h & (unsigned long long)(m.slots - 1));
+    for (;;) {
+        const unsigned long long cur = m.hkeys[s];
+        if (cur == key) return s;
+        if (cur == 0ull) {
+            const unsigned long long old = atomicCAS(&m.hkeys[s], 0ull, key);
+            if (old == 0ull || old == key) return s;
+        }
+        s = (s + 1) & (m.slots - 1);
+    }
+}
+
+// record j of shard r is live when j < the count its flag word carries
+__device__ __forceinline__ bool merge_record(const PartialRec *recs, const unsigned long long *flags, int world, long long capacity,
+                                             long long g, PartialRec &out) {
+    const long long r = g / capacity, j = g - r * capacity;
+    if (r >= world) return false;
+    const unsigned long long n = flags[r] & 0xffffffffull;
+    if (n == 0xffffffffull || (unsigned long long)j >= n) return false;
+    out = recs[g];
+    return !(out.flags & 1) && out.score == out.score;
+}
+
+__global__ void merge_max_kernel(MergeState m, const PartialRec *__restrict__ recs, const unsigned long long *__restrict__ flags, int world,
+                                 long long capacity) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < world && (flags[g] & 0xffffffffull) == 0xffffffffull) m.counters[1] = 1ull;      // a shard had more records than its slot holds
+    PartialRec p;
+    if (!merge_record(recs, flags, world, capacity, g, p)) return;
+    atomicMax(&m.gmax[merge_slot(m, p.group_key)], score_bits(p.score));
+}
+__global__ void merge_rep_kernel(MergeState m, const PartialRec *__restrict__ recs, const unsigned long long *__restrict__ flags, int world,
+                                 long long capacity) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PartialRec p;
+    if (!merge_record(recs, flags, world, capacity, g, p)) return;
+    const long long s = merge_slot(m, p.group_key);
+    if (score_bits(p.score) == m.gmax[s]) atomicMin(&m.gidx[s], (unsigned long long)p.series_idx);
+}
+__global__ void merge_emit_kernel(MergeState m, const PartialRec *__restrict__ recs, const unsigned long long *__restrict__ flags, int world,
+                                  long long capacity, FilterArgs f) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PartialRec p;
+    bool emit = merge_record(recs, flags, world, capacity, g, p);
+    if (emit) {
+        const long long s = merge_slot(m, p.group_key);
+        emit = score_bits(p.score) == m.gmax[s] && (unsigned long long)p.series_idx == m.gidx[s] && passed(f, p.score, p.lag);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, emit);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&m.counters[0], (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (emit) {
+        const unsigned long long pos = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+        m.ckey[pos] = score_bits(p.score);
+        m.cidx[pos] = p.series_idx;
+        m.clag[pos] = 2 * p.lag + (p.score < 0.0 ? 1 : 0);
+    }
+}
+// rank by counting, as partial_topn_kernel, on (|score| desc, GLOBAL series index asc); out[0 .. top_n) padded with flags = 1,
+// out[0].flags = 2 when the list is too long for this kernel or a shard overflowed (the caller takes the host path)
+__global__ void __launch_bounds__(256)
+merged_topn_kernel(MergeState m, long long top_n, PartialRec *__restrict__ out) {
+    const unsigned long long n = m.counters[0];
+    const bool overflow = n > MUSE_PARTIAL_RANK_CAP || m.counters[1] != 0ull;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long take = overflow ? 0 : ((long long)n < top_n ? (long long)n : top_n);
+    for (long long r = take + gtid; r < top_n; r += (long long)gridDim.x * blockDim.x)
+        out[r] = PartialRec{0ull, 0.0, 0ll, 0, (overflow && r == 0) ? 2 : 1};
+    if (overflow) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long i = (unsigned long long)gtid >> 5; i < n; i += nwarps) {
+        const unsigned long long k = m.ckey[i];
+        const long long ix = m.cidx[i];
+        unsigned before = 0;
+        for (unsigned long long j = lane; j < n; j += 32) {
+            const unsigned long long kj = m.ckey[j];
+            before += (kj > k || (kj == k && m.cidx[j] < ix)) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
+        if (lane == 0 && (long long)before < top_n) {
+            const int ls = m.clag[i];
+            const double a = __longlong_as_double((long long)k);
+            out[before] = PartialRec{(unsigned long long)ix, (ls & 1) ? -a : a, ix, (ls - (ls & 1)) / 2, 0};
+        }
+    }
 }
 
 // ---- radix select of the top_n candidates by (key desc, idx asc) ---------------------

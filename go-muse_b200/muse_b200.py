@@ -151,6 +151,7 @@ ABI = {
     "muse_batch_run_partial_device": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32, _vp, C.c_int64]),
     "muse_multi_run": (C.c_int, [_vp, _vp, _dp, C.c_int64, C.c_int64, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double,
                                  C.c_int32, C.c_int32, _dp, _ip64, _ip64, _ip64]),
+    "muse_multi_last_stats": (C.c_int, [_vp, _ip64, _ip64]),
     "muse_multi_bounds_tc": (C.c_int, [_vp, _vp, _dp, C.c_int64, C.c_int64, _vp]),
     "muse_xcorr": (C.c_int, [_vp, _dp, C.c_int64, _dp, C.c_int64, C.c_int64, C.c_int32, _dp, C.c_int64, _ip64, _ip64,
                              C.POINTER(C.c_double), _ip32]),
@@ -160,6 +161,8 @@ ABI = {
     "muse_exchange_destroy": (None, [_vp]),
     "muse_batch_run_exchange": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32,
                                           _dp, _ip64, _ip64, _ip64]),
+    "muse_batch_run_exchange_ex": (C.c_int, [_vp, _vp, _ip32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_int32, C.c_int32,
+                                             _dp, _ip64, _ip64, _ip64]),
     "muse_batch_partial_capacity": (C.c_int64, [_vp, _ip32, C.c_int32, C.c_int64]),
     "muse_merge_partials": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32,
                                       _dp, _ip64, _ip64, _ip64]),
@@ -435,6 +438,13 @@ def multi_run(store: "DeviceStore", refs, key_cols: Sequence[int], max_lag: int,
         return sc[:Q], lg[:Q], ix[:Q], n_out[:Q]
     return [None if n_out[q] < 0 else (sc[q, :n_out[q]].copy(), lg[q, :n_out[q]].copy(), ix[q, :n_out[q]].copy())
             for q in range(Q)]
+
+
+def multi_last_stats(ctx: Context) -> Tuple[int, int]:
+    """(second stages, fp64 re-scorings) of the context's last multi_run, summed over its queries."""
+    a, b = C.c_int64(0), C.c_int64(0)
+    _check(lib().muse_multi_last_stats(ctx.h, C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
 
 
 def multi_bounds_tc(store: "DeviceStore", refs) -> np.ndarray:
@@ -900,16 +910,19 @@ class Exchange:
         dist.barrier()
 
     def run(self, batch: DeviceBatch, max_lag: int, top_n: int, threshold: float, sign_filter: int = 0,
-            mode: int = MODE_AUTO):
+            mode: int = MODE_AUTO, key_cols: Sequence[int] = ()):
         """One multi-GPU step; returns the merged (scores, lags, series_idx) -- identical on every rank -- or None
-        when every rank must take the host path (a candidate list too long for the device-side select)."""
+        when every rank must take the host path (a record list too long for the device-side select or merge).
+        key_cols: grouped run (every group representative of the shard is exchanged; the capacity must hold them)."""
         cap = max(1, int(top_n))
         sc = np.zeros(cap)
         lg = np.zeros(cap, dtype=np.int64)
         ix = np.zeros(cap, dtype=np.int64)
         n_out = C.c_int64(0)
-        rc = lib().muse_batch_run_exchange(batch.h, self.h, max_lag, top_n, threshold, sign_filter, mode, _d(sc),
-                                           lg.ctypes.data_as(_ip64), ix.ctypes.data_as(_ip64), C.byref(n_out))
+        kc = np.asarray(list(key_cols), dtype=np.int32)
+        rc = lib().muse_batch_run_exchange_ex(batch.h, self.h, kc.ctypes.data_as(_ip32) if kc.size else None, kc.size, max_lag, top_n,
+                                              threshold, sign_filter, mode, _d(sc), lg.ctypes.data_as(_ip64),
+                                              ix.ctypes.data_as(_ip64), C.byref(n_out))
         if rc == MUSE_ERR_UNSUPPORTED:
             return None
         _check(rc)

@@ -202,6 +202,10 @@ int  muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_
                     int32_t sign_filter, int32_t mode,
                     double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
 
+/* Totals of the context's last muse_multi_run over all its queries: (series, query) pairs that took the fp32 second stage and
+ * pairs re-scored by the fp64 kernel (one-pass paths only; 0 otherwise). */
+int  muse_multi_last_stats(const muse_ctx *ctx, int64_t *n_refined, int64_t *n_rescored);
+
 /* Diagnostic: the screening bounds of n_refs <= 256 reference queries against the whole store as ONE bf16 contraction on the
  * tensor cores (tcgen05.mma, fp32 accumulation in TMEM; the first stage of muse_multi_run for FFT length 2048):
  * upper[q * muse_group_size() + i] >= the score muse_batch_score_all gives series i against reference q (2.0 = undecided).
@@ -256,6 +260,13 @@ void muse_exchange_destroy(muse_exchange *x);
 int  muse_batch_run_exchange(muse_batch *b, muse_exchange *x, int64_t max_lag, int64_t top_n, double threshold,
                              int32_t sign_filter, int32_t mode,
                              double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
+/* The same step for GROUPED runs (n_key_cols > 0; n_key_cols == 0 is muse_batch_run_exchange): every group representative of the
+ * shard, unfiltered (the filter needs the global group max, muse_batch.go:87-89 before results.go:46-52), is pushed to every
+ * rank, and the group max across shards, the filter and the top-N run on the device; only top_n records reach the host.  The
+ * exchange's capacity must hold the shard's group representatives (at most min(series, groups) of the shard). */
+int  muse_batch_run_exchange_ex(muse_batch *b, muse_exchange *x, const int32_t *key_cols, int32_t n_key_cols, int64_t max_lag,
+                                int64_t top_n, double threshold, int32_t sign_filter, int32_t mode,
+                                double *scores, int64_t *lags, int64_t *series_idx, int64_t *n_out);
 /* Upper bound on the records run_partial can emit for these arguments. */
 int64_t muse_batch_partial_capacity(muse_batch *b, const int32_t *key_cols, int32_t n_key_cols,
                                     int64_t top_n);

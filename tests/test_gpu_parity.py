@@ -460,6 +460,28 @@ def test_peer_memory_exchange_single_rank(ctx):
     ex.close()
 
 
+def test_peer_memory_exchange_grouped_single_rank(ctx):
+    # grouped runs through the exchange: every group representative of the shard is pushed (unfiltered), the
+    # group max across shards, the filter and the top-N run on the device -> with one shard it must be the plain grouped Run
+    rng = np.random.default_rng(6)
+    S, N = 12000, 480
+    ref, Y = _siggen(rng, S, N)
+    ids = np.stack([np.arange(S) // 40, np.arange(S) % 40, rng.integers(0, 3, S)], axis=1).astype(np.int32)
+    store = mb.DeviceStore(ctx, N, 3, S)
+    store.append(Y, ids)
+    b = mb.DeviceBatch(ctx, store, ref)
+    ex = mb.Exchange(ctx, 1024)
+    for cols in ([0], [1], [0, 2]):
+        for max_lag, top_n, thr in ((15, 50, 0.3), (15, 1000, 0.0), (3, 1, 0.9)):
+            want = b.run(cols, max_lag, top_n, thr)
+            got = ex.run(b, max_lag, top_n, thr, key_cols=cols)
+            assert got is not None
+            for g, w in zip(got, want):
+                np.testing.assert_array_equal(g, w)
+    assert ex.run(b, 15, 50, 0.3, key_cols=[0, 1]) is None      # 12000 groups do not fit 1024 records: the host path is asked for
+    ex.close()
+
+
 def test_peer_memory_exchange_two_gpus():
     # two ranks, one per GPU (skipped on a one-GPU box): tools/exchange_check.py compares the peer-memory push
     # with the NCCL all-gather path and the host path for several argument sets

@@ -25,6 +25,17 @@ for max_lag, top_n, thr in ((60, 100, 0.5), (15, 10, 0.0), (60, 128, 0.9), (5, 1
     ok &= bool(same)
     if rank == 0:
         print("max_lag %d top_n %d thr %g: %s (n=%d, top score %.6f)" % (max_lag, top_n, thr, "identical" if same else "MISMATCH", len(got[0]) if got else -1, got[0][0] if got and len(got[0]) else float("nan")), flush=True)
+# grouped: labels (i / 1000, i % 1000) of the GLOBAL index -> groups straddle the shards when grouped by "host"
+gex = mb.Exchange(ctx, 4096)
+for cols, max_lag, top_n, thr in (([1], 60, 100, 0.5), ([0], 60, 50, 0.0), ([1], 15, 1000, 0.2)):
+    got = gex.run(b, max_lag, top_n, thr, key_cols=cols)
+    parts = b.run_partial(cols, max_lag, top_n, thr)
+    host = mb.allgather_merge(parts, max_lag, top_n, thr, 0)
+    same = got is not None and all(np.array_equal(x, y) for x, y in zip(got, host))
+    ok &= bool(same)
+    if rank == 0:
+        print("grouped by %s max_lag %d top_n %d thr %g: %s (n=%d)" % (cols, max_lag, top_n, thr, "identical" if same else "MISMATCH", len(got[0]) if got else -1), flush=True)
+gex.close()
 def now(): torch.cuda.synchronize(); return time.perf_counter()
 for name, fn in (("peer-memory exchange", lambda: ex.run(b, 60, 100, 0.5)), ("NCCL all-gather from device memory", lambda: mb.allgather_merge_device(b, 60, 100, 0.5, 0))):
     for _ in range(3): fn()
