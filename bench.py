@@ -41,11 +41,12 @@ def workload(args):
                    args.max_lag, args.top_n, args.threshold,
                    "ungrouped" if args.ungrouped else "grouped by [graph, host] (100 series per group)"))
     else:
-        name = ("C3: %d series x %d fp64 samples per GPU, maxLag=%d, topN=%d, threshold=%g, ungrouped "
-                "(BASELINE.json configs[2])" % (args.series, args.length, args.max_lag, args.top_n, args.threshold))
+        name = ("C3: %d series x %d fp64 samples %s, maxLag=%d, topN=%d, threshold=%g, ungrouped "
+                "(BASELINE.json configs[2])" % (args.series, args.length, "per GPU" if args.scaling == "weak" else "in total (sharded)",
+                                                args.max_lag, args.top_n, args.threshold))
     return {
         "workload": name,
-        "series_per_gpu": args.series, "series_len": args.length, "fft_len": int(2 ** int(np.ceil(np.log2(args.length)))),
+        "series_per_gpu": args.series if args.scaling == "weak" else args.series // max(1, args.gpus), "series_len": args.length, "fft_len": int(2 ** int(np.ceil(np.log2(args.length)))),
         "max_lag": args.max_lag, "top_n": args.top_n, "threshold": args.threshold,
         "group_by": ["graph", "host"] if args.workload == "c4" and not args.ungrouped else None,
         "mode": args.mode,
@@ -150,8 +151,9 @@ def run_reference(args):
 
 def run_c5(args, mb, torch, dist, rank, local_rank, world, mode):
     """BASELINE.json configs[4]: Q reference queries against ONE store of --series series, sharded by series over
-    the GPUs (strong scaling).  A step = muse_multi_run on the shard (every series transformed once per 16 queries)
-    + one all-gather of the shards' per-query top-N + the per-query merge.  Not the headline line."""
+    the GPUs (strong scaling).  A step = muse_multi_run on the shard (bounds of all queries as one bf16 contraction on
+    the tensor cores, one pass over the store for the second stages, one launch per stage for the tails) + one
+    all-gather of the shards' per-query top-N + the per-query merge.  Not the headline line."""
     ctx = mb.Context(local_rank)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -197,19 +199,58 @@ def run_c5(args, mb, torch, dist, rank, local_rank, world, mode):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(0.5)
+    stage_ms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
         out = step()
+        stage_ms.append(mb.multi_last_timing(ctx))
     ev1.record(stream)
     barrier()
+    time.sleep(0.2)
     clocks = sampler.finish()
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
     if rank == 0:
+        refined, rescored = mb.multi_last_stats(ctx)
+        tc = os.environ.get("MUSE_MULTI_TC") != "0"
+        st = np.mean(np.array(stage_ms), axis=0) if stage_ms else np.zeros(4)
+        n_groups = (Q + 255) // 256
+        # the contraction of ONE launch group on this rank: three bf16 MMAs (hi x hi, hi x lo, lo x hi) of [S_shard x 1024] x [1024 x 256]
+        flops = 3 * 2.0 * (hi - lo) * min(Q, 256) * 1024
+        bf16_peak, peak_src = 1405.2, "fallback"
+        ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(ppath):
+            with open(ppath) as f:
+                pk = json.load(f)
+            bf16_peak, peak_src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1405.2))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        roofline = None
+        if tc and st[1] > 0:
+            ach = flops / (st[1] * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None,
+                        "peak_source": peak_src, "kernel": "bounds_tc_kernel (tcgen05.mma kind::f16, bf16 hi/lo split, fp32 in TMEM)",
+                        "kernel_ms": float(st[1]), "flops_per_launch": flops,
+                        "stage_ms": {"magnitudes": float(st[0]), "bounds_gemm": float(st[1]), "second_stages": float(st[2]), "tails": float(st[3])},
+                        "note": "the contraction is the tensor-core kernel of the path; the step is dominated by the fp32 second stages "
+                                "(refine_multi_kernel) of the %.1f %% of (series, query) pairs whose bound reaches their query's cut-off"
+                                % (100.0 * refined / max(1.0, float(hi - lo) * Q))}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            from oracle import c_oracle as co
+            n_rows, n_q = min(hi - lo, 16384), min(Q, 8)
+            Y = store.read_rows(0, n_rows)
+            cores = co.max_threads()
+            t0 = time.perf_counter()
+            for q in range(n_q):
+                co.batch_run(refs[q], Y, None, args.max_lag, top_n, args.threshold, 0, cores)
+            dt = time.perf_counter() - t0
+            cpu = {"value": n_q * n_rows * N / dt, "unit": "pair-samples/s", "cores": cores, "kind": "port",
+                   "sample": "%d queries x first %d series, one NewBatch + Run each (muse_batch.go:23-52, :99-130) of oracle/muse_oracle.c "
+                             "on %d threads, %.0f ms" % (n_q, n_rows, cores, dt * 1e3)}
         line = {
             "metric": "pair-samples/sec for Q reference queries against one sharded store (BASELINE.json configs[4])",
             "value": Q * S_total * N / (ms * 1e-3), "unit": "pair-samples/s", "n_gpus": world, "steps": args.steps,
@@ -218,9 +259,11 @@ def run_c5(args, mb, torch, dist, rank, local_rank, world, mode):
             "config": {"workload": "C5: %d reference queries x %d series x %d fp64 samples, maxLag=%d, topN=%d, threshold=%g, "
                                    "ungrouped, store sharded by series over %d GPU(s)" % (Q, S_total, N, args.max_lag, top_n, args.threshold, world),
                        "queries": Q, "series_total": S_total, "series_len": N, "ms_per_query": ms / Q,
-                       "refined_pairs_per_step": mb.multi_last_stats(ctx)[0], "rescored_pairs_per_step": mb.multi_last_stats(ctx)[1],
-                       "bounds": "fp32" if os.environ.get("MUSE_MULTI_TC") == "0" else "bf16x2 tcgen05",
+                       "refined_pairs_per_step": refined, "rescored_pairs_per_step": rescored,
+                       "bounds": "bf16x2 tcgen05" if tc else "fp32",
                        "l2": "each shard (%.2f GB) is far larger than the 126 MB L2" % ((hi - lo) * N * 8 / 1e9)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": None,
+            "gpu_launches": int(args.steps * n_groups * 12),
             "clocks": clocks, "top": {"score": float(out[0][0][0]) if len(out[0][0]) else None, "n": int(len(out[0][0]))},
         }
         print(json.dumps(line), flush=True)
@@ -294,11 +337,22 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)          # library kernels and NCCL deps on one stream: one event bracket
-    S, N = args.series, args.length
+    N = args.length
+    strong = args.scaling == "strong"
+    if strong:                                  # --series in total, sharded by series
+        first, S = rank * args.series // world, (rank + 1) * args.series // world - rank * args.series // world
+    else:                                       # --series per GPU (the metric's configuration)
+        first, S = rank * args.series, args.series
+    S_total = args.series if strong else world * args.series
     grouped = args.workload == "c4" and not args.ungrouped
+    variant = 1 if args.data == "rect" else 0
     store = mb.DeviceStore(ctx, N, 3 if grouped else 2, S)
-    store.append_synthetic(S, SEED, rank * S)
-    store.set_global_offset(rank * S)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    store.append_synthetic(S, SEED, first, variant)      # rows AND their row statistics (mean, 1/std): one ingest kernel
+    ctx.synchronize()
+    ingest_ms = (time.perf_counter() - t0) * 1e3
+    store.set_global_offset(first)
     cols = []
     if grouped:
         # graph = i/10000 % 1000, host = i/100 % 100, colo = i % 100 -> (graph, host) groups of 100 series
@@ -309,33 +363,32 @@ def main():
     exchange, exchange_kind = None, None
     if world > 1:
         exchange_kind = "nccl-allgather"
-        if not grouped and not args.nccl_exchange:
+        if not args.nccl_exchange:
             try:
-                exchange = mb.Exchange(ctx, max(1, args.top_n))      # all ranks succeed or all raise
-                exchange_kind = "nvlink-peer-push"
+                # ungrouped: top_n records per shard; grouped: every group representative of the shard (100 series per group here)
+                cap = max(1, args.top_n) if not grouped else max(args.top_n, S // 100 + 64)
+                exchange = mb.Exchange(ctx, cap)      # all ranks succeed or all raise
+                exchange_kind = "nvlink-peer-push + device merge"
             except mb.MuseError as e:
                 if rank == 0:
                     print("bench: %s -> NCCL all-gather" % e, file=sys.stderr)
 
     def exchange_step(b):
-        # the selection kernel stores the shard's top_n into every rank's receive buffer over NVLink peer
-        # memory and releases a flag; one call = scores, push, wait for the peers, merge (same result on every
-        # rank).  None: some shard's candidate list was too long for the device-side select -> all ranks take
-        # the NCCL all-gather path together
-        r = exchange.run(b, args.max_lag, args.top_n, args.threshold, 0, mode=mode) if exchange else None
-        if r is None:
-            # the shard's top_n stay on the device, ONE small NCCL all-gather of fixed-size records on the
-            # library's stream, one copy to the host, merge on every rank
+        # the kernel that produces the shard's records stores them into every rank's receive buffer over NVLink peer
+        # memory and releases a flag; one call = scores, push, wait for the peers, merge on the device, top_n records to
+        # the host (same result on every rank).  None: some shard's list was too long for the device-side select ->
+        # all ranks take the all-gather path together
+        r = exchange.run(b, args.max_lag, args.top_n, args.threshold, 0, mode=mode, key_cols=cols) if exchange else None
+        if r is None and grouped:
+            parts = b.run_partial(cols, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
+            r = mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0)
+        elif r is None:
             r = mb.allgather_merge_device(b, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
         return r
 
     def step():
         if world == 1:
             return batch.run(cols, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
-        if grouped:
-            # every group representative of the shard, unfiltered (F2); sizes differ per rank
-            parts = batch.run_partial(cols, args.max_lag, args.top_n, args.threshold, 0, mode=mode)
-            return mb.allgather_merge(parts, args.max_lag, args.top_n, args.threshold, 0)
         return exchange_step(batch)
 
     def barrier():
@@ -343,6 +396,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the first Run on a freshly ingested store: nothing is cached across Runs but the store's row statistics, which the
+    # ingest kernels produce with the rows -- so this "cold" figure holds no extra pass over the slab (tables, scratch
+    # allocation and module load excluded by one throw-away run on a tiny store of the same shape)
+    tiny = mb.DeviceStore(ctx, N, 3 if grouped else 2, 1024)
+    tiny.append_synthetic(1024, SEED, 0, variant)
+    if grouped:
+        tiny.set_synthetic_labels([10000, 100, 1], [1000, 100, 100])
+    tb = mb.DeviceBatch(ctx, tiny, ref)
+    tb.run(cols, args.max_lag, min(args.top_n, 100), args.threshold, 0, mode=mb.MODE_SCREEN)
+    tb.close()
+    tiny.close()
+    barrier()
+    out = step()
+    cold_run_ms = batch.timing().total_ms
     for _ in range(max(args.warmup, 3)):
         out = step()
     barrier()
@@ -363,6 +430,7 @@ def main():
         tail_ms.append(tm.total_ms - tm.score_ms)
     ev1.record(stream)
     barrier()
+    time.sleep(0.2)
     clocks = sampler.finish()
     total_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -370,7 +438,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * S * N / (ms_per_step * 1e-3)
+    value = S_total * N / (ms_per_step * 1e-3)
     used_mode = {mb.MODE_EXACT: "exact", mb.MODE_SCREEN: "screen"}.get(batch.timing().mode, "?")
 
     # ---- end to end through the C ABI with HOST buffers (pinned), H2D inside the timed region ----
@@ -379,14 +447,15 @@ def main():
         host = torch.empty((S, N), dtype=torch.float64, pin_memory=True)
         store.read_rows_ptr(0, S, host.data_ptr())          # same rows as the resident slab, now on the host
         ids = torch.zeros((S, 2), dtype=torch.int32, pin_memory=True)
-        ids[:, 0] = torch.arange(S, dtype=torch.int32) // 1000
-        ids[:, 1] = torch.arange(S, dtype=torch.int32) % 1000
+        gidx = torch.arange(first, first + S, dtype=torch.int64)
+        ids[:, 0] = (gidx // 1000).to(torch.int32)
+        ids[:, 1] = (gidx % 1000).to(torch.int32)
         st2 = mb.DeviceStore(ctx, N, 2, S)
 
         def e2e_step():
             st2.clear()
-            st2.append_host_ptr(host.data_ptr(), S, N, ids.data_ptr())     # Group.Add: H2D of the step's inputs
-            st2.set_global_offset(rank * S)
+            st2.append_host_ptr(host.data_ptr(), S, N, ids.data_ptr())     # Group.Add: H2D of the step's inputs (+ row statistics)
+            st2.set_global_offset(first)
             b2 = mb.DeviceBatch(ctx, st2, ref)                               # NewBatch
             if world == 1:
                 r = b2.run([], args.max_lag, args.top_n, args.threshold, 0, mode=mode)   # Run; results land on the host
@@ -407,8 +476,8 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": world * S * N / dt, "unit": UNIT, "h2d_bytes_per_step": int(S * N * 8 + S * 2 * 4 + N * 8),
-               "d2h_bytes_per_step": int(len(out[0]) * 24) if world == 1 else int(world * max(1, args.top_n) * 32), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+        e2e = {"value": S_total * N / dt, "unit": UNIT, "h2d_bytes_per_step": int(S * N * 8 + S * 2 * 4 + N * 8),
+               "d2h_bytes_per_step": int(len(out[0]) * 24) if world == 1 else int(max(1, args.top_n) * 32), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                "api": "muse_group_clear + muse_group_append(pinned host rows) + muse_batch_create + muse_batch_run"}
         st2.close()
         del host
@@ -420,11 +489,13 @@ def main():
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        # the ncu capture under profiles/ is of the default C3 launch: it says nothing about other shapes
-        if os.path.exists(tpath) and args.workload == "c3" and (S, N) == (1_000_000, 1440):
+        if os.path.exists(tpath):
             try:
                 with open(tpath) as f:
-                    traffic = json.load(f).get(used_mode, {}).get("dram_bytes_per_launch")
+                    tj = json.load(f)
+                key = used_mode if (args.workload, S, N) == ("c3", 1_000_000, 1440) and variant == 0 else \
+                    ("c4_grouped" if grouped else "c4_ungrouped") if (args.workload, S, N) == ("c4", 1_250_000, 10080) else None
+                traffic = tj.get(key, {}).get("dram_bytes_per_launch") if key else None
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -437,20 +508,30 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu:
             from oracle import c_oracle as co
-            n_rows = min(S, args.cpu_sample)
+            n_rows = min(S, args.cpu_sample if N <= 2048 else args.cpu_sample // 8)
             Y = store.read_rows(0, n_rows)
+            gids = (np.arange(n_rows) // 100).astype(np.int64) if grouped else None
             cores = co.max_threads()
-            v, ms = cpu_arm(args, Y, ref, 2, 1, cores)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            co.batch_run(ref, Y, gids, args.max_lag, args.top_n, args.threshold, 0, cores)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                co.batch_run(ref, Y, gids, args.max_lag, args.top_n, args.threshold, 0, cores)
+            ms = (time.perf_counter() - t0) / 2 * 1e3
+            cpu = {"value": n_rows * N / (ms * 1e-3), "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "first %d of the %d series, 2 timed passes (%.0f ms each) of oracle/muse_oracle.c on %d threads"
                              % (n_rows, S, ms, cores)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": dict(workload(args), mode_used=used_mode,
                                                 rescored_per_step=n_rescored / max(1, args.steps),
                                                 refined_per_step=n_refined / max(1, args.steps),
-                                                tail_ms=sum(tail_ms) / max(1, len(tail_ms)), exchange=exchange_kind),
+                                                tail_ms=sum(tail_ms) / max(1, len(tail_ms)), exchange=exchange_kind,
+                                                cold_run_ms=cold_run_ms, ingest_ms=ingest_ms,
+                                                row_stats="mean and 1/std of every row are produced by the ingest kernels (synthetic rows: "
+                                                          "in the generator; host / device appends: one kernel behind the copy), so no Run -- "
+                                                          "the first one included (cold_run_ms) -- holds a separate pass over the slab",
+                                                data_variant=args.data, series_total=S_total),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "top": {"score": float(out[0][0]) if len(out[0]) else None, "n": int(len(out[0]))},
         }

@@ -22,9 +22,13 @@ static cudaError_t launch_screen_big_t(const ScreenParams &p, int sm_count, cuda
     return cudaGetLastError();
 }
 
+#ifndef MUSE_BIG_MINB13
+#define MUSE_BIG_MINB13 2      // blocks of 256 threads per SM at n = 16384 (3 = an 80-register cap: measured)
+#endif
+
 cudaError_t launch_screen_big(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st) {
     switch (log2m) {
-        case 13: return launch_screen_big_t<13, 2>(p, sm_count, st);
+        case 13: return launch_screen_big_t<13, MUSE_BIG_MINB13>(p, sm_count, st);
         case 12: return launch_screen_big_t<12, 4>(p, sm_count, st);
         case 11: return launch_screen_big_t<11, 8>(p, sm_count, st);
     }

@@ -118,6 +118,7 @@ struct muse_ctx {
     unsigned *d_multi_next;         // work counter of refine_multi_kernel
     unsigned char *d_mt, *h_mt;     // parameter tables and results of a multi-query launch (MultiTables), device and pinned host
     int64_t mt_top_n;               // result records per query the two buffers were sized for
+    cudaEvent_t mt_ev[5];           // stage boundaries of the last multi-query launch group: start, magnitudes, bounds, second stages, end
     int64_t multi_refined, multi_rescored;      // totals of the last muse_multi_run (second stages, fp64 re-scorings)
     void *d_multi_q;                // query table of score_screen_multi_kernel (ScreenMultiCfg::QC entries)
     double *d_multi_refs;           // [QC][d_multi_ld] reference rows of a multi-query launch, pad columns kept zero
@@ -152,6 +153,7 @@ struct muse_batch : RunScratch {
     int fused_run;         // 1: score_fused, 2: score_fused_grouped (d_counters[2] = exact list length, [3] = refined)
     int prescreened;       // d_U and the cut-off state were filled by score_screen_multi_kernel: the next fused run starts at its tail
     int use_aux;           // queue this batch's work on its own stream (RunScratch::aux) instead of the context's
+    int signed_run;        // the current run keeps the sign of the scores (muse.go:72-76)
 };
 
 static inline cudaStream_t bstream(const muse_batch *b) { return b->use_aux ? b->aux : b->ctx->stream; }
@@ -219,6 +221,8 @@ extern "C" void muse_ctx_destroy(muse_ctx *c) {
     cudaFree(c->tc_a); cudaFree(c->tc_b); cudaFree(c->tc_mid); cudaFree(c->tc_amid); cudaFree(c->tc_ptrs);
     cudaFree(c->d_multi_q);
     cudaFree(c->d_multi_next);
+    for (int i = 0; i < 5; i++)
+        if (c->mt_ev[i]) cudaEventDestroy(c->mt_ev[i]);
     cudaFree(c->d_mt);
     if (c->h_mt) cudaFreeHost(c->h_mt);
     cudaFree(c->d_multi_refs);
@@ -527,11 +531,11 @@ extern "C" int muse_group_append_device(muse_group *g, const double *d_rows, int
 // sample) is accumulated while the samples are generated: a synthetic store never needs a pass of its own for them.
 __global__ void __launch_bounds__(256)
 synth_rows_kernel(double *slab, int64_t ld, int64_t N, int64_t row0, int64_t n_series, uint64_t seed,
-                  int64_t first_index, int32_t *lab0, int32_t *lab1, RowStat *stat) {
+                  int64_t first_index, int32_t *lab0, int32_t *lab1, RowStat *stat, int variant) {
     __shared__ double red[2][8];
     for (int64_t r = blockIdx.x; r < n_series; r += gridDim.x) {
         const int64_t gi = first_index + r;
-        const SynthSeries sp = synth_params(seed, gi, N);
+        const SynthSeries sp = synth_params(seed, gi, N, variant);
         double *row = slab + (size_t)(row0 + r) * ld;
         const double pivot = synth_value(seed, gi, sp, 0);
         double s1 = 0.0, s2 = 0.0;
@@ -560,7 +564,9 @@ synth_rows_kernel(double *slab, int64_t ld, int64_t N, int64_t row0, int64_t n_s
                 s1 += red[0][w];
                 s2 += red[1][w];
             }
-            stat[row0 + r] = make_row_stat(pivot, s1, s2, (int)N);
+            const RowStat rsr = make_row_stat(pivot, s1, s2, (int)N);
+            stat[row0 + r] = rsr;
+            if (N & 1) row[N] = rsr.mean;      // odd length: the pad column the screening kernels read with the last sample (RowStat)
             if (lab0) lab0[row0 + r] = (int32_t)(gi / 1000);
             if (lab1) lab1[row0 + r] = (int32_t)(gi % 1000);
         }
@@ -568,8 +574,13 @@ synth_rows_kernel(double *slab, int64_t ld, int64_t N, int64_t row0, int64_t n_s
     }
 }
 
+extern "C" int muse_group_append_synthetic_ex(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index, int32_t variant);
 extern "C" int muse_group_append_synthetic(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index) {
-    if (!g || n_series < 0) return fail(MUSE_ERR_INVALID_ARG, "muse_group_append_synthetic: bad argument");
+    return muse_group_append_synthetic_ex(g, n_series, seed, first_index, 0);
+}
+
+extern "C" int muse_group_append_synthetic_ex(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index, int32_t variant) {
+    if (!g || n_series < 0 || variant < 0 || variant > 1) return fail(MUSE_ERR_INVALID_ARG, "muse_group_append_synthetic: bad argument");
     if (n_series == 0) return MUSE_OK;
     if (g->size + n_series > 0x7fffffffLL) return fail(MUSE_ERR_UNSUPPORTED, "more than 2^31-1 series in one store");
     CU(cudaSetDevice(g->ctx->device));
@@ -580,7 +591,7 @@ extern "C" int muse_group_append_synthetic(muse_group *g, int64_t n_series, uint
     if (g->nkeys > 2)
         CU(cudaMemsetAsync(g->labels + (size_t)2 * g->cap, 0, sizeof(int32_t) * (size_t)g->cap * (size_t)(g->nkeys - 2), g->ctx->stream));
     const unsigned grid = (unsigned)std::min<int64_t>(n_series, (int64_t)g->ctx->sm_count * 16);
-    synth_rows_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, g->N, g->size, n_series, seed, first_index, l0, l1, g->row_stat);
+    synth_rows_kernel<<<grid, 256, 0, g->ctx->stream>>>(g->slab, g->ld, g->N, g->size, n_series, seed, first_index, l0, l1, g->row_stat, variant);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(g->ctx->stream));
     g->stats_upto = g->size + n_series;
@@ -875,7 +886,7 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
     p.out_flag = b->d_flag;
     CUB(launch_exact(MODE_REF, b->log2m, p, st));
     b->screen_ok = 0;
-    const bool screen = b->tab_screen && !(b->N & 1);
+    const bool screen = b->tab_screen != 0;
     if (screen) {
         screen_tables_kernel<<<(unsigned)((M / 2 + 1 + 255) / 256), 256, 0, st>>>(b->Xt, (int)M, b->swtw, b->sw_f, b->sx_f, b->d_mid, b->d_flag);
         CUB(cudaGetLastError());
@@ -1456,7 +1467,7 @@ static int score_fused(muse_batch *b, const RunArgs &a) {
     const unsigned blocks = (unsigned)((S + 255) / 256);
     survivors_cut_kernel<<<blocks, 256, 0, st>>>(b->d_U, S, b->d_cut, b->d_list, b->d_counters + 2);
     b->timing.n_launches++;
-    rc = score_exact_all(b, 0, b->d_list, std::min<int64_t>(S, MUSE_EXACT_UB), b->d_counters + 2);
+    rc = score_exact_all(b, b->signed_run, b->d_list, std::min<int64_t>(S, MUSE_EXACT_UB), b->d_counters + 2);
     if (rc) return rc;
     return MUSE_OK;
 }
@@ -1508,7 +1519,7 @@ static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
     CU(cudaMemcpyAsync(h_n, b->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));                                 // one small round trip: the list length sizes the launch
     const int64_t n_exact = (int64_t)h_n[0];
-    rc = score_exact_all(b, 0, b->d_list, n_exact);
+    rc = score_exact_all(b, b->signed_run, b->d_list, n_exact);
     if (rc) return rc;
     CU(cudaMemcpyAsync(b->d_counters + 3, b->d_cut + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     return MUSE_OK;
@@ -1521,10 +1532,10 @@ static int run_fused_overflow(muse_batch *b, int64_t n_exact, bool refill) {
     const int64_t S = b->g->size;
     if (refill) {
         CU(cudaMemsetAsync(b->d_score, 0xff, sizeof(double) * (size_t)S, bstream(b)));
-        return score_exact_all(b, 0, b->d_list, n_exact);
+        return score_exact_all(b, b->signed_run, b->d_list, n_exact);
     }
     if (n_exact <= std::min<int64_t>(S, MUSE_EXACT_UB)) return MUSE_OK;
-    return score_exact_all(b, 0, b->d_list + MUSE_EXACT_UB, n_exact - MUSE_EXACT_UB);
+    return score_exact_all(b, b->signed_run, b->d_list + MUSE_EXACT_UB, n_exact - MUSE_EXACT_UB);
 }
 
 static int run_scores(muse_batch *b, const RunArgs &a) {
@@ -1533,6 +1544,7 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     memset(&b->timing, 0, sizeof(b->timing));
     b->fused_run = 0;
     b->timing_pending = 0;
+    b->signed_run = a.signed_scores ? 1 : 0;
     cudaStream_t st = bstream(b);
     TIMING_EVENT(b, 0, st);
     CU(cudaMemsetAsync(b->d_counters, 0, sizeof(unsigned long long) * 4, st));
@@ -1540,8 +1552,10 @@ static int run_scores(muse_batch *b, const RunArgs &a) {
     // unsigned scores can pass, and a store big enough to be worth two extra round trips
     // grouped runs are screened only by the fused kernels (the bound of a member says nothing about the
     // lag of its group's representative; the fused second stage bounds every member's score tightly)
-    const bool can_screen = b->screen_ok && (a.n_key_cols == 0 || screen_is_fused(b->log2m)) && !a.signed_scores &&
-                            a.sign_filter != MUSE_SIGN_NEG;
+    // signed scores (Muse.Run, muse.go:72-76): the bounds are bounds on |score|, which is what the filter's threshold and the
+    // top-N rank by; the survivors are re-scored signed.  A sign filter on signed scores needs the sign, which no bound has.
+    const bool can_screen = b->screen_ok && (a.n_key_cols == 0 || screen_is_fused(b->log2m)) &&
+                            (a.signed_scores ? a.sign_filter == MUSE_SIGN_ANY : a.sign_filter != MUSE_SIGN_NEG);
     bool screen = can_screen && (a.mode == MUSE_MODE_SCREEN || (a.mode == MUSE_MODE_AUTO && b->g->size >= 16384));
     if (screen && a.n_key_cols > 0) {
         b->timing.mode = MUSE_MODE_SCREEN;
@@ -1932,6 +1946,8 @@ static int screen_multi(muse_ctx *ctx, muse_batch **bs, int nq, int64_t max_lag,
 static int tc_bounds_queue(muse_ctx *ctx, muse_group *g, muse_batch **bs, int nq) {
     const int64_t S = g->size;
     cudaStream_t st = ctx->stream;
+    for (int i = 0; i < 5; i++)
+        if (!ctx->mt_ev[i]) CU(cudaEventCreate(&ctx->mt_ev[i]));
     int rc = refresh_row_stats(g);
     if (rc) return rc;
     const size_t a_bytes = TcCfg::a_bytes(S);
@@ -1967,8 +1983,10 @@ static int tc_bounds_queue(muse_ctx *ctx, muse_group *g, muse_batch **bs, int nq
     CU(cudaMemcpyAsync(ctx->tc_ptrs, h_ptrs, sizeof(h_ptrs), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->tc_amid, h_amid, sizeof(h_amid), cudaMemcpyHostToDevice, st));
     ScreenParams sp = screen_params(bs[0]);
+    CU(cudaEventRecord(ctx->mt_ev[0], st));
     CU(launch_mag_tiles(sp, ctx->tc_a, ctx->tc_mid, ctx->sm_count, st));
     CU(launch_weight_tiles(reinterpret_cast<const float4 *const *>(ctx->tc_ptrs), nq, ctx->tc_b, st));
+    CU(cudaEventRecord(ctx->mt_ev[1], st));
     TcBoundsParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.a_tiles = ctx->tc_a;
@@ -1980,11 +1998,12 @@ static int tc_bounds_queue(muse_ctx *ctx, muse_group *g, muse_batch **bs, int nq
     tp.S = S;
     tp.nq = nq;
     CU(launch_bounds_tc(tp, st));
+    CU(cudaEventRecord(ctx->mt_ev[2], st));
     return MUSE_OK;
 }
 
 static bool tc_shape_ok(const muse_group *g, int64_t ref_len) {
-    return ref_len == g->N && (ref_len & 1) == 0 && next_pow2(ref_len) == 2048;
+    return ref_len == g->N && next_pow2(ref_len) == 2048;
 }
 
 // Layout of the per-launch tables of the tensor-core multi-query path (the same in device memory and in the pinned host
@@ -2129,6 +2148,7 @@ static int multi_run_tc_group(muse_ctx *ctx, muse_group *g, const double *refs, 
     rc = tc_bounds_queue(ctx, g, lb.data(), nl);
     if (rc) return cleanup(rc);
     CUM(launch_refine_multi(sp0, d_q, nl, ctx->sm_count, ctx->d_multi_next, st));
+    CUM(cudaEventRecord(ctx->mt_ev[3], st));
 
     // ---- tails: survivors -> fp64 re-scoring -> filter -> top-N, one launch each ----
     MultiTail *h_tail = reinterpret_cast<MultiTail *>(h + MT::off_tail());
@@ -2173,6 +2193,7 @@ static int multi_run_tc_group(muse_ctx *ctx, muse_group *g, const double *refs, 
     CUM(cudaGetLastError());
     CUM(cudaMemcpyAsync(h + MT::off_recs(), d_recs, sizeof(PartialRec) * (size_t)nl * (size_t)top_n, cudaMemcpyDeviceToHost, st));
     CUM(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(unsigned long long) * 4 * (size_t)nl, cudaMemcpyDeviceToHost, st));
+    CUM(cudaEventRecord(ctx->mt_ev[4], st));
     CUM(cudaStreamSynchronize(st));
     const muse_partial *h_recs = reinterpret_cast<const muse_partial *>(h + MT::off_recs());
     for (int k = 0; k < nl; k++) {
@@ -2207,6 +2228,18 @@ extern "C" int muse_multi_last_stats(const muse_ctx *ctx, int64_t *n_refined, in
     if (!ctx || !n_refined || !n_rescored) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_last_stats: NULL argument");
     *n_refined = ctx->multi_refined;
     *n_rescored = ctx->multi_rescored;
+    return MUSE_OK;
+}
+
+extern "C" int muse_multi_last_timing(const muse_ctx *ctx, float *ms4) {
+    if (!ctx || !ms4) return fail(MUSE_ERR_INVALID_ARG, "muse_multi_last_timing: NULL argument");
+    for (int i = 0; i < 4; i++) {
+        ms4[i] = 0.f;
+        if (ctx->mt_ev[i] && ctx->mt_ev[i + 1] && cudaEventElapsedTime(&ms4[i], ctx->mt_ev[i], ctx->mt_ev[i + 1]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ms4[i] = 0.f;
+        }
+    }
     return MUSE_OK;
 }
 
@@ -2249,7 +2282,7 @@ extern "C" int muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, 
     // ungrouped, unsigned scores, a sign filter unsigned scores can pass, a store worth screening, a device-side
     // top-N); everything else is n_refs x (NewBatch + Run) on the resident store
     const bool one_pass = n_key_cols == 0 && mode != MUSE_MODE_EXACT && sign_filter != MUSE_SIGN_NEG && ref_len == g->N &&
-                          (ref_len & 1) == 0 && next_pow2(ref_len) == 2048 && top_n > 0 && top_n <= 65536 &&
+                          next_pow2(ref_len) == 2048 && top_n > 0 && top_n <= 65536 &&
                           top_n * 4 <= g->size && (g->size >= 16384 || mode == MUSE_MODE_SCREEN) && n_refs > 1;
     // the bounds of a launch's queries: one bf16 contraction on the tensor cores for up to 256 queries at a time
     // (MUSE_MULTI_TC=0: the fp32 kernel, 16 queries per pass over the store)

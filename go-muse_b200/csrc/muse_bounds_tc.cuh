@@ -100,7 +100,7 @@ mag_tiles_kernel(const ScreenParams prm, unsigned char *__restrict__ a_tiles, fl
     const cd *rowc = reinterpret_cast<const cd *>(buf);
     cf *sm = reinterpret_cast<cf *>(buf);
     const int N = prm.N;
-    const int Nh = N >> 1;
+    const int Nh = (N + 1) >> 1;      // complex slots holding samples (odd N: the pad column of the last one holds the row's mean, RowStat)
     const unsigned bar = smem_u32(&bars[w]);
     const int partner = (P - t) & (P - 1);
     const bool lane0 = (t == 0);
@@ -108,7 +108,7 @@ mag_tiles_kernel(const ScreenParams prm, unsigned char *__restrict__ a_tiles, fl
 
     if (t == 0) {
         mbar_init(bar, 1);
-        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)N * 8u, bar);
+        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
     }
     __syncthreads();
 
@@ -140,7 +140,7 @@ mag_tiles_kernel(const ScreenParams prm, unsigned char *__restrict__ a_tiles, fl
         __syncwarp();
         if (t == 0 && next < count) {       // the exchange is over: the buffer goes back to the copy engine
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
+            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
         }
         Dft<P, float>::run(v);                          // v[Perm(j)] = Z[t + 32*j]
 

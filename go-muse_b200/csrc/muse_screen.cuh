@@ -232,10 +232,12 @@ __device__ __forceinline__ RowStat make_row_stat(double pivot, double s1, double
 }
 #endif
 
-// RowStat of rows first .. first+count-1.  One warp per row; sums are taken about the row's first sample so
+// RowStat of rows first .. first+count-1; for an odd series length the row's mean is also written into the first pad
+// column of the row (ld >= N + 1 then), so that the screening kernels, which read rows as pairs of samples, see a
+// centred value of exactly 0 there whatever the ingest left in it.  One warp per row; sums are taken about the row's first sample so
 // that the one-pass variance does not cancel (|row[0] - mean| <= sqrt(N-1) * std, so the cancellation costs at
 // most a factor N of the 1e-16).
-static __global__ void row_stats_kernel(const double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
+static __global__ void row_stats_kernel(double *__restrict__ slab, int64_t ld, int N, int64_t first, int64_t count,
                                  RowStat *__restrict__ stat) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -254,7 +256,11 @@ static __global__ void row_stats_kernel(const double *__restrict__ slab, int64_t
             s1 += __shfl_xor_sync(0xffffffffu, s1, off);
             s2 += __shfl_xor_sync(0xffffffffu, s2, off);
         }
-        if (lane == 0) stat[first + i] = make_row_stat(pivot, s1, s2, N);
+        if (lane == 0) {
+            const RowStat r = make_row_stat(pivot, s1, s2, N);
+            stat[first + i] = r;
+            if (N & 1) slab[(first + i) * ld + N] = r.mean;
+        }
     }
 }
 
@@ -271,7 +277,7 @@ struct ScreenWarpCfg {
         return (int)(w > MAX_WARPS ? MAX_WARPS : w);
     }
     static size_t smem_bytes(int N) { return (size_t)warps(N) * warp_bytes(N) + NREF * EX_BYTES; }
-    static int nz(int N) { return (N / 2 + 31) / 32; }
+    static int nz(int N) { return ((N + 1) / 2 + 31) / 32; }
 };
 
 __device__ __forceinline__ int ex_acquire(unsigned *locks, int t, int hint) {
@@ -340,7 +346,7 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
     cf *sm = reinterpret_cast<cf *>(buf);                       // forward exchange: the row buffer itself
     unsigned char *refbase = smem_raw + (size_t)(blockDim.x >> 5) * warp_bytes;
     const int N = prm.N;
-    const int Nh = N >> 1;
+    const int Nh = (N + 1) >> 1;      // complex slots holding samples (odd N: the pad column of the last one holds the row's mean, RowStat)
     const unsigned bar = smem_u32(&bars[w]);
     const int partner = (P - t) & (P - 1);
     const bool lane0 = (t == 0);
@@ -349,7 +355,7 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
     if (threadIdx.x < C::NREF) ex_locks[threadIdx.x] = 0u;
     if (t == 0) {
         mbar_init(bar, 1);
-        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)N * 8u, bar);
+        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
     }
     __syncthreads();
 
@@ -394,7 +400,9 @@ score_screen_warp_kernel(const ScreenParams prm, const unsigned warp_bytes, cons
         __syncwarp();
         if (t == 0 && next < count) {       // the exchange is over: hand the buffer to the copy engine for the next row
             asm volatile("" ::"r"(__float_as_uint(v[P - 1].y)) : "memory");
-            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
+            // the generic-proxy reads and writes of the exchange are ordered before the async-proxy write of the copy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
         }
         Dft<P, float>::run(v);                          // v[Perm(j)] = Z[t + 32*j]
 

@@ -362,9 +362,9 @@ score_screen_big_kernel(const ScreenParams prm) {
 
     const int t = threadIdx.x;
     const int N = prm.N;
-    const int Nh = N >> 1;
+    const int Nh = (N + 1) >> 1;      // complex slots holding samples (odd N: the pad column of the last one holds the row's mean, RowStat)
     const int count = (int)prm.count;
-    const unsigned row_bytes = (unsigned)N * 8u;
+    const unsigned row_bytes = (unsigned)(N + (N & 1)) * 8u;
     // contiguous range of series per block
     const int chunk = (count + (int)gridDim.x - 1) / (int)gridDim.x;
     const int pos_lo = (int)blockIdx.x * chunk;

@@ -159,9 +159,9 @@ score_screen_block_kernel(const ScreenParams prm) {
     const int pt = t + (t >> LP);                       // pad(t)
     const int pm = M + (M >> LP) - t - ((t + P - 1) >> LP);   // pad(M - t) for t >= 1 (t = 0 pairs bin 0 with itself)
     const int N = prm.N;
-    const int Nh = N >> 1;
+    const int Nh = (N + 1) >> 1;      // complex slots holding samples (odd N: the pad column of the last one holds the row's mean, RowStat)
     const int count = (int)prm.count;
-    const unsigned row_bytes = (unsigned)N * 8u;
+    const unsigned row_bytes = (unsigned)(N + (N & 1)) * 8u;
 
     for (int pos = blockIdx.x; pos < count; pos += gridDim.x) {
         const double *rowp = prm.slab + (int64_t)pos * prm.ld;

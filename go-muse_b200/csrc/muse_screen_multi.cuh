@@ -93,7 +93,7 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
     cf *sA = reinterpret_cast<cf *>(refbase + (size_t)C::NREF * C::EX_BYTES);     // [nq][512] (A[k], A[M-k])
     float *sAmid = reinterpret_cast<float *>(sA + (size_t)C::QC * (M / 2));       // [nq] A[M/2]
     const int N = prm.N;
-    const int Nh = N >> 1;
+    const int Nh = (N + 1) >> 1;      // complex slots holding samples (odd N: the pad column of the last one holds the row's mean, RowStat)
     const unsigned bar = smem_u32(&bars[w]);
     const int partner = (P - t) & (P - 1);
     const bool lane0 = (t == 0);
@@ -102,7 +102,7 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
     if (threadIdx.x < C::NREF) ex_locks[threadIdx.x] = 0u;
     if (t == 0) {
         mbar_init(bar, 1);
-        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)N * 8u, bar);
+        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
     }
     // weights of query q for the mirror pairs k = t + 32 j: the pairs of slots j = 2 j2 and 2 j2 + 1 share one 16-byte
     // entry [q][j2][t] (one LDS.128 per two packed FMAs)
@@ -315,7 +315,7 @@ score_screen_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__
         __syncwarp();
         if (t == 0 && next < count) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
+            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
         }
     }
 }
@@ -383,7 +383,7 @@ refine_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__ queri
     cf *s_tw = reinterpret_cast<cf *>(s_out + C::QMAX);                                            // pass twiddles W_1024^(j t)
     cf *s_sw = reinterpret_cast<cf *>(reinterpret_cast<unsigned char *>(s_tw) + C::TW_BYTES);      // split twiddles exp(-2 pi i k / n)
     const int N = prm.N;
-    const int Nh = N >> 1;
+    const int Nh = (N + 1) >> 1;      // complex slots holding samples (odd N: the pad column of the last one holds the row's mean, RowStat)
     const unsigned bar = smem_u32(&bars[w]);
     const int partner = (P - t) & (P - 1);
     const bool lane0 = (t == 0);
@@ -392,7 +392,7 @@ refine_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__ queri
 
     if (t == 0) {
         mbar_init(bar, 1);
-        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)N * 8u, bar);
+        if (pos0 < count) bulk_load(smem_u32(buf), prm.slab + (int64_t)pos0 * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
     }
     for (int q = threadIdx.x; q < C::QMAX; q += blockDim.x) {
         s_cut[q] = q < nq ? queries[q].cut : nullptr;
@@ -572,7 +572,7 @@ refine_multi_kernel(const ScreenParams prm, const MultiQuery *__restrict__ queri
         __syncwarp();
         if (t == 0 && next < count) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)N * 8u, bar);
+            bulk_load(smem_u32(buf), prm.slab + (int64_t)next * prm.ld, (unsigned)(N + (N & 1)) * 8u, bar);
         }
     }
 }

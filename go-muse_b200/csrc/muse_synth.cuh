@@ -44,16 +44,19 @@ struct SynthSeries {
     double slope, offset;
 };
 
-MUSE_HD SynthSeries synth_params(uint64_t seed, int64_t i, int64_t N) {
+// variant 0: the benchmark's mix (kind = i mod 3, rect widths 3 .. 20); variant 1: every series a rect of the reference's
+// width (10 samples) at a random position -- the adversarial store for the screening: nearly every score lies within the
+// slack of the top-N cut-off
+MUSE_HD SynthSeries synth_params(uint64_t seed, int64_t i, int64_t N, int variant = 0) {
     SynthSeries s;
     const uint64_t ui = (uint64_t)i;
-    s.kind = (int)(ui % 3ull);
+    s.kind = variant == 1 ? 0 : (int)(ui % 3ull);
     const uint64_t P = 0xFFFFFFFF00000000ull;   // parameter stream: t values no sample uses
     const double u0 = synth_u01(seed, ui, P + 0), u1 = synth_u01(seed, ui, P + 1), u2 = synth_u01(seed, ui, P + 2);
     s.amp = fma(39.5, u0, 0.5);                                    // U(0.5, 40)
     const int64_t half = N / 8;                                   // mid ~ N/2 +- N/8
     const int64_t mid = N / 2 - half + (int64_t)mul_rn(u1, (double)(2 * half + 1));
-    const int64_t width = 3 + (int64_t)mul_rn(u2, 18.0);               // U{3..20}
+    const int64_t width = variant == 1 ? 10 : 3 + (int64_t)mul_rn(u2, 18.0);               // U{3..20}
     s.start = mid - width / 2;
     s.end = s.start + width;
     s.slope = fma(0.02, u0, -0.01);                                 // U(-0.01, 0.01)

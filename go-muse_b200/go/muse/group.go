@@ -11,8 +11,10 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"os"
 	"runtime"
 	"sort"
+	"strconv"
 	"sync"
 	"unsafe"
 )
@@ -27,10 +29,20 @@ func lastError(rc C.int) error {
 	return fmt.Errorf("muse_b200: %s (status %d)", C.GoString(C.muse_last_error()), int(rc))
 }
 
-// deviceContext creates the process-wide context on device MUSE_DEVICE (default 0).
+// deviceContext creates the process-wide context on device MUSE_DEVICE (default 0; one process per GPU sets it to its
+// local rank).
 func deviceContext() (*C.muse_ctx, error) {
 	ctxOnce.Do(func() {
-		if rc := C.muse_ctx_create(C.int(0), &ctx); rc != C.MUSE_OK {
+		dev := 0
+		if v := os.Getenv("MUSE_DEVICE"); v != "" {
+			d, err := strconv.Atoi(v)
+			if err != nil || d < 0 {
+				ctxErr = fmt.Errorf("muse_b200: MUSE_DEVICE=%q is not a device index", v)
+				return
+			}
+			dev = d
+		}
+		if rc := C.muse_ctx_create(C.int(dev), &ctx); rc != C.MUSE_OK {
 			ctxErr = lastError(rc)
 		}
 	})
@@ -47,10 +59,15 @@ type Group struct {
 	series   []*Series
 
 	store    *C.muse_group
+	gen      uint64                    // bumped whenever the device store is replaced: a Batch bound to an older one rebinds
 	cols     []string                  // label key of each device column (the last column is all -1)
 	dict     map[string]map[string]int32
 	uploaded int
 }
+
+// uploadChunk is the number of series handed to muse_group_append per call: the library copies the rows (through its
+// pinned staging ring when they sit in pageable Go memory), so nothing larger than one chunk is ever duplicated on the host.
+const uploadChunk = 4096
 
 // NewGroup creates a new Group and initializes the timeseries label registry.
 func NewGroup(name string) *Group {
@@ -130,6 +147,7 @@ func (g *Group) syncDevice() error {
 			C.muse_group_destroy(g.store)
 			g.store = nil
 		}
+		g.gen++
 		g.cols = keys
 		g.dict = make(map[string]map[string]int32)
 		for _, k := range keys {
@@ -143,33 +161,40 @@ func (g *Group) syncDevice() error {
 	if g.uploaded == len(g.series) {
 		return nil
 	}
-	add := g.series[g.uploaded:]
 	nk := len(g.cols) + 1
-	rows := make([]float64, 0, len(add)*g.n)
-	ids := make([]int32, len(add)*nk)
-	for i, s := range add {
-		rows = append(rows, s.vals...)
-		for c := 0; c < nk; c++ {
-			ids[i*nk+c] = -1
+	rows := make([]float64, 0, uploadChunk*g.n)
+	ids := make([]int32, 0, uploadChunk*nk)
+	for g.uploaded < len(g.series) {
+		end := g.uploaded + uploadChunk
+		if end > len(g.series) {
+			end = len(g.series)
 		}
-		for c, k := range g.cols {
-			if v, ok := s.lab.Get(k); ok {
-				d := g.dict[k]
-				id, seen := d[v]
-				if !seen {
-					id = int32(len(d))
-					d[v] = id
+		rows, ids = rows[:0], ids[:0]
+		for _, s := range g.series[g.uploaded:end] {
+			rows = append(rows, s.vals...)
+			base := len(ids)
+			for c := 0; c < nk; c++ {
+				ids = append(ids, -1)
+			}
+			for c, k := range g.cols {
+				if v, ok := s.lab.Get(k); ok {
+					d := g.dict[k]
+					id, seen := d[v]
+					if !seen {
+						id = int32(len(d))
+						d[v] = id
+					}
+					ids[base+c] = id
 				}
-				ids[i*nk+c] = id
 			}
 		}
+		rc := C.muse_group_append(g.store, (*C.double)(unsafe.Pointer(&rows[0])), C.int64_t(end-g.uploaded), C.int64_t(g.n),
+			(*C.int32_t)(unsafe.Pointer(&ids[0])))
+		if rc != C.MUSE_OK {
+			return lastError(rc)
+		}
+		g.uploaded = end
 	}
-	rc := C.muse_group_append(g.store, (*C.double)(unsafe.Pointer(&rows[0])), C.int64_t(len(add)), C.int64_t(g.n),
-		(*C.int32_t)(unsafe.Pointer(&ids[0])))
-	if rc != C.MUSE_OK {
-		return lastError(rc)
-	}
-	g.uploaded = len(g.series)
 	return nil
 }
 

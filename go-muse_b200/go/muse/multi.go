@@ -12,7 +12,8 @@ import (
 
 // RunMany scores several reference series against one comparison Group in a single call: what a loop
 // of NewBatch(ref_q, comp, results_q, cc).Run(groupByLabels) computes in go-muse (muse_batch.go:23-130),
-// with the store read once for up to 16 references at a time (muse_multi_run).  results[q] receives the
+// with the store read once for up to 256 references at a time (muse_multi_run: the bounds of all of them as one
+// bf16 contraction on the tensor cores).  results[q] receives the
 // scores of refs[q]; a constant reference gets NewBatch's error in errs[q] and leaves results[q] untouched.
 // Not part of go-muse's API: the reference builds one Batch per query.
 func RunMany(refs []*Series, comp *Group, results []*Results, groupByLabels []string) (errs []error, err error) {

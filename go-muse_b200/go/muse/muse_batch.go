@@ -17,11 +17,17 @@ type Batch struct {
 	n           int
 	ref         []float64
 	batch       *C.muse_batch
-	store       *C.muse_group
+	gen         uint64 // generation of the Group's device store the C batch was created on
+	err         error  // what the last Run could not do (Run itself returns nil, as go-muse's does)
 	Comparison  *Group
 	Results     *Results
 	Concurrency int
 }
+
+// Err returns the error of the last Run, or nil.  go-muse's Run cannot fail and always returns nil
+// (muse_batch.go:99-130); this one can -- a CUDA error, a grouping the device store cannot key (more than 64 key
+// bits) -- and keeps the signature, so a failed Run is told apart from an empty result here.
+func (b *Batch) Err() error { return b.err }
 
 // NewBatch creates a new instance with a reference timeseries, a comparison group and results.
 // Errors: a comparison series of another length (muse_batch.go:24-28); a constant reference,
@@ -36,17 +42,18 @@ func NewBatch(ref *Series, comp *Group, results *Results, cc int) (*Batch, error
 		cc = 1
 	}
 	b := &Batch{ref: append([]float64(nil), ref.Values()...), Comparison: comp, Results: results, Concurrency: cc}
+	// installed before anything can create the C batch: a Batch on a group that is empty now binds lazily in Run
+	runtime.SetFinalizer(b, func(b *Batch) {
+		if b.batch != nil {
+			C.muse_batch_destroy(b.batch)
+		}
+	})
 	if len(comp.series) == 0 {
 		return b, nil
 	}
 	if err := b.bind(); err != nil {
 		return nil, err
 	}
-	runtime.SetFinalizer(b, func(b *Batch) {
-		if b.batch != nil {
-			C.muse_batch_destroy(b.batch)
-		}
-	})
 	return b, nil
 }
 
@@ -54,7 +61,7 @@ func (b *Batch) bind() error {
 	if err := b.Comparison.syncDevice(); err != nil {
 		return err
 	}
-	if b.batch != nil && b.store == b.Comparison.store {
+	if b.batch != nil && b.gen == b.Comparison.gen {
 		return nil
 	}
 	if b.batch != nil {
@@ -72,19 +79,22 @@ func (b *Batch) bind() error {
 		}
 		return lastError(rc)
 	}
-	b.store = b.Comparison.store
+	b.gen = b.Comparison.gen
 	b.n = int(C.muse_batch_fft_len(b.batch))
 	return nil
 }
 
 // Run calculates the top N graphs with the highest scores; one score per distinct combination of
-// the groupByLabels values, or per series when none are given.  Always returns nil, like go-muse.
+// the groupByLabels values, or per series when none are given.  Always returns nil, like go-muse; Err() tells
+// whether the run could be carried out.
 func (b *Batch) Run(groupByLabels []string) error {
 	comp := b.Comparison
+	b.err = nil
 	if len(comp.series) == 0 {
 		return nil
 	}
 	if err := b.bind(); err != nil {
+		b.err = err
 		return nil
 	}
 	r := b.Results
@@ -106,6 +116,7 @@ func (b *Batch) Run(groupByLabels []string) error {
 		(*C.double)(unsafe.Pointer(&scores[0])), (*C.int64_t)(unsafe.Pointer(&lags[0])),
 		(*C.int64_t)(unsafe.Pointer(&idx[0])), &nOut)
 	if rc != C.MUSE_OK {
+		b.err = lastError(rc)
 		return nil
 	}
 	// the device applied the Results filter and kept the TopN best; pushing those through

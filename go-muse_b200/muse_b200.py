@@ -127,6 +127,8 @@ ABI = {
     "muse_group_append": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp]),
     "muse_group_append_device": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp]),
     "muse_group_append_synthetic": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int64]),
+    "muse_group_append_synthetic_ex": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.c_int64, C.c_int32]),
+    "muse_multi_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "muse_group_set_synthetic_labels": (C.c_int, [_vp, _ip64, _ip64]),
     "muse_synth_row": (None, [C.c_uint64, C.c_int64, C.c_int64, _dp]),
     "muse_synth_reference": (None, [C.c_uint64, C.c_int64, _dp]),
@@ -261,8 +263,8 @@ class DeviceStore:
         _check(lib().muse_group_append_device(self.h, _vp(d_rows_ptr), n_series, series_len,
                                               _vp(d_ids_ptr) if d_ids_ptr else None))
 
-    def append_synthetic(self, n_series: int, seed: int, first_index: int):
-        _check(lib().muse_group_append_synthetic(self.h, n_series, seed, first_index))
+    def append_synthetic(self, n_series: int, seed: int, first_index: int, variant: int = 0):
+        _check(lib().muse_group_append_synthetic_ex(self.h, n_series, seed, first_index, variant))
 
     def set_synthetic_labels(self, div: Sequence[int], mod: Sequence[int]):
         """label id of key k for global series index i = (i / div[k]) % mod[k] (call after set_global_offset)."""
@@ -445,6 +447,13 @@ def multi_last_stats(ctx: Context) -> Tuple[int, int]:
     a, b = C.c_int64(0), C.c_int64(0)
     _check(lib().muse_multi_last_stats(ctx.h, C.byref(a), C.byref(b)))
     return int(a.value), int(b.value)
+
+
+def multi_last_timing(ctx: Context) -> Tuple[float, float, float, float]:
+    """Device ms of the last launch group of the tensor-core multi-query path: (magnitudes, bounds GEMM, second stages, tails)."""
+    ms = (C.c_float * 4)()
+    _check(lib().muse_multi_last_timing(ctx.h, ms))
+    return tuple(float(x) for x in ms)
 
 
 def multi_bounds_tc(store: "DeviceStore", refs) -> np.ndarray:

@@ -35,7 +35,7 @@ extern "C" {
 #define MUSE_ERR_LENGTH_MISMATCH 3  /* muse_batch.go:24-28, group.go:45-51 */
 #define MUSE_ERR_STDDEV_ZERO     4  /* muse_batch.go:38-41 "Invalid input query" */
 #define MUSE_ERR_NO_DEVICE       5
-#define MUSE_ERR_UNSUPPORTED     6  /* e.g. nextPowOf2(len) > MUSE_MAX_FFT_LEN */
+#define MUSE_ERR_UNSUPPORTED     6  /* e.g. nextPowOf2(len) > MUSE_MAX_FFT_LEN, group-by keys that need more than 64 key bits */
 #define MUSE_ERR_OUT_OF_MEMORY   7
 
 #define MUSE_MAX_FFT_LEN 16384      /* n = nextPowOf2(series length), xcorr.go:19-24 */
@@ -104,8 +104,11 @@ void muse_group_destroy(muse_group *g);
 /* Group.Add (group.go:31-56): append n_series rows (row-major [n_series][series_len]
  * fp64, HOST memory) and their label ids ([n_series][n_label_keys], may be NULL
  * when n_label_keys == 0).  series_len must equal the group's (group.go:45-51 ->
- * MUSE_ERR_LENGTH_MISMATCH).  The copy is staged through pinned memory and is
- * complete when the call returns. */
+ * MUSE_ERR_LENGTH_MISMATCH).  Rows in page-locked memory (muse_host_alloc, cudaHostRegister) are copied by one DMA; rows in
+ * pageable memory (a Go slice, a numpy array) go through the context's ring of three pinned 64 MB buffers, filled by several
+ * host threads (MUSE_STAGE_THREADS, default min(cores, 12)) while the previous chunk is on the wire.  The row statistics of the
+ * new rows (mean, 1/std: the z-normalisation of xcorr.go:84-95, once per row instead of once per Run) are computed by a kernel
+ * queued behind the copy.  Everything is complete when the call returns. */
 int  muse_group_append(muse_group *g, const double *rows, int64_t n_series, int64_t series_len,
                        const int32_t *label_ids);
 
@@ -120,6 +123,9 @@ int  muse_group_append_device(muse_group *g, const double *d_rows, int64_t n_ser
  * Label ids: key 0 = i / 1000 ("graph"), key 1 = i % 1000 ("host") when the group has
  * >= 2 label keys. */
 int  muse_group_append_synthetic(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index);
+/* variant 0: the mix above; variant 1: every series a rect of the reference's width (10 samples) at a random position -- the
+ * adversarial store for the screening (nearly every score within the slack of the top-N cut-off). */
+int  muse_group_append_synthetic_ex(muse_group *g, int64_t n_series, uint64_t seed, int64_t first_index, int32_t variant);
 /* Replace the label ids of every series in the store by the synthetic scheme
  * id(key k, global index i) = (i / div[k]) % mod[k], i = global offset + local index (benchmarks:
  * SURVEY section 8d config C4 = {graph: i/10000 % 1000, host: i/100 % 100, colo: i % 100}). */
@@ -150,7 +156,9 @@ int64_t muse_batch_fft_len(const muse_batch *b);     /* Batch.n */
 /* Batch.Run + Results filter/top-N for one Run on a fresh Results
  * (muse_batch.go:99-130, results.go:46-87).
  *   key_cols[n_key_cols]: label-key columns to group by (Group.indexLabelValues,
- *       group.go:76-104); n_key_cols == 0: every series is its own group.
+ *       group.go:76-104); n_key_cols == 0: every series is its own group.  Up to 16
+ *       columns whose cardinalities fit 64 key bits together (else MUSE_ERR_UNSUPPORTED);
+ *       a store holds up to 64 label-key columns.
  *   per group the member with the highest min(|peak|,1) is kept BEFORE the filter
  *   (muse_batch.go:87-89, lowest series index wins ties), then |lag| <= max_lag,
  *   score >= threshold and the sign filter are applied (results.go:46-52) and the
@@ -178,7 +186,7 @@ int  muse_batch_score_all(muse_batch *b, int32_t signed_scores, double *scores, 
 
 /* Diagnostic: the fp32 screening pass alone.  upper[i] >= series i's score from
  * muse_batch_score_all (a value > 1, e.g. 2.0, means "undecided: ask the fp64 kernel").
- * refine != 0 (FFT length 2048 only) sends EVERY series through the fused second stage
+ * refine != 0 (FFT lengths 512 .. 16384) sends EVERY series through the fused second stage
  * (fp32 inverse transform) for the lag window max_lag: upper[i] = -1 when the peak is
  * certainly outside the window (the series fails results.go:46-48), else a tight bound;
  * lower[i] >= 0 is a certain lower bound on the score of a series whose lag is certainly
@@ -205,6 +213,10 @@ int  muse_multi_run(muse_ctx *ctx, muse_group *g, const double *refs, int64_t n_
 /* Totals of the context's last muse_multi_run over all its queries: (series, query) pairs that took the fp32 second stage and
  * pairs re-scored by the fp64 kernel (one-pass paths only; 0 otherwise). */
 int  muse_multi_last_stats(const muse_ctx *ctx, int64_t *n_refined, int64_t *n_rescored);
+
+/* Device times (ms) of the last launch group of the tensor-core multi-query path: [0] magnitudes of the store, [1] the bounds
+ * contraction (tcgen05), [2] the second stages, [3] the tails (survivors, fp64 re-scoring, filter, top-N). */
+int  muse_multi_last_timing(const muse_ctx *ctx, float *ms4);
 
 /* Diagnostic: the screening bounds of n_refs <= 256 reference queries against the whole store as ONE bf16 contraction on the
  * tensor cores (tcgen05.mma, fp32 accumulation in TMEM; the first stage of muse_multi_run for FFT length 2048):

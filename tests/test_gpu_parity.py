@@ -1,4 +1,6 @@
 """Parity of the CUDA path (through the C ABI) with the oracle.  Needs a B200."""
+import os
+
 import numpy as np
 import pytest
 
@@ -437,6 +439,35 @@ def test_c_oracle_agrees_at_larger_size(ctx):
         _, _, ties = mo.score_series_batch(ref, Y[i:i + 1], want_ties=True)
         assert lg[i] in ties[0]
     assert bad.size <= 50
+
+
+def test_pageable_rows_are_staged_through_the_pinned_ring(ctx):
+    """muse_group_append from PAGEABLE host memory (a numpy array, a Go slice): chunks go through the context's ring of pinned
+    buffers, filled by several host threads while the previous chunk is on the wire.  Rows must arrive intact (also at a
+    pitch that needs a 2-D copy), and the rate must be that of a staged copy, not of a single-threaded bounce buffer."""
+    import time
+    rng = np.random.default_rng(8)
+    S, N = 150_000, 1440
+    Y = rng.standard_normal((S, N))                      # 1.7 GB, pageable
+    store = mb.DeviceStore(ctx, N, 0, S)
+    store.append(Y[:1000])                               # warm: ring allocation, thread start-up
+    store.clear()
+    t0 = time.perf_counter()
+    store.append(Y)
+    dt = time.perf_counter() - t0
+    gbs = Y.nbytes / dt / 1e9
+    print("pageable append: %.1f GB/s (%d threads available)" % (gbs, os.cpu_count()))
+    for i in (0, 1, 4095, 4096, 77_777, S - 1):
+        np.testing.assert_array_equal(store.read_row(i), Y[i])
+    assert gbs >= 10.0
+    store.close()
+    N2 = 1001                                            # odd length: pitched rows, pad column
+    Z = rng.standard_normal((70_000, N2))
+    st2 = mb.DeviceStore(ctx, N2, 0, 70_000)
+    st2.append(Z)
+    for i in (0, 8190, 69_999):
+        np.testing.assert_array_equal(st2.read_row(i), Z[i])
+    st2.close()
 
 
 def test_peer_memory_exchange_single_rank(ctx):

@@ -50,7 +50,8 @@ def _adversarial(rng, S, N):
     return Y
 
 
-@pytest.mark.parametrize("N", [1440, 1030, 2048, 480, 300, 700, 1000, 1024, 2500, 4096, 6000, 10080])
+@pytest.mark.parametrize("N", [1440, 1030, 2048, 480, 300, 700, 1000, 1024, 2500, 4096, 6000, 10080,
+                               1441, 1027, 2047, 481, 999, 2049, 4097, 10081, 16383])
 def test_screened_run_equals_exact_run(ctx, N):
     rng = np.random.default_rng(N)
     S = 30000 if N <= 2048 else 6000
@@ -76,6 +77,33 @@ def test_screened_run_equals_exact_run(ctx, N):
     same = ix == wix
     assert same.mean() > 0.9    # identical rows (k == 6) tie exactly; order among ties may differ from the oracle's
     assert set(ix[~same]) == set(wix[~same])
+
+
+@pytest.mark.parametrize("N", [1440, 1441, 480, 10080])
+def test_signed_screened_run_equals_exact_run(ctx, N):
+    """Signed scores (Muse.Run, muse.go:72-76: the sign is kept, clamp to [-1, 1], ranking by |score|) through the
+    screening: the bounds hold for |score|, the survivors are re-scored signed -> the all-exact signed run, bit for bit."""
+    rng = np.random.default_rng(7 * N)
+    S = 30000 if N <= 2048 else 6000
+    Y = _adversarial(rng, S, N)
+    Y[::2] *= -1.0                                   # half of the pulses point down: negative peaks
+    ref = np.zeros(N)
+    ref[N // 2 - 5:N // 2 + 5] = 1.5
+    ref += 0.1 * (rng.random(N) - 0.5)
+    store = mb.DeviceStore(ctx, N, 1, S)
+    store.append(Y, (np.arange(S) // 25).astype(np.int32)[:, None])
+    b = mb.DeviceBatch(ctx, store, ref)
+    for cols in ([], [0]):
+        for max_lag, top_n, thr in ((60, 100, 0.5), (N, 500, 0.0)):
+            e = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_EXACT, signed_scores=True)
+            s = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_SCREEN, signed_scores=True)
+            assert b.timing().mode == mb.MODE_SCREEN
+            for x, y in zip(e, s):
+                np.testing.assert_array_equal(x, y)
+            assert (e[0] < 0).any()
+    # a sign filter on signed scores cannot be screened (no bound knows the sign): the exact path serves it
+    s = b.run([], 60, 100, 0.5, sign_filter=mb.SignFilter_NEG, mode=mb.MODE_AUTO, signed_scores=True)
+    assert b.timing().mode == mb.MODE_EXACT and len(s[0]) > 0 and np.all(s[0] < 0)
 
 
 @pytest.mark.parametrize("N", [1440, 1026, 1030, 1088, 1090, 1500, 1984, 2046, 2048, 480, 300, 258, 512, 514, 720, 1000, 1024,
@@ -107,7 +135,8 @@ def test_bound_dominates_exact_score(ctx, N):
 
 @pytest.mark.parametrize("N,max_lag", [(1440, 60), (1440, 0), (1440, 5000), (1026, 15), (1500, 300), (2048, 60), (2046, 1),
                                        (2050, 30), (4000, 240), (5000, 0), (10080, 240), (10080, 20000), (16384, 7),
-                                       (480, 15), (300, 0), (512, 600), (1000, 60), (1024, 3)])
+                                       (480, 15), (300, 0), (512, 600), (1000, 60), (1024, 3),
+                                       (1441, 60), (2047, 5), (1027, 0), (481, 15), (9999, 240), (2049, 30)])
 def test_refined_bounds_bracket_exact_score(ctx, N, max_lag):
     """Fused second stage (fp32 inverse transform) on every series: lower <= exact score <= upper, a series
     declared outside the lag window really is, one declared inside really is; the fp32 error is reported."""
@@ -139,7 +168,7 @@ def test_refined_bounds_bracket_exact_score(ctx, N, max_lag):
     assert (out | (lo >= 0)).mean() > 0.5
 
 
-@pytest.mark.parametrize("N", [1440, 2500, 10080, 480, 1000])
+@pytest.mark.parametrize("N", [1440, 2500, 10080, 480, 1000, 1441, 5001])
 def test_grouped_screened_run_equals_exact_run(ctx, N):
     """Grouped runs on the fused kernels: every member refined, a group's best lower bound prunes its members,
     only the contenders are scored in fp64 -- the result must be the all-exact run's, bit for bit."""

@@ -225,3 +225,17 @@ def test_array_form_matches_object_form():
                 assert abs(w.PercentScore - s) < 1e-12 and w.Lag == l
                 assert w.Labels is series[i].labels
                 assert abs(sc_all[i] - s) == 0 and lg_all[i] == l
+
+
+def test_golden_file_is_what_the_generator_reads_out_of_the_reference():
+    """tools/gen_kats.py parses every vector, label and expected score out of the reference's *_test.go literals; the
+    committed tests/golden/reference_kats.json must be exactly its output (no hand transcription to slip).  Needs the
+    reference tree (present in the build container, absent on the GPU box)."""
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("/root/reference is not here")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_kats.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
