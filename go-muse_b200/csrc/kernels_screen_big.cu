@@ -1,8 +1,11 @@
 // kernels_screen_big.cu -- instantiations of score_screen_big_kernel (muse_screen_big.cuh), n = 4096 .. 16384.
 #include <algorithm>
 
+#define MUSE_WIDE_KERNEL
+
 #include "muse_launch.h"
 #include "muse_screen_big.cuh"
+#include "muse_screen_wide.cuh"
 
 namespace muse {
 
@@ -17,6 +20,21 @@ static cudaError_t launch_screen_big_t(const ScreenParams &p, int sm_count, cuda
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     // persistent: every block walks a contiguous range of the series
+    const int64_t blocks = std::min<int64_t>(p.count, (int64_t)sm_count * per_sm);
+    kern<<<(unsigned)blocks, C::T, C::SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+// n = 16384 on 512 threads per series (muse_screen_wide.cuh)
+cudaError_t launch_screen_wide(const ScreenParams &p, int sm_count, cudaStream_t st) {
+    using C = ScreenWideCfg;
+    auto kern = score_screen_wide_kernel;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, C::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
     const int64_t blocks = std::min<int64_t>(p.count, (int64_t)sm_count * per_sm);
     kern<<<(unsigned)blocks, C::T, C::SMEM, st>>>(p);
     return cudaGetLastError();

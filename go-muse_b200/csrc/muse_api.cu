@@ -91,7 +91,8 @@ struct RunScratch {
     double *d_ref;                    // padded copy of the reference row
     cd *Xt, *twM, *twn;
     cf *twp_f;                        // fp32 screening pass: per-pass twiddles
-    cf *twi_f;                        // n = 4096 .. 16384: twiddles of the transposed inverse (muse_screen_big.cuh)
+    cf *twi_f;                        // n = 4096 .. 16384: twiddle tables of muse_screen_big.cuh
+    cf *twide_f;                      // n = 16384: twiddle tables of muse_screen_wide.cuh
     float2 *swtw;                     // split twiddles exp(-2*pi*i*k/n), k < M/2, fp32
     float4 *sw_f;                     // fused kernels: (twn, A[k], A[M-k]) per k < M/2
     float4 *sx_f;                     // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
@@ -203,7 +204,7 @@ static void scratch_free(RunScratch &r) {
     cudaFree(r.d_gmax); cudaFree(r.d_hkeys); cudaFree(r.d_gidx);
     cudaFree(r.d_flag); cudaFree(r.d_counters); cudaFree(r.d_sel); cudaFree(r.d_cut);
     cudaFree(r.d_ref); cudaFree(r.Xt); cudaFree(r.twM); cudaFree(r.twn);
-    cudaFree(r.twp_f); cudaFree(r.twi_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.d_mid);
+    cudaFree(r.twp_f); cudaFree(r.twi_f); cudaFree(r.twide_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.d_mid);
     for (int i = 0; i < 4; i++) if (r.ev[i]) cudaEventDestroy(r.ev[i]);
     if (r.aux) cudaStreamDestroy(r.aux);
     if (r.h_pin) cudaFreeHost(r.h_pin);
@@ -733,9 +734,9 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     if (!b->d_mid) CU(cudaMalloc(&b->d_mid, sizeof(float) * 4));
     const bool want_screen = screen_log2m_supported(b->log2m);
     if (b->tab_n == n && (b->tab_screen || !want_screen)) return MUSE_OK;
-    cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
+    cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->twide_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
     b->Xt = b->twM = b->twn = nullptr;
-    b->twp_f = b->twi_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
+    b->twp_f = b->twi_f = b->twide_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
     b->tab_n = 0;
     b->tab_screen = 0;
     const long double PI2 = 6.283185307179586476925286766559005768L;
@@ -752,7 +753,7 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     CU(cudaMalloc(&b->twn, sizeof(cd) * (size_t)(M / 2 + 1)));
     CU(cudaMemcpyAsync(b->twM, twM.data(), sizeof(cd) * twM.size(), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(b->twn, twn.data(), sizeof(cd) * (size_t)(M / 2 + 1), cudaMemcpyHostToDevice, st));
-    std::vector<cf> twp, twi;
+    std::vector<cf> twp, twi, twide;
     std::vector<float2> swtw;
     if (want_screen) {
         if (screen_is_big(b->log2m)) {
@@ -762,6 +763,14 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
             });
             CU(cudaMalloc(&b->twi_f, sizeof(cf) * twi.size()));
             CU(cudaMemcpyAsync(b->twi_f, twi.data(), sizeof(cf) * twi.size(), cudaMemcpyHostToDevice, st));
+            if (b->log2m == 13 && getenv("MUSE_WIDE13")) {
+                twide.resize(ScreenWideCfg::TW_TOTAL);
+                fill_wide_twiddles(twide.data(), [&](long long num, long long den) {
+                    return cf{(float)cosl(-PI2 * num / den), (float)sinl(-PI2 * num / den)};
+                });
+                CU(cudaMalloc(&b->twide_f, sizeof(cf) * twide.size()));
+                CU(cudaMemcpyAsync(b->twide_f, twide.data(), sizeof(cf) * twide.size(), cudaMemcpyHostToDevice, st));
+            }
         }
         twp.resize((size_t)M + 64);
         fill_pass_twiddles(b->log2m, screen_log2p(b->log2m), twp.data(), [&](long long num, long long den) {
@@ -949,7 +958,8 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(bstream(b));
-    {   // the store-sized scratch goes back to the context (at most 4 sets are kept)
+    {   // the store-sized scratch goes back to the context (at most MUSE_SCRATCH_POOL sets are kept: a multi-query launch
+        // group has 256 batches alive at once)
         std::lock_guard<std::mutex> lk(b->ctx->mu);
         if (b->ctx->pool.size() < MUSE_SCRATCH_POOL) {
             b->ctx->pool.push_back(static_cast<RunScratch &>(*b));
@@ -1259,6 +1269,14 @@ static int run_select(muse_batch *b, const RunArgs &a, int apply_filter, int64_t
 
 static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cudaStream_t st) {
     if (b->log2m == 10) return launch_screen_warp(p, b->ctx->sm_count, st);
+    // MUSE_WIDE13=1: the 512-thread, 64-register variant for n = 16384 (muse_screen_wide.cuh).  Measured SLOWER than the
+    // 256-thread kernel (56.8 ms against 45.9 ms per 1.25 M x 10080): both issue at 39 % of peak, so its 24 % more
+    // instructions decide; kept as the measured record of that design, off by default.
+    if (b->log2m == 13 && b->twide_f && getenv("MUSE_WIDE13")) {
+        ScreenParams pw = p;
+        pw.twi = b->twide_f;
+        return launch_screen_wide(pw, b->ctx->sm_count, st);
+    }
     if (screen_is_big(b->log2m)) return launch_screen_big(b->log2m, p, b->ctx->sm_count, st);
     return launch_screen_block(b->log2m, p, b->ctx->sm_count, st);
 }
@@ -2394,7 +2412,8 @@ extern "C" int muse_xcorr(muse_ctx *ctx, const double *x, int64_t x_len, const d
     if (!ctx || !x || !y || !n_out || !lag || !value) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: NULL argument");
     if (x_len < 1 || y_len < 1) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: empty input (x %lld, y %lld samples)", (long long)x_len, (long long)y_len);
     const int64_t nn = std::max(n, std::max(x_len, y_len));   // xcorr.go:104-106
-    if (nn > (1ll << 24)) return fail(MUSE_ERR_UNSUPPORTED, "muse_xcorr: n = %lld above 2^24 (direct evaluation)", (long long)nn);
+    // direct evaluation: n^2 fp64 FMAs (n = 32768, the reference's benchmark shape: 1.1e9, ~30 ms; 2^18: 7e10, seconds)
+    if (nn > (1ll << 18)) return fail(MUSE_ERR_UNSUPPORTED, "muse_xcorr: n = %lld above 2^18 (direct evaluation)", (long long)nn);
     if (cc && cc_capacity < nn) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: cc holds %lld values, n = %lld", (long long)cc_capacity, (long long)nn);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

@@ -6,6 +6,7 @@
 
 #include "muse_exact.cuh"
 #include "muse_screen_big.cuh"
+#include "muse_screen_wide.cuh"
 #include "muse_screen_block.cuh"
 #include "muse_screen_multi.cuh"
 #include "muse_bounds_tc.cuh"
@@ -23,6 +24,8 @@ cudaError_t launch_screen_warp(const ScreenParams &p, int sm_count, cudaStream_t
 cudaError_t launch_screen_block(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st);
 // n = 4096 .. 16384 (muse_screen_big.cuh)
 cudaError_t launch_screen_big(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st);
+// n = 16384 at twice the occupancy (muse_screen_wide.cuh); its twiddle tables are fill_wide_twiddles'
+cudaError_t launch_screen_wide(const ScreenParams &p, int sm_count, cudaStream_t st);
 // the same pass for up to ScreenMultiCfg::QC reference queries at once (n = 2048)
 cudaError_t launch_screen_multi(const ScreenParams &p, const MultiQuery *d_queries, int nq, int sm_count, cudaStream_t st);
 

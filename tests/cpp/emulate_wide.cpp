@@ -1,4 +1,4 @@
-// CPU emulation of score_screen_big_kernel's per-thread phases (muse_screen_big.cuh compiled as host code).
+// CPU emulation of score_screen_big_kernel's per-thread phases (muse_screen_wide.cuh compiled as host code).
 // Each barrier-delimited phase is run for all T "threads" of a series in sequence.  Checked against a direct
 // evaluation in long double:
 //   * the bound  sum_f |Y_f| A_f  against  (1/n) sum_f |Y_f||X_f|  computed from an O(n^2)-free reference
@@ -13,7 +13,7 @@
 #include <random>
 #include <vector>
 
-#include "muse_screen_big.cuh"
+#include "muse_screen_wide.cuh"
 
 using namespace muse;
 typedef std::complex<double> zd;
@@ -34,9 +34,8 @@ static void fft_rec(std::vector<zd> &a, bool inv) {
     }
 }
 
-template <int LOG2M>
 static int run_case(int N, unsigned seed, int max_lag) {
-    using C = ScreenBigCfg<LOG2M>;
+    using C = ScreenWideCfg;
     constexpr int M = C::M, n = 2 * M, T = C::T;
     std::mt19937_64 rng(seed);
     std::uniform_real_distribution<double> U(-1.0, 1.0);
@@ -79,10 +78,9 @@ static int run_case(int N, unsigned seed, int max_lag) {
     }
     // ---- tables as the library builds them ----
     std::vector<cf> twi(C::TW_TOTAL);
-    fill_big_twiddles(LOG2M, twi.data(), [](long long num, long long den) {
+    fill_wide_twiddles(twi.data(), [](long long num, long long den) {
         return cf{(float)cosl(-2 * PI_L * num / den), (float)sinl(-2 * PI_L * num / den)};
     });
-    const std::vector<cf> &twp = twi;
     std::vector<float4> sw(M / 2), sx(M / 2);
     auto Xt = [&](int k) { return xt[k] / (2.0 * n); };
     for (int k = 0; k < M / 2; k++) {
@@ -94,29 +92,33 @@ static int run_case(int N, unsigned seed, int max_lag) {
     const cf x_mid{(float)Xt(M / 2).real(), (float)Xt(M / 2).imag()};
 
     // ---- the kernel's phases, thread by thread ----
-    std::vector<std::vector<cf>> regs(T, std::vector<cf>(32));
+    std::vector<std::vector<cf>> regs(T, std::vector<cf>(16));
     std::vector<cf> sm(C::SM_ELEMS);
     for (int t = 0; t < T; t++)
-        for (int j = 0; j < 32; j++) {
+        for (int j = 0; j < 16; j++) {
             const int e = t + j * T;
             regs[t][j] = e < Nh ? cf{(float)(y[2 * e] - ym), 2 * e + 1 < N ? (float)(y[2 * e + 1] - ym) : 0.f} : cf{0.f, 0.f};
         }
-    for (int t = 0; t < T; t++) big_fwd_pass0<LOG2M>(regs[t].data(), sm.data(), t, twp.data());
-    for (int t = 0; t < T; t++) big_load_stride_t<LOG2M>(regs[t].data(), sm.data(), t);
-    for (int t = 0; t < T; t++) big_fwd_pass1<LOG2M>(regs[t].data(), sm.data(), t, twp.data());
-    for (int t = 0; t < T; t++) big_fwd_last<LOG2M>(regs[t].data(), sm.data(), t);
+    for (int t = 0; t < T; t++) wide_fwd_pass0(regs[t].data(), sm.data(), t, twi.data());
+    for (int t = 0; t < T; t++) wide_load_stride_t(regs[t].data(), sm.data(), t);
+    for (int t = 0; t < T; t++) wide_fwd_pass1(regs[t].data(), sm.data(), t, twi.data());
+    for (int t = 0; t < T; t++) wide_load_stride_t(regs[t].data(), sm.data(), t);
+    for (int t = 0; t < T; t++) wide_fwd_pass2(regs[t].data(), sm.data(), t, twi.data());
+    for (int t = 0; t < T; t++) wide_fwd_last(regs[t].data(), sm.data(), t);
     double acc = 0;
-    for (int t = 0; t < T; t++) acc += big_split_bound<LOG2M>(regs[t].data(), t, sw.data(), a_mid);
-    for (int t = 0; t < T; t++) big_pointwise<LOG2M>(regs[t].data(), t, sw.data(), sx.data(), x_mid);
-    for (int t = 0; t < T; t++) big_inv_pass0<LOG2M>(regs[t].data(), sm.data(), t, twi.data());
-    for (int t = 0; t < T; t++) big_inv_pass1_load<LOG2M>(regs[t].data(), sm.data(), t);
-    for (int t = 0; t < T; t++) big_inv_pass1<LOG2M>(regs[t].data(), sm.data(), t, twi.data());
-    for (int t = 0; t < T; t++) big_load_stride_t<LOG2M>(regs[t].data(), sm.data(), t);
+    for (int t = 0; t < T; t++) acc += wide_split_bound(regs[t].data(), t, sw.data(), a_mid);
+    for (int t = 0; t < T; t++) wide_pointwise(regs[t].data(), t, sw.data(), sx.data(), x_mid);
+    for (int t = 0; t < T; t++) wide_inv_pass0(regs[t].data(), sm.data(), t, twi.data());
+    for (int t = 0; t < T; t++) wide_inv_pass1_load(regs[t].data(), sm.data(), t);
+    for (int t = 0; t < T; t++) wide_inv_pass1(regs[t].data(), sm.data(), t, twi.data());
+    for (int t = 0; t < T; t++) wide_load_stride_t(regs[t].data(), sm.data(), t);
+    for (int t = 0; t < T; t++) wide_inv_pass2(regs[t].data(), sm.data(), t, twi.data());
+    for (int t = 0; t < T; t++) wide_load_stride_t(regs[t].data(), sm.data(), t);
     float k_in = 0, k_out = 0;
     for (int t = 0; t < T; t++) {
-        Dft<32, float>::run(regs[t].data());
+        Dft<16, float>::run(regs[t].data());
         float a, b;
-        big_window_max<LOG2M>(regs[t].data(), t, win_lo, win_len, a, b);
+        wide_window_max(regs[t].data(), t, win_lo, win_len, a, b);
         k_in = std::max(k_in, a);
         k_out = std::max(k_out, b);
     }
@@ -130,15 +132,10 @@ static int run_case(int N, unsigned seed, int max_lag) {
 
 int main() {
     int bad = 0;
-    bad += run_case<11>(2050, 1, 30);
-    bad += run_case<11>(4096, 2, 2047);
-    bad += run_case<11>(3000, 3, 0);
-    bad += run_case<12>(4100, 4, 100);
-    bad += run_case<12>(8192, 5, 240);
-    bad += run_case<13>(10080, 6, 240);
-    bad += run_case<13>(16384, 7, 60);
-    bad += run_case<13>(8194, 8, 5);
-    bad += run_case<12>(4101, 9, 17);
-    bad += run_case<13>(10081, 10, 240);
+    bad += run_case(10080, 6, 240);
+    bad += run_case(16384, 7, 60);
+    bad += run_case(8194, 8, 5);
+    bad += run_case(10081, 9, 0);
+    bad += run_case(12345, 10, 8000);
     return bad ? 1 : 0;
 }

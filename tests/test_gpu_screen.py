@@ -79,6 +79,33 @@ def test_screened_run_equals_exact_run(ctx, N):
     assert set(ix[~same]) == set(wix[~same])
 
 
+@pytest.mark.parametrize("N", [10080, 16384, 8195])
+def test_wide_kernel_variant_equals_exact_run(ctx, N, monkeypatch):
+    """The 512-thread variant of the n = 16384 screening kernel (MUSE_WIDE13=1; off by default because it measured slower):
+    ungrouped and grouped screened runs must still be the all-exact run, bit for bit."""
+    monkeypatch.setenv("MUSE_WIDE13", "1")
+    rng = np.random.default_rng(13 * N)
+    S = 5000
+    Y = _adversarial(rng, S, N)
+    ref = np.zeros(N)
+    ref[N // 2 - 5:N // 2 + 5] = 1.5
+    ref += 0.1 * (rng.random(N) - 0.5)
+    store = mb.DeviceStore(ctx, N, 1, S)
+    store.append(Y, (np.arange(S) // 25).astype(np.int32)[:, None])
+    b = mb.DeviceBatch(ctx, store, ref)
+    for cols in ([], [0]):
+        for max_lag, top_n, thr in ((240, 100, 0.5), (N, 300, 0.0)):
+            e = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_EXACT)
+            s = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_SCREEN)
+            assert b.timing().mode == mb.MODE_SCREEN
+            for x, y in zip(e, s):
+                np.testing.assert_array_equal(x, y)
+    up, lo = b.screen_bounds(refine=True, max_lag=240)
+    sc, lg = b.score_all()
+    dec = up >= 0
+    assert np.all(up[dec].astype(np.float64) >= sc[dec] + 0.5e-4)
+
+
 @pytest.mark.parametrize("N", [1440, 1441, 480, 10080])
 def test_signed_screened_run_equals_exact_run(ctx, N):
     """Signed scores (Muse.Run, muse.go:72-76: the sign is kept, clamp to [-1, 1], ranking by |score|) through the
