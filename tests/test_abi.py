@@ -1,6 +1,7 @@
 """CPU-side checks of the boundary: the C-ABI library builds, loads and exports every
 symbol include/muse_b200.h declares; host-side facade logic (labels, group, results)
 mirrors the reference's tests.  No compute calls (no GPU here)."""
+import json
 import os
 import re
 
@@ -200,3 +201,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_screen_error_survey_keeps_its_margins():
+    """profiles/screen_error_survey.json (tools/screen_error_survey.py, measured on a B200): for every FFT length the
+    screening kernels serve, the fp32 second stage stays within a quarter of the slack of the fp64 score and no bound
+    comes closer than a quarter of the slack to the score it brackets."""
+    path = os.path.join(ROOT, "profiles", "screen_error_survey.json")
+    d = json.load(open(path))
+    slack = d["slack"]
+    assert slack == 2e-4
+    lens = {r["fft_len"] for r in d["rows"]}
+    assert {512, 1024, 2048, 4096, 8192, 16384} <= lens
+    assert any(r["N"] & 1 for r in d["rows"])                  # odd lengths are part of the survey
+    for r in d["rows"]:
+        assert r["fp32_vs_fp64_worst_abs_error"] <= slack / 4, r
+        for k in ("spectral_bound_min_margin", "refined_upper_min_margin", "refined_lower_min_margin"):
+            assert r[k] >= slack / 4, (k, r)
