@@ -155,6 +155,11 @@ struct muse_batch : RunScratch {
     int prescreened;       // d_U and the cut-off state were filled by score_screen_multi_kernel: the next fused run starts at its tail
     int use_aux;           // queue this batch's work on its own stream (RunScratch::aux) instead of the context's
     int signed_run;        // the current run keeps the sign of the scores (muse.go:72-76)
+    // n > MUSE_MAX_FUSED_FFT_LEN: Stockham passes through global memory (kernels_long.cu); Xt holds n entries, twM the n twiddles
+    int is_long;
+    void *d_long;          // work buffer of launch_long
+    size_t d_long_bytes;
+    long long long_pairs;  // pairs of series per chunk d_long was sized for
 };
 
 static inline cudaStream_t bstream(const muse_batch *b) { return b->use_aux ? b->aux : b->ctx->stream; }
@@ -696,7 +701,12 @@ static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 
 static int screen_is_fused(int log2m) { return log2m >= 8 && log2m <= 13; }
 static int screen_is_big(int log2m) { return log2m >= 11 && log2m <= 13; }      // muse_screen_big.cuh
 static int screen_log2m_supported(int log2m) { return screen_is_fused(log2m); }
-static int screen_log2p(int log2m) { return log2m >= 10 ? 5 : (log2m == 9 ? 4 : 3); }
+// n = 512 / 1024: several series per warp (muse_screen_sub.cuh); MUSE_BLOCK_SMALL=1 keeps round 1's block kernel for A/B runs
+static bool block_small() {
+    static const bool v = getenv("MUSE_BLOCK_SMALL") != nullptr;
+    return v;
+}
+static int screen_log2p(int log2m) { return (log2m >= 10 || !block_small()) ? 5 : (log2m == 9 ? 4 : 3); }
 
 // The per-reference tables of the fp32 kernels, from Xt on the device: weights of the bound
 // A[k] = |Xt[k]| * (1 at DC and Nyquist, else 2) rounded UP (the bound must not shrink), one 16-byte entry per
@@ -734,6 +744,18 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     if (!b->d_mid) CU(cudaMalloc(&b->d_mid, sizeof(float) * 4));
     const bool want_screen = screen_log2m_supported(b->log2m);
     if (b->tab_n == n && (b->tab_screen || !want_screen)) return MUSE_OK;
+    if (b->is_long) {      // the reference's transform has n entries, the twiddles are generated on the device
+        cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->twide_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
+        b->Xt = b->twM = b->twn = nullptr;
+        b->twp_f = b->twi_f = b->twide_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
+        b->tab_n = 0;
+        b->tab_screen = 0;
+        CU(cudaMalloc(&b->Xt, sizeof(cd) * (size_t)n));
+        CU(cudaMalloc(&b->twM, sizeof(cd) * (size_t)n));
+        CU(launch_long_twiddles(b->twM, b->log2m + 1, st));
+        b->tab_n = n;
+        return MUSE_OK;
+    }
     cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->twide_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
     b->Xt = b->twM = b->twn = nullptr;
     b->twp_f = b->twi_f = b->twide_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
@@ -797,6 +819,8 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
 // d_ref_row != NULL: the reference row is already on the device, zero-padded to the slab's row pitch (muse_multi_run
 // uploads the references of a launch with one copy).
 extern "C" void muse_batch_destroy(muse_batch *b);
+static int ensure_long_work(muse_batch *b, int64_t count);
+static LongParams long_params(const muse_batch *b, const double *slab, int64_t count, const int32_t *idx, int signed_scores);
 
 // as CU, for code that owns a half-built batch `b`: it goes back to the pool before the error is returned
 #define CUB(call)                                                                                  \
@@ -822,6 +846,7 @@ static int batch_alloc(muse_ctx *ctx, muse_group *g, int64_t ref_len, muse_batch
     CU(cudaSetDevice(ctx->device));
     muse_batch *b = new muse_batch();
     memset(b, 0, sizeof(*b));
+    b->is_long = n > MUSE_MAX_FUSED_FFT_LEN;
     b->ctx = ctx;
     b->g = g;
     b->N = ref_len;
@@ -893,7 +918,18 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
     p.twn = b->twn;
     p.out_X = b->Xt;
     p.out_flag = b->d_flag;
-    CUB(launch_exact(MODE_REF, b->log2m, p, st));
+    if (b->is_long) {
+        int rcl = ensure_long_work(b, 1);
+        if (rcl) {
+            muse_batch_destroy(b);
+            return rcl;
+        }
+        LongParams lp = long_params(b, p.slab, 1, nullptr, 0);
+        lp.out_X = b->Xt;
+        CUB(launch_long(MODE_REF, lp, b->d_long, b->long_pairs, st));
+    } else {
+        CUB(launch_exact(MODE_REF, b->log2m, p, st));
+    }
     b->screen_ok = 0;
     const bool screen = b->tab_screen != 0;
     if (screen) {
@@ -967,6 +1003,7 @@ extern "C" void muse_batch_destroy(muse_batch *b) {
         }
     }
     scratch_free(*b);
+    cudaFree(b->d_long);
     delete b;
 }
 
@@ -999,6 +1036,40 @@ static int check_batch(muse_batch *b) {
     return MUSE_OK;
 }
 
+// n > MUSE_MAX_FUSED_FFT_LEN: the work buffer of launch_long, sized for `count` series or 256 MB worth of pairs
+static int ensure_long_work(muse_batch *b, int64_t count) {
+    const int log2n = b->log2m + 1;
+    const size_t per_pair = long_work_bytes(log2n, 1);
+    long long pairs = std::max<long long>(1, (long long)(((size_t)256 << 20) / per_pair));
+    pairs = std::min<long long>(pairs, std::max<long long>(1, (count + 1) / 2));
+    if (b->d_long && b->long_pairs >= pairs) return MUSE_OK;
+    cudaFree(b->d_long);
+    b->d_long = nullptr;
+    b->long_pairs = 0;
+    b->d_long_bytes = long_work_bytes(log2n, pairs);
+    CU(cudaMalloc(&b->d_long, b->d_long_bytes));
+    b->long_pairs = pairs;
+    return MUSE_OK;
+}
+
+static LongParams long_params(const muse_batch *b, const double *slab, int64_t count, const int32_t *idx, int signed_scores) {
+    LongParams lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.slab = slab;
+    lp.ld = b->g->ld;
+    lp.count = count;
+    lp.idx = idx;
+    lp.N = (int)b->N;
+    lp.log2n = b->log2m + 1;
+    lp.signed_scores = signed_scores;
+    lp.X = b->Xt;
+    lp.tw = b->twM;
+    lp.out_score = b->d_score;
+    lp.out_lag = b->d_lag;
+    lp.out_flag = b->d_flag;
+    return lp;
+}
+
 // All series of the store through the exact kernel -> d_score / d_lag.
 static int score_exact_all(muse_batch *b, int signed_scores, const int32_t *idx, int64_t count,
                            const unsigned long long *d_count = nullptr) {
@@ -1016,7 +1087,14 @@ static int score_exact_all(muse_batch *b, int signed_scores, const int32_t *idx,
     p.twn = b->twn;
     p.out_score = b->d_score;
     p.out_lag = b->d_lag;
-    if (count > 0) {
+    if (count > 0 && b->is_long) {
+        if (d_count) return fail(MUSE_ERR_UNSUPPORTED, "device-side list lengths do not exist above FFT length %d", MUSE_MAX_FUSED_FFT_LEN);
+        int rc = ensure_long_work(b, count);
+        if (rc) return rc;
+        LongParams lp = long_params(b, b->g->slab, count, idx, signed_scores);
+        CU(launch_long(MODE_SCORE, lp, b->d_long, b->long_pairs, bstream(b)));
+        b->timing.n_launches++;
+    } else if (count > 0) {
         CU(launch_exact(MODE_SCORE, b->log2m, p, bstream(b)));
         b->timing.n_launches++;
     }
@@ -1057,7 +1135,18 @@ extern "C" int muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, 
     p.twn = b->twn;
     p.out_score = d_cc;
     p.out_flag = b->d_flag;
-    CU(launch_exact(MODE_CC, b->log2m, p, bstream(b)));
+    if (b->is_long) {
+        rc = ensure_long_work(b, 1);
+        if (rc) {
+            cudaFree(d_cc);
+            return rc;
+        }
+        LongParams lp = long_params(b, p.slab, 1, nullptr, 0);
+        lp.out_score = d_cc;
+        CU(launch_long(MODE_CC, lp, b->d_long, b->long_pairs, bstream(b)));
+    } else {
+        CU(launch_exact(MODE_CC, b->log2m, p, bstream(b)));
+    }
     int32_t flag = 0;
     CU(cudaMemcpyAsync(cc, d_cc, sizeof(double) * (size_t)b->n, cudaMemcpyDeviceToHost, bstream(b)));
     CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, bstream(b)));
@@ -1278,6 +1367,8 @@ static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cud
         return launch_screen_wide(pw, b->ctx->sm_count, st);
     }
     if (screen_is_big(b->log2m)) return launch_screen_big(b->log2m, p, b->ctx->sm_count, st);
+    if (b->log2m == 8 && !block_small()) return launch_screen_sub3(p, b->ctx->sm_count, st);
+    if (b->log2m == 9 && !block_small()) return launch_screen_sub4(p, b->ctx->sm_count, st);
     return launch_screen_block(b->log2m, p, b->ctx->sm_count, st);
 }
 
@@ -2412,8 +2503,14 @@ extern "C" int muse_xcorr(muse_ctx *ctx, const double *x, int64_t x_len, const d
     if (!ctx || !x || !y || !n_out || !lag || !value) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: NULL argument");
     if (x_len < 1 || y_len < 1) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: empty input (x %lld, y %lld samples)", (long long)x_len, (long long)y_len);
     const int64_t nn = std::max(n, std::max(x_len, y_len));   // xcorr.go:104-106
-    // direct evaluation: n^2 fp64 FMAs (n = 32768, the reference's benchmark shape: 1.1e9, ~30 ms; 2^18: 7e10, seconds)
-    if (nn > (1ll << 18)) return fail(MUSE_ERR_UNSUPPORTED, "muse_xcorr: n = %lld above 2^18 (direct evaluation)", (long long)nn);
+    // up to 4096 lags: direct evaluation, n^2 fp64 FMAs (the reference's own vectors are n = 5).  Above: the FFT passes of
+    // kernels_long.cu -- one transform of length n when n is a power of two (the reference's benchmark shape, n = 32768),
+    // else the linear correlation at a power of two >= 2n, folded
+    if (nn > (1ll << 26)) return fail(MUSE_ERR_UNSUPPORTED, "muse_xcorr: n = %lld above 2^26", (long long)nn);
+    const bool by_fft = nn > 4096;
+    long long L = nn;
+    if (by_fft && (nn & (nn - 1))) L = next_pow2(2 * nn);
+    const size_t work_bytes = by_fft ? long_xcorr_work_bytes(L) : 0;
     if (cc && cc_capacity < nn) return fail(MUSE_ERR_INVALID_ARG, "muse_xcorr: cc holds %lld values, n = %lld", (long long)cc_capacity, (long long)nn);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -2424,7 +2521,8 @@ extern "C" int muse_xcorr(muse_ctx *ctx, const double *x, int64_t x_len, const d
     // one allocation: x, y, xp, yp, cc (doubles), then lag, value, flag
     const size_t nd = (size_t)x_len + (size_t)y_len + 3 * (size_t)nn;
     unsigned char *d = nullptr;
-    CU(cudaMalloc(&d, nd * sizeof(double) + 32));
+    CU(cudaMalloc(&d, nd * sizeof(double) + 32 + 256 + work_bytes));
+    void *d_work = d + ((nd * sizeof(double) + 32 + 255) / 256) * 256;
     double *dx = reinterpret_cast<double *>(d), *dy = dx + x_len, *dxp = dy + y_len, *dyp = dxp + nn, *dcc = dyp + nn;
     long long *dlag = reinterpret_cast<long long *>(dcc + nn);
     double *dval = reinterpret_cast<double *>(dlag + 1);
@@ -2438,7 +2536,8 @@ extern "C" int muse_xcorr(muse_ctx *ctx, const double *x, int64_t x_len, const d
         // xcorr.go:139-142: gonum's inverse transform is unnormalised (n x the correlation); the reference scales
         // by 1/(n(n-1)) for z-normalised inputs and by 1/n otherwise -> 1/(n-1) and 1 on a direct sum
         const double scale = normalize ? 1.0 / (double)(nn - 1) : 1.0;
-        xcorr_direct_kernel<<<(unsigned)((nn + XC_LAGS - 1) / XC_LAGS), XC_LAGS, 0, st>>>(dxp, dyp, nn, scale, dcc);
+        if (by_fft) CU(launch_long_xcorr(dxp, dyp, nn, L, scale, dcc, d_work, st));
+        else xcorr_direct_kernel<<<(unsigned)((nn + XC_LAGS - 1) / XC_LAGS), XC_LAGS, 0, st>>>(dxp, dyp, nn, scale, dcc);
         xcorr_argmax_kernel<<<1, 256, 0, st>>>(dcc, nn, dlag, dval);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(&tail, dlag, sizeof(tail), cudaMemcpyDeviceToHost, st));

@@ -8,8 +8,8 @@ import "C"
 import "unsafe"
 
 // xCorr computes the cross correlation slice between x and y, the lag of the maximum absolute value
-// and that value (go-muse xcorr.go:102-153), for any n -- on the device, by direct evaluation of the
-// circular correlation (muse_xcorr).  n is raised to max(n, len(x), len(y)); with normalize both
+// and that value (go-muse xcorr.go:102-153), for any n -- on the device (muse_xcorr: the circular
+// correlation evaluated directly up to 4096 lags, by FFT passes above).  n is raised to max(n, len(x), len(y)); with normalize both
 // inputs are z-normalized first and a constant input yields (nil, 0, 0) exactly as the reference does.
 func xCorr(x []float64, y []float64, n int, normalize bool) ([]float64, int, float64) {
 	if len(x) == 0 || len(y) == 0 {

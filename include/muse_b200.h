@@ -38,7 +38,8 @@ extern "C" {
 #define MUSE_ERR_UNSUPPORTED     6  /* e.g. nextPowOf2(len) > MUSE_MAX_FFT_LEN, group-by keys that need more than 64 key bits */
 #define MUSE_ERR_OUT_OF_MEMORY   7
 
-#define MUSE_MAX_FFT_LEN 16384      /* n = nextPowOf2(series length), xcorr.go:19-24 */
+#define MUSE_MAX_FFT_LEN (1 << 24)        /* n = nextPowOf2(series length), xcorr.go:19-24: 16 M samples per series */
+#define MUSE_MAX_FUSED_FFT_LEN 16384      /* up to here one fused kernel per run; above, FFT passes through global memory */
 
 /* results.go:20-26 */
 #define MUSE_SIGN_ANY  0
@@ -147,7 +148,10 @@ int  muse_group_read_rows(muse_group *g, int64_t first, int64_t n_rows, double *
  * NewBatch (muse_batch.go:23-52): checks ref_len against the group
  * (MUSE_ERR_LENGTH_MISMATCH), n = nextPowOf2(ref_len), computes on the device
  * X = rfft(zeroPad(zNormalize(ref)/(N-1), n)); std(ref)==0 -> MUSE_ERR_STDDEV_ZERO.
- * The reference row is copied; unlike go-muse nothing is mutated in place. */
+ * The reference row is copied; unlike go-muse nothing is mutated in place.
+ * n <= MUSE_MAX_FUSED_FFT_LEN: one fused kernel scores a series from its row (fp32 screening for n = 512 .. 16384).
+ * Above (go-muse has no limit; BenchmarkXCorrWithX is n = 32768, xcorr_test.go:330-348): every series is scored in fp64 by
+ * FFT passes through global memory, two series per complex transform, 256 MB of work space at a time. */
 int  muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len,
                        muse_batch **out);
 void muse_batch_destroy(muse_batch *b);
@@ -229,7 +233,9 @@ int  muse_multi_bounds_tc(muse_ctx *ctx, muse_group *g, const double *refs, int6
  * two; the reference's own KATs use n = 5): n' = max(n, x_len, y_len) (:104-106), optional z-normalisation
  * of both inputs (:108-127), LEADING zero pads (:128-129), cc[k] = sum_t xp[(t+k) mod n'] * yp[t], divided
  * by n'-1 when normalised (:139-140 on gonum's unnormalised inverse), arg-max of |cc| with the first index winning and the wrap to
- * (-n'/2, n'/2] (:145-151).  Evaluated directly in fp64 on the device (a utility, one pair per call).
+ * (-n'/2, n'/2] (:145-151).  In fp64 on the device, one pair per call: up to 4096 lags by direct evaluation of that sum; above, by
+ * FFT passes through global memory -- one transform of length n' when n' is a power of two (BenchmarkXCorr's n = 32768,
+ * xcorr_test.go:310-326), else the linear correlation at a power of two >= 2n', folded.  n' <= 2^26.
  * x, y: host rows.  cc (host, may be NULL): n' values when cc_capacity >= n'.  *n_out = n', or 0 with
  * *std_zero = 1, *lag = 0, *value = 0 when a normalised input has std == 0 (:109-126, the reference returns
  * (nil, 0, 0)). */
