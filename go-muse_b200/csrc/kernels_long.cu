@@ -120,8 +120,22 @@ long_pass_kernel(const cd *__restrict__ in, cd *__restrict__ out, const cd *__re
 #pragma unroll
     for (int r = 0; r < R; r++) v[r] = src[j + ((long long)r << lb)];
     if (log2ns > 0) {
+        // W^(r k): one table read, the higher powers by multiplication (depth <= 3, a few ulp): the strided reads of a
+        // flat table cost this pass twice the sectors of its data
+        cd wp[R];
+        wp[1] = tw[k << shift];
+        if constexpr (R > 2) {
+            wp[2] = cmul(wp[1], wp[1]);
+            wp[3] = cmul(wp[2], wp[1]);
+        }
+        if constexpr (R > 4) {
+            wp[4] = cmul(wp[2], wp[2]);
+            wp[5] = cmul(wp[4], wp[1]);
+            wp[6] = cmul(wp[3], wp[3]);
+            wp[7] = cmul(wp[4], wp[3]);
+        }
 #pragma unroll
-        for (int r = 1; r < R; r++) v[r] = cmul(v[r], tw[(k * r) << shift]);
+        for (int r = 1; r < R; r++) v[r] = cmul(v[r], wp[r]);
     }
     Dft<R, double>::run(v);
     const long long base = ((j >> log2ns) << (log2ns + LR)) + k;

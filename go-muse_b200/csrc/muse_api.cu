@@ -697,8 +697,10 @@ static int64_t next_pow2(int64_t v) {   // == nextPowOf2 (xcorr.go:19-24) for 1 
 }
 
 // fp32 tables of the screening kernel; leaves screen_ok = 0 when the shape has no screening kernel
-// n = 512 .. 16384: kernels with the fused fp32 second stage (warp kernel at 2048, block kernel elsewhere)
-static int screen_is_fused(int log2m) { return log2m >= 8 && log2m <= 13; }
+// n = 128 .. 16384: kernels with the fused fp32 second stage (several series per warp up to 1024, one warp per series at 2048,
+// one block per series above)
+static bool block_small();
+static int screen_is_fused(int log2m) { return log2m >= (block_small() ? 8 : 6) && log2m <= 13; }
 static int screen_is_big(int log2m) { return log2m >= 11 && log2m <= 13; }      // muse_screen_big.cuh
 static int screen_log2m_supported(int log2m) { return screen_is_fused(log2m); }
 // n = 512 / 1024: several series per warp (muse_screen_sub.cuh); MUSE_BLOCK_SMALL=1 keeps round 1's block kernel for A/B runs
@@ -1040,7 +1042,9 @@ static int check_batch(muse_batch *b) {
 static int ensure_long_work(muse_batch *b, int64_t count) {
     const int log2n = b->log2m + 1;
     const size_t per_pair = long_work_bytes(log2n, 1);
-    long long pairs = std::max<long long>(1, (long long)(((size_t)256 << 20) / per_pair));
+    // both buffers of a chunk together: MUSE_LONG_WORK_MB (default 256)
+    static const size_t work_mb = getenv("MUSE_LONG_WORK_MB") ? (size_t)std::max(1, atoi(getenv("MUSE_LONG_WORK_MB"))) : 256;
+    long long pairs = std::max<long long>(1, (long long)((work_mb << 20) / per_pair));
     pairs = std::min<long long>(pairs, std::max<long long>(1, (count + 1) / 2));
     if (b->d_long && b->long_pairs >= pairs) return MUSE_OK;
     cudaFree(b->d_long);
@@ -1367,6 +1371,8 @@ static cudaError_t launch_screen(const muse_batch *b, const ScreenParams &p, cud
         return launch_screen_wide(pw, b->ctx->sm_count, st);
     }
     if (screen_is_big(b->log2m)) return launch_screen_big(b->log2m, p, b->ctx->sm_count, st);
+    if (b->log2m == 6) return launch_screen_sub1(p, b->ctx->sm_count, st);
+    if (b->log2m == 7) return launch_screen_sub2(p, b->ctx->sm_count, st);
     if (b->log2m == 8 && !block_small()) return launch_screen_sub3(p, b->ctx->sm_count, st);
     if (b->log2m == 9 && !block_small()) return launch_screen_sub4(p, b->ctx->sm_count, st);
     return launch_screen_block(b->log2m, p, b->ctx->sm_count, st);

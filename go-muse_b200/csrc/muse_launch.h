@@ -23,7 +23,9 @@ inline int exact_log2p(int log2m) { return log2m < 4 ? log2m : 4; }
 // fp32 screening + fused second stage: warp kernel (n = 2048), block kernel (n = 512, 1024, 4096 .. 16384)
 cudaError_t launch_screen_warp(const ScreenParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_screen_block(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st);
-// n = 512 / 1024: four / two series per warp (muse_screen_sub.cuh)
+// n = 128 .. 1024: sixteen .. two series per warp (muse_screen_sub.cuh)
+cudaError_t launch_screen_sub1(const ScreenParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_screen_sub2(const ScreenParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_screen_sub3(const ScreenParams &p, int sm_count, cudaStream_t st);
 cudaError_t launch_screen_sub4(const ScreenParams &p, int sm_count, cudaStream_t st);
 // n = 4096 .. 16384 (muse_screen_big.cuh)

@@ -1,9 +1,9 @@
-// muse_screen_sub.cuh -- the fp32 screening + fused second stage for FFT lengths 512 and 1024 (series of 258 .. 1024
+// muse_screen_sub.cuh -- the fp32 screening + fused second stage for FFT lengths 128 .. 1024 (series of 65 .. 1024
 // samples; go-muse's own benchmark shape is 480 samples, muse_batch_test.go:135-162): the design of
 // score_screen_warp_kernel (muse_screen.cuh) with SEVERAL series per warp.
 //
-// M = n/2 = 32 T complex points per series, T = 8 (n = 512) or 16 (n = 1024) lanes per series, 32 points per lane, so a
-// warp carries GS = 32 / T = 4 or 2 series side by side in the register layout of the n = 2048 kernel.  Pass 0 is the
+// M = n/2 = 32 T complex points per series, T = 2, 4, 8, 16 lanes per series (n = 128, 256, 512, 1024), 32 points per
+// lane, so a warp carries GS = 32 / T = 16 .. 2 series side by side in the register layout of the n = 2048 kernel.  Pass 0 is the
 // same pruned radix-32 transform in registers (inputs z[t + T r]), the exchange goes through the series' own row
 // buffer, pass 1 is GS radix-T transforms per lane; its outputs k = t + T m (m = slot) mirror into lane (T - t) % T,
 // slot 31 - m, exactly as in the n = 2048 kernel with 32 replaced by T, so the real split, the magnitudes and (second
@@ -21,13 +21,15 @@
 // run bit-identical to the all-exact run (tests/test_gpu_screen.py).
 #pragma once
 
+#include <stdlib.h>
+
 #include "muse_screen.cuh"
 
 namespace muse {
 
 template <int LOG2T>
 struct ScreenSubCfg {
-    static_assert(LOG2T == 3 || LOG2T == 4, "sub-warp kernel: n = 512 (8 lanes per series) or 1024 (16)");
+    static_assert(LOG2T >= 1 && LOG2T <= 4, "sub-warp kernel: n = 128 (2 lanes per series), 256 (4), 512 (8) or 1024 (16)");
     static constexpr int LOG2M = LOG2T + 5;
     using G = Geo<LOG2M, 5>;
     static constexpr int T = 1 << LOG2T;
@@ -37,7 +39,18 @@ struct ScreenSubCfg {
     static constexpr size_t SMEM_BUDGET = 227 * 1024;
     static constexpr size_t EX_SERIES = ((size_t)(G::MP + 1) * sizeof(cf) + 127) / 128 * 128;   // one series' padded exchange
     static constexpr size_t EX_BYTES = (size_t)GS * EX_SERIES;
-    static size_t row_bytes(int N) { const size_t r = ((size_t)N * 8 + 127) / 128 * 128; return r > EX_SERIES ? r : EX_SERIES; }
+    // the row buffers of a warp's series sit row_bytes apart: a multiple of 128 bytes plus a skew that spreads the
+    // series over the shared-memory banks (2 lanes x 16 bytes per series at T = 2: without it all 16 series of a warp
+    // hit the same 8 banks on every row read and every exchange)
+    static size_t row_skew() {
+        static const long env = getenv("MUSE_SUB_SKEW") ? atol(getenv("MUSE_SUB_SKEW")) : -1;
+        return env >= 0 ? (size_t)env / 16 * 16 : (size_t)SKEW;
+    }
+    static constexpr int SKEW = T >= 8 ? 0 : 16 * T;
+    static size_t row_bytes(int N) {
+        const size_t r = ((size_t)N * 8 + 127) / 128 * 128;
+        return (r > EX_SERIES ? r : EX_SERIES) + row_skew();
+    }
     static size_t warp_bytes(int N) { return (size_t)GS * row_bytes(N); }
     static int warps(int N) {
         const size_t w = (SMEM_BUDGET - NREF * EX_BYTES) / warp_bytes(N);

@@ -51,7 +51,7 @@ def _adversarial(rng, S, N):
 
 
 @pytest.mark.parametrize("N", [1440, 1030, 2048, 480, 300, 700, 1000, 1024, 2500, 4096, 6000, 10080,
-                               1441, 1027, 2047, 481, 999, 2049, 4097, 10081, 16383])
+                               1441, 1027, 2047, 481, 999, 2049, 4097, 10081, 16383, 66, 100, 127, 128, 130, 200, 255, 256, 257, 259, 513])
 def test_screened_run_equals_exact_run(ctx, N):
     rng = np.random.default_rng(N)
     S = 30000 if N <= 2048 else 6000
@@ -134,7 +134,7 @@ def test_signed_screened_run_equals_exact_run(ctx, N):
 
 
 @pytest.mark.parametrize("N", [1440, 1026, 1030, 1088, 1090, 1500, 1984, 2046, 2048, 480, 300, 258, 512, 514, 720, 1000, 1024,
-                               2050, 3000, 4096, 4098, 7000, 8192, 8194, 10080, 16384])
+                               2050, 3000, 4096, 4098, 7000, 8192, 8194, 10080, 16384, 66, 101, 128, 130, 199, 256])
 def test_bound_dominates_exact_score(ctx, N):
     """U >= exact fp64 score for every series, on the adversarial inputs and on siggen-style rows;
     the margin U - score is reported (it must never be negative)."""
@@ -163,7 +163,8 @@ def test_bound_dominates_exact_score(ctx, N):
 @pytest.mark.parametrize("N,max_lag", [(1440, 60), (1440, 0), (1440, 5000), (1026, 15), (1500, 300), (2048, 60), (2046, 1),
                                        (2050, 30), (4000, 240), (5000, 0), (10080, 240), (10080, 20000), (16384, 7),
                                        (480, 15), (300, 0), (512, 600), (1000, 60), (1024, 3),
-                                       (1441, 60), (2047, 5), (1027, 0), (481, 15), (9999, 240), (2049, 30)])
+                                       (1441, 60), (2047, 5), (1027, 0), (481, 15), (9999, 240), (2049, 30),
+                                       (66, 3), (100, 10), (128, 0), (129, 200), (200, 15), (255, 7), (256, 30)])
 def test_refined_bounds_bracket_exact_score(ctx, N, max_lag):
     """Fused second stage (fp32 inverse transform) on every series: lower <= exact score <= upper, a series
     declared outside the lag window really is, one declared inside really is; the fp32 error is reported."""
@@ -195,7 +196,7 @@ def test_refined_bounds_bracket_exact_score(ctx, N, max_lag):
     assert (out | (lo >= 0)).mean() > 0.5
 
 
-@pytest.mark.parametrize("N", [1440, 2500, 10080, 480, 1000, 1441, 5001])
+@pytest.mark.parametrize("N", [1440, 2500, 10080, 480, 1000, 1441, 5001, 100, 250])
 def test_grouped_screened_run_equals_exact_run(ctx, N):
     """Grouped runs on the fused kernels: every member refined, a group's best lower bound prunes its members,
     only the contenders are scored in fp64 -- the result must be the all-exact run's, bit for bit."""

@@ -12,3 +12,5 @@ timeout 600 ncu --set full --import-source on --clock-control none --kernel-name
 tail -3 gpurun_out/ncu_exact.log
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:score_screen_sub --launch-skip 3 -c 1 -o gpurun_out/prof_sub3_r02 -f python bench.py --length 480 --series 3000000 --max-lag 15 --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_sub3.log 2>&1
 tail -3 gpurun_out/ncu_sub3.log
+timeout 300 python tools/long_probe.py > gpurun_out/long_probe.log 2>&1; tail -5 gpurun_out/long_probe.log
+MUSE_LONG_WORK_MB=64 timeout 300 python tools/long_probe.py > gpurun_out/long_probe64.log 2>&1; tail -5 gpurun_out/long_probe64.log
