@@ -502,7 +502,7 @@ def main():
                     "traffic": traffic, "peak_source": peak_src,
                     "kernel": "score_exact_kernel" if used_mode == "exact" else
                               ("score_screen_warp_kernel" if 1024 < N <= 2048 else "score_screen_big_kernel" if N > 2048
-                               else "score_screen_block_kernel" if (N <= 256 or os.environ.get("MUSE_BLOCK_SMALL"))
+                               else "score_screen_block_kernel" if os.environ.get("MUSE_BLOCK_SMALL")
                                else "score_screen_sub_kernel"),
                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                     "frac_of_nominal_8TBps": achieved / 8000.0}

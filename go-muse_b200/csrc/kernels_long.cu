@@ -44,38 +44,68 @@ __device__ __forceinline__ double long_block_sum(double v, double *red) {
     return s;
 }
 
-// One block per pair of series: mean (xcorr.go:85-86), centred values with their sum of squares and the
-// residual sum the corrected two-pass variance needs (:88), written as z[j] = (y1[j], y2[j]) behind n - N
-// zeros.  stats[2*pos] = (ss, comp).
+// Scratch of a chunk behind its two buffers (doubles): stats[4 per pair] = (ss, comp) of each series, then per pair and
+// series LONG_NB_MAX partial row sums, 2 x LONG_NB_MAX partial (ss, comp), 3 x LONG_NB_MAX partial peaks.
+constexpr int LONG_NB_MAX = 64;
+constexpr int LONG_SCRATCH_PER_PAIR = 4 + 2 * 6 * LONG_NB_MAX;
+__device__ __forceinline__ double *long_part(const LongParams &prm, long long pairs_cap, long long pair, int h, int what) {
+    // what: 0 = row sums [NB], 1 = (ss, comp) [2 NB], 2 = peaks [3 NB]
+    double *base = prm.stats + 4 * pairs_cap + (size_t)(2 * pair + h) * (6 * LONG_NB_MAX);
+    return base + (what == 0 ? 0 : what == 1 ? LONG_NB_MAX : 3 * LONG_NB_MAX);
+}
+__device__ __forceinline__ const double *long_row(const LongParams &prm, long long first, long long pair, int h) {
+    const long long pos = first + 2 * pair + h;
+    if (pos >= prm.count) return nullptr;
+    const long long row = prm.idx ? (long long)prm.idx[pos] : pos;
+    return prm.slab + (size_t)row * (size_t)prm.ld;
+}
+
+// A row is cut into nb segments (blockIdx.x), one block each, so that a chunk of few long rows still fills the GPU; every
+// sum is then taken over the segments' partial sums in segment order, so results do not depend on scheduling.
+// Step 1: partial row sums (xcorr.go:85-86).
 __global__ void __launch_bounds__(256)
-long_load_kernel(const LongParams prm, long long first, long long pairs, cd *__restrict__ z) {
+long_sum_kernel(const LongParams prm, long long first, long long pairs_cap, int nb) {
     __shared__ double red[8];
-    const long long pair = blockIdx.x;
-    if (pair >= pairs) return;
+    const long long pair = blockIdx.y;
+    const long long N = prm.N, seg = (N + nb - 1) / nb;
+    const long long lo = seg * blockIdx.x, hi = lo + seg < N ? lo + seg : N;
+    for (int h = 0; h < 2; h++) {
+        const double *row = long_row(prm, first, pair, h);
+        if (!row) continue;            // uniform over the block
+        double s = 0.0;
+        for (long long i = lo + threadIdx.x; i < hi; i += 256) s += row[i];
+        s = long_block_sum(s, red);
+        if (threadIdx.x == 0) long_part(prm, pairs_cap, pair, h, 0)[blockIdx.x] = s;
+    }
+}
+
+// Step 2: centred values with their partial sum of squares and the residual sum the corrected two-pass variance needs
+// (xcorr.go:88), written as z[j] = (y1[j], y2[j]) behind n - N zeros.
+__global__ void __launch_bounds__(256)
+long_load_kernel(const LongParams prm, long long first, long long pairs_cap, int nb, cd *__restrict__ z) {
+    __shared__ double red[8];
+    const long long pair = blockIdx.y;
     const long long n = 1ll << prm.log2n;
     const long long N = prm.N, pad = n - N;
-    const long long count = prm.count;
     cd *out = z + (size_t)pair * (size_t)n;
     const double *rows[2];
-    for (int h = 0; h < 2; h++) {
-        const long long pos = first + 2 * pair + h;
-        if (pos < count) {
-            const long long row = prm.idx ? (long long)prm.idx[pos] : pos;
-            rows[h] = prm.slab + (size_t)row * (size_t)prm.ld;
-        } else {
-            rows[h] = nullptr;
-        }
-    }
     double mu[2] = {0.0, 0.0};
     for (int h = 0; h < 2; h++) {
-        if (!rows[h]) continue;            // uniform over the block
+        rows[h] = long_row(prm, first, pair, h);
+        if (!rows[h]) continue;
+        const double *ps = long_part(prm, pairs_cap, pair, h, 0);
         double s = 0.0;
-        for (long long i = threadIdx.x; i < N; i += 256) s += rows[h][i];
-        mu[h] = long_block_sum(s, red) / (double)N;
+        for (int k = 0; k < nb; k++) s += ps[k];
+        mu[h] = s / (double)N;
     }
-    for (long long i = threadIdx.x; i < pad; i += 256) out[i] = cd{0.0, 0.0};
+    {   // this block's share of the leading zeros
+        const long long zseg = (pad + nb - 1) / nb, zlo = zseg * blockIdx.x, zhi = zlo + zseg < pad ? zlo + zseg : pad;
+        for (long long i = zlo + threadIdx.x; i < zhi; i += 256) out[i] = cd{0.0, 0.0};
+    }
+    const long long seg = (N + nb - 1) / nb;
+    const long long lo = seg * blockIdx.x, hi = lo + seg < N ? lo + seg : N;
     double ss[2] = {0.0, 0.0}, cp[2] = {0.0, 0.0};
-    for (long long i = threadIdx.x; i < N; i += 256) {
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
         cd v{0.0, 0.0};
         if (rows[0]) {
             v.x = rows[0][i] - mu[0];
@@ -94,10 +124,26 @@ long_load_kernel(const LongParams prm, long long first, long long pairs, cd *__r
         const double a = long_block_sum(ss[h], red);
         const double c = long_block_sum(cp[h], red);
         if (threadIdx.x == 0) {
-            prm.stats[2 * (2 * pair + h)] = a;
-            prm.stats[2 * (2 * pair + h) + 1] = c;
+            double *pp = long_part(prm, pairs_cap, pair, h, 1);
+            pp[2 * blockIdx.x] = a;
+            pp[2 * blockIdx.x + 1] = c;
         }
     }
+}
+
+// Step 3: stats[2 * (2 pair + h)] = (ss, comp) from the partials, in segment order.
+__global__ void __launch_bounds__(256)
+long_stats_kernel(const LongParams prm, long long pairs, long long pairs_cap, int nb) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= 2 * pairs) return;
+    const double *pp = long_part(prm, pairs_cap, i >> 1, (int)(i & 1), 1);
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < nb; k++) {
+        a += pp[2 * k];
+        c += pp[2 * k + 1];
+    }
+    prm.stats[2 * i] = a;
+    prm.stats[2 * i + 1] = c;
 }
 
 // One Stockham pass of radix R over every transform of the chunk: butterfly j of a transform reads
@@ -181,17 +227,17 @@ long_cc_kernel(const LongParams prm, const cd *__restrict__ W) {
     prm.out_score[k] = sd == 0.0 ? 0.0 : W[k].y * (1.0 / sd);      // W = swap(cc1 + i cc2)
 }
 
-// maxAbsIndex over all n lags (xcorr.go:39-50, :189) for both series of a pair, then finish_series.
+// maxAbsIndex over all n lags (xcorr.go:39-50, :189) for both series of a pair: partial peaks per segment of the lags ...
 __global__ void __launch_bounds__(256)
-long_peak_kernel(const LongParams prm, long long first, long long pairs, const cd *__restrict__ W) {
+long_peak_kernel(const LongParams prm, long long pairs_cap, int nb, const cd *__restrict__ W) {
     __shared__ double sa[2][256], sv[2][256];
     __shared__ int si[2][256];
-    const long long pair = blockIdx.x;
-    if (pair >= pairs) return;
+    const long long pair = blockIdx.y;
     const long long n = 1ll << prm.log2n;
+    const long long seg = (n + nb - 1) / nb, lo = seg * blockIdx.x, hi = lo + seg < n ? lo + seg : n;
     const cd *w = W + (size_t)pair * (size_t)n;
     Peak p0{0.0, 0.0, 0x7fffffff}, p1{0.0, 0.0, 0x7fffffff};
-    for (long long j = threadIdx.x; j < n; j += 256) {
+    for (long long j = lo + threadIdx.x; j < hi; j += 256) {
         const cd v = w[j];
         peak_merge(p0, fabs(v.y), v.y, (int)j);      // series 1: the real part of the un-swapped result
         peak_merge(p1, fabs(v.x), v.x, (int)j);
@@ -201,19 +247,31 @@ long_peak_kernel(const LongParams prm, long long first, long long pairs, const c
     __syncthreads();
     if (threadIdx.x < 2) {
         const int h = threadIdx.x;
-        const long long pos = first + 2 * pair + h;
-        if (pos < prm.count) {
-            Peak r{0.0, 0.0, 0x7fffffff};
-            for (int i = 0; i < 256; i++) peak_merge(r, sa[h][i], sv[h][i], si[h][i]);
-            const long long row = prm.idx ? (long long)prm.idx[pos] : pos;
-            double score;
-            int lag;
-            finish_series(r, prm.stats[2 * (2 * pair + h)], prm.stats[2 * (2 * pair + h) + 1], prm.N, (int)n, prm.signed_scores != 0,
-                          score, lag);
-            prm.out_score[row] = score;
-            prm.out_lag[row] = lag;
-        }
+        Peak r{0.0, 0.0, 0x7fffffff};
+        for (int i = 0; i < 256; i++) peak_merge(r, sa[h][i], sv[h][i], si[h][i]);
+        double *pk = long_part(prm, pairs_cap, pair, h, 2) + 3 * blockIdx.x;
+        pk[0] = r.a;
+        pk[1] = r.v;
+        pk[2] = (double)r.idx;
     }
+}
+
+// ... merged (lowest index wins ties, whatever the order), then finish_series.
+__global__ void __launch_bounds__(256)
+long_finish_kernel(const LongParams prm, long long first, long long pairs, long long pairs_cap, int nb) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= 2 * pairs) return;
+    const long long pos = first + i;
+    if (pos >= prm.count) return;
+    const double *pk = long_part(prm, pairs_cap, i >> 1, (int)(i & 1), 2);
+    Peak r{0.0, 0.0, 0x7fffffff};
+    for (int k = 0; k < nb; k++) peak_merge(r, pk[3 * k], pk[3 * k + 1], (int)pk[3 * k + 2]);
+    const long long row = prm.idx ? (long long)prm.idx[pos] : pos;
+    double score;
+    int lag;
+    finish_series(r, prm.stats[2 * i], prm.stats[2 * i + 1], prm.N, 1 << prm.log2n, prm.signed_scores != 0, score, lag);
+    prm.out_score[row] = score;
+    prm.out_lag[row] = lag;
 }
 
 // every transform of `transforms` consecutive n-point rows of buf[0] -> returns the buffer index holding the result
@@ -234,7 +292,7 @@ static int long_fft(cd *buf[2], int cur, const cd *tw, int log2n, long long tran
 }
 
 size_t long_work_bytes(int log2n, long long chunk_pairs) {
-    return 2 * sizeof(cd) * ((size_t)chunk_pairs << log2n) + sizeof(double) * 4 * (size_t)chunk_pairs;
+    return 2 * sizeof(cd) * ((size_t)chunk_pairs << log2n) + sizeof(double) * LONG_SCRATCH_PER_PAIR * (size_t)chunk_pairs;
 }
 
 cudaError_t launch_long_twiddles(cd *tw, int log2n, cudaStream_t st) {
@@ -252,9 +310,19 @@ cudaError_t launch_long(int mode, LongParams p, void *work, long long chunk_pair
     buf[1] = buf[0] + ((size_t)chunk_pairs << p.log2n);
     p.stats = reinterpret_cast<double *>(buf[1] + ((size_t)chunk_pairs << p.log2n));
     if (mode != MODE_SCORE) p.count = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     for (long long first = 0; first < p.count; first += 2 * chunk_pairs) {
         const long long pairs = std::min<long long>(chunk_pairs, (p.count - first + 1) / 2);
-        long_load_kernel<<<(unsigned)pairs, 256, 0, st>>>(p, first, pairs, buf[0]);
+        // segments per row: enough blocks for two per SM, at least 4096 samples each
+        int nb = (int)std::min<long long>(LONG_NB_MAX, std::max<long long>(1, (2 * sms + pairs - 1) / pairs));
+        nb = (int)std::max<long long>(1, std::min<long long>(nb, (long long)p.N / 4096));
+        const dim3 grid((unsigned)nb, (unsigned)pairs);
+        const unsigned small = (unsigned)((2 * pairs + 255) / 256);
+        long_sum_kernel<<<grid, 256, 0, st>>>(p, first, chunk_pairs, nb);
+        long_load_kernel<<<grid, 256, 0, st>>>(p, first, chunk_pairs, nb, buf[0]);
+        long_stats_kernel<<<small, 256, 0, st>>>(p, pairs, chunk_pairs, nb);
         int cur = long_fft(buf, 0, p.tw, p.log2n, pairs, st);
         if (mode == MODE_REF) {
             long_ref_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, buf[cur]);
@@ -267,7 +335,8 @@ cudaError_t launch_long(int mode, LongParams p, void *work, long long chunk_pair
             long_cc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, buf[cur]);
             return cudaGetLastError();
         }
-        long_peak_kernel<<<(unsigned)pairs, 256, 0, st>>>(p, first, pairs, buf[cur]);
+        long_peak_kernel<<<grid, 256, 0, st>>>(p, chunk_pairs, nb, buf[cur]);
+        long_finish_kernel<<<small, 256, 0, st>>>(p, first, pairs, chunk_pairs, nb);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

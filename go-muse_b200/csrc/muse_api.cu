@@ -145,7 +145,7 @@ struct muse_batch : RunScratch {
     muse_group *g;
     int64_t N, n;
     int log2m;
-    // fp32 screening pass (n = 512, 2048 .. 16384): the tables live in RunScratch
+    // fp32 screening pass (n = 128 .. 16384): the tables live in RunScratch
     int screen_ok;
     float a_mid;
     cf x_mid;
@@ -703,7 +703,7 @@ static bool block_small();
 static int screen_is_fused(int log2m) { return log2m >= (block_small() ? 8 : 6) && log2m <= 13; }
 static int screen_is_big(int log2m) { return log2m >= 11 && log2m <= 13; }      // muse_screen_big.cuh
 static int screen_log2m_supported(int log2m) { return screen_is_fused(log2m); }
-// n = 512 / 1024: several series per warp (muse_screen_sub.cuh); MUSE_BLOCK_SMALL=1 keeps round 1's block kernel for A/B runs
+// n = 128 .. 1024: several series per warp (muse_screen_sub.cuh); MUSE_BLOCK_SMALL=1 keeps round 1's block kernel for A/B runs
 static bool block_small() {
     static const bool v = getenv("MUSE_BLOCK_SMALL") != nullptr;
     return v;
@@ -1534,7 +1534,7 @@ extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t m
     if (rc) return rc;
     if (!upper || (refine && !lower)) return fail(MUSE_ERR_INVALID_ARG, "muse_batch_screen_bounds: NULL output");
     if (!b->screen_ok) return fail(MUSE_ERR_UNSUPPORTED, "no screening kernel for series length %lld", (long long)b->N);
-    if (refine && !screen_is_fused(b->log2m)) return fail(MUSE_ERR_UNSUPPORTED, "the fused refinement needs an FFT length of 2048 .. 16384");
+    if (refine && !screen_is_fused(b->log2m)) return fail(MUSE_ERR_UNSUPPORTED, "the fused refinement needs an FFT length of 128 .. 16384");
     CU(cudaSetDevice(b->ctx->device));
     rc = ensure_scratch(b);
     if (rc) return rc;

@@ -38,15 +38,17 @@ struct ScreenSubCfg {
     static constexpr int NREF = 2;                    // warp-wide exchange buffers of the second stage, under a lock
     static constexpr size_t SMEM_BUDGET = 227 * 1024;
     static constexpr size_t EX_SERIES = ((size_t)(G::MP + 1) * sizeof(cf) + 127) / 128 * 128;   // one series' padded exchange
-    static constexpr size_t EX_BYTES = (size_t)GS * EX_SERIES;
-    // the row buffers of a warp's series sit row_bytes apart: a multiple of 128 bytes plus a skew that spreads the
-    // series over the shared-memory banks (2 lanes x 16 bytes per series at T = 2: without it all 16 series of a warp
-    // hit the same 8 banks on every row read and every exchange)
+    // buffers of a warp's series sit a multiple of 128 bytes plus SKEW apart, which spreads the series over the
+    // shared-memory banks: without it the 16 series of a warp at T = 2 (2 lanes x 16 bytes each) hit the same 8 banks on
+    // every row read and every exchange.  Measured (kernel, 11.5 GB stores, skew 0 -> 8 T): n = 128 5.17 -> 2.48 ms,
+    // n = 256 3.08 -> 2.29 ms, n = 512 2.08 -> 1.92 ms, n = 1024 unchanged (MUSE_SUB_SKEW overrides, for such sweeps)
+    static constexpr int SKEW = (8 * T) % 128;
+    static constexpr size_t EX_STRIDE = EX_SERIES + SKEW;
+    static constexpr size_t EX_BYTES = (size_t)GS * EX_STRIDE;
     static size_t row_skew() {
         static const long env = getenv("MUSE_SUB_SKEW") ? atol(getenv("MUSE_SUB_SKEW")) : -1;
         return env >= 0 ? (size_t)env / 16 * 16 : (size_t)SKEW;
     }
-    static constexpr int SKEW = T >= 8 ? 0 : 16 * T;
     static size_t row_bytes(int N) {
         const size_t r = ((size_t)N * 8 + 127) / 128 * 128;
         return (r > EX_SERIES ? r : EX_SERIES) + row_skew();
@@ -243,7 +245,7 @@ score_screen_sub_kernel(const ScreenParams prm, const unsigned warp_bytes, const
             Dft<P, float>::run(u);
             {
                 const int slot = ex_acquire(ex_locks, lane, w);
-                cf *smr = reinterpret_cast<cf *>(refbase + (size_t)slot * C::EX_BYTES + (size_t)g * C::EX_SERIES);
+                cf *smr = reinterpret_cast<cf *>(refbase + (size_t)slot * C::EX_BYTES + (size_t)g * C::EX_STRIDE);
 #pragma unroll
                 for (int j = 0; j < P; j++) {
                     cf val = u[Perm<P>::at(j)];

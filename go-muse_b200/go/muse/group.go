@@ -63,6 +63,11 @@ type Group struct {
 	cols     []string                  // label key of each device column (the last column is all -1)
 	dict     map[string]map[string]int32
 	uploaded int
+
+	// sharded groups (exchange.go): index of this block's first series in the whole group, and the label dictionary
+	// every process agreed on
+	shardFirst int64
+	fixedDict  map[string][]string
 }
 
 // uploadChunk is the number of series handed to muse_group_append per call: the library copies the rows (through its
@@ -128,6 +133,9 @@ func (g *Group) syncDevice() error {
 		return err
 	}
 	keySet := map[string]struct{}{}
+	for k := range g.fixedDict { // sharded: every process has the same columns, whatever its own series carry
+		keySet[k] = struct{}{}
+	}
 	for _, s := range g.series {
 		for _, k := range s.lab.Keys() {
 			keySet[k] = struct{}{}
@@ -152,9 +160,17 @@ func (g *Group) syncDevice() error {
 		g.dict = make(map[string]map[string]int32)
 		for _, k := range keys {
 			g.dict[k] = make(map[string]int32)
+			for i, v := range g.fixedDict[k] {
+				g.dict[k][v] = int32(i)
+			}
 		}
 		if rc := C.muse_group_create(c, C.int64_t(g.n), C.int32_t(len(keys)+1), C.int64_t(len(g.series)), &g.store); rc != C.MUSE_OK {
 			return lastError(rc)
+		}
+		if g.shardFirst != 0 {
+			if rc := C.muse_group_set_global_offset(g.store, C.int64_t(g.shardFirst)); rc != C.MUSE_OK {
+				return lastError(rc)
+			}
 		}
 		g.uploaded = 0
 	}

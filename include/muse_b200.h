@@ -149,7 +149,7 @@ int  muse_group_read_rows(muse_group *g, int64_t first, int64_t n_rows, double *
  * (MUSE_ERR_LENGTH_MISMATCH), n = nextPowOf2(ref_len), computes on the device
  * X = rfft(zeroPad(zNormalize(ref)/(N-1), n)); std(ref)==0 -> MUSE_ERR_STDDEV_ZERO.
  * The reference row is copied; unlike go-muse nothing is mutated in place.
- * n <= MUSE_MAX_FUSED_FFT_LEN: one fused kernel scores a series from its row (fp32 screening for n = 512 .. 16384).
+ * n <= MUSE_MAX_FUSED_FFT_LEN: one fused kernel scores a series from its row (fp32 screening for n = 128 .. 16384).
  * Above (go-muse has no limit; BenchmarkXCorrWithX is n = 32768, xcorr_test.go:330-348): every series is scored in fp64 by
  * FFT passes through global memory, two series per complex transform, 256 MB of work space at a time. */
 int  muse_batch_create(muse_ctx *ctx, muse_group *g, const double *ref, int64_t ref_len,
@@ -190,7 +190,7 @@ int  muse_batch_score_all(muse_batch *b, int32_t signed_scores, double *scores, 
 
 /* Diagnostic: the fp32 screening pass alone.  upper[i] >= series i's score from
  * muse_batch_score_all (a value > 1, e.g. 2.0, means "undecided: ask the fp64 kernel").
- * refine != 0 (FFT lengths 512 .. 16384) sends EVERY series through the fused second stage
+ * refine != 0 (FFT lengths 128 .. 16384) sends EVERY series through the fused second stage
  * (fp32 inverse transform) for the lag window max_lag: upper[i] = -1 when the peak is
  * certainly outside the window (the series fails results.go:46-48), else a tight bound;
  * lower[i] >= 0 is a certain lower bound on the score of a series whose lag is certainly

@@ -218,3 +218,26 @@ def test_screen_error_survey_keeps_its_margins():
         assert r["fp32_vs_fp64_worst_abs_error"] <= slack / 4, r
         for k in ("spectral_bound_min_margin", "refined_upper_min_margin", "refined_lower_min_margin"):
             assert r[k] >= slack / 4, (k, r)
+
+
+def test_go_facade_binds_only_declared_symbols():
+    """The cgo facade cannot be compiled here (no Go toolchain): at least every C.muse_* function and C.MUSE_* constant it
+    names must be one include/muse_b200.h declares, and braces / parentheses must balance in every file."""
+    hdr = open(os.path.join(ROOT, "include", "muse_b200.h")).read()
+    declared = set(_declared_symbols())
+    consts = set(re.findall(r"#define\s+(MUSE_[A-Z0-9_]+)", hdr))
+    types = set(re.findall(r"typedef struct (muse_[a-z_]+)", hdr)) | {"muse_partial", "muse_timing"}
+    godir = os.path.join(ROOT, "go-muse_b200", "go", "muse")
+    used = set()
+    for name in sorted(os.listdir(godir)):
+        if not name.endswith(".go"):
+            continue
+        src = open(os.path.join(godir, name)).read()
+        code = re.sub(r"//[^\n]*", "", re.sub(r"/\*.*?\*/", "", src, flags=re.S))
+        code = re.sub(r'"(\\.|[^"\\])*"', '""', code)
+        for a, b in ("{}", "()", "[]"):
+            assert code.count(a) == code.count(b), (name, a, code.count(a), code.count(b))
+        for sym in re.findall(r"\bC\.(muse_[a-z0-9_]+|MUSE_[A-Z0-9_]+)", code):
+            used.add(sym)
+            assert sym in declared or sym in consts or sym in types, (name, sym)
+    assert {"muse_batch_run", "muse_group_append", "muse_batch_run_exchange_ex", "muse_exchange_open_peers"} <= used
