@@ -494,7 +494,8 @@ def main():
                 with open(tpath) as f:
                     tj = json.load(f)
                 key = used_mode if (args.workload, S, N) == ("c3", 1_000_000, 1440) and variant == 0 else \
-                    ("c4_grouped" if grouped else "c4_ungrouped") if (args.workload, S, N) == ("c4", 1_250_000, 10080) else None
+                    ("c4_grouped" if grouped else "c4_ungrouped") if (args.workload, S, N) == ("c4", 1_250_000, 10080) else \
+                    "n512" if (args.workload, S, N, used_mode) == ("c3", 3_000_000, 480, "screen") else None
                 traffic = tj.get(key, {}).get("dram_bytes_per_launch") if key else None
             except Exception:
                 traffic = None

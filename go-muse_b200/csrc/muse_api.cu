@@ -96,6 +96,7 @@ struct RunScratch {
     float2 *swtw;                     // split twiddles exp(-2*pi*i*k/n), k < M/2, fp32
     float4 *sw_f;                     // fused kernels: (twn, A[k], A[M-k]) per k < M/2
     float4 *sx_f;                     // fused refinement: (Xt[k], Xt[M-k]) in fp32 per k < M/2
+    float *sb_f;                      // warp / sub-warp kernels: sqrt(2 (A[k]^2 + A[M-k]^2)) rounded up per k < M/2
     float *d_mid;                     // [0] std-zero flag of the reference (as float bits), [1] A[M/2], [2..3] Xt[M/2] in fp32
     cudaEvent_t ev[4];
     cudaStream_t aux;                 // the batch's own stream: the tails of the queries of a multi-query launch run side by side
@@ -209,7 +210,7 @@ static void scratch_free(RunScratch &r) {
     cudaFree(r.d_gmax); cudaFree(r.d_hkeys); cudaFree(r.d_gidx);
     cudaFree(r.d_flag); cudaFree(r.d_counters); cudaFree(r.d_sel); cudaFree(r.d_cut);
     cudaFree(r.d_ref); cudaFree(r.Xt); cudaFree(r.twM); cudaFree(r.twn);
-    cudaFree(r.twp_f); cudaFree(r.twi_f); cudaFree(r.twide_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.d_mid);
+    cudaFree(r.twp_f); cudaFree(r.twi_f); cudaFree(r.twide_f); cudaFree(r.swtw); cudaFree(r.sw_f); cudaFree(r.sx_f); cudaFree(r.sb_f); cudaFree(r.d_mid);
     for (int i = 0; i < 4; i++) if (r.ev[i]) cudaEventDestroy(r.ev[i]);
     if (r.aux) cudaStreamDestroy(r.aux);
     if (r.h_pin) cudaFreeHost(r.h_pin);
@@ -715,7 +716,8 @@ static int screen_log2p(int log2m) { return (log2m >= 10 || !block_small()) ? 5 
 // mirror pair (k, M-k), k < M/2, with the split twiddle exp(-2*pi*i*k/n); the two reference coefficients of the
 // second stage; and A[M/2], Xt[M/2] for the host (kernel parameters).
 __global__ void screen_tables_kernel(const cd *__restrict__ Xt, int M, const float2 *__restrict__ swtw, float4 *__restrict__ sw,
-                                     float4 *__restrict__ sx, float *__restrict__ mid, const int32_t *__restrict__ std_zero) {
+                                     float4 *__restrict__ sx, float *__restrict__ sb, float *__restrict__ mid,
+                                     const int32_t *__restrict__ std_zero) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > M / 2) return;
     if (k == 0) mid[0] = __int_as_float(*std_zero);      // the reference's std-zero flag rides along: one copy to the host
@@ -731,6 +733,7 @@ __global__ void screen_tables_kernel(const cd *__restrict__ Xt, int M, const flo
     const float2 w = swtw[k];
     sw[k] = make_float4(w.x, w.y, wa, wc);
     sx[k] = make_float4((float)a.x, (float)a.y, (float)c.x, (float)c.y);
+    sb[k] = __double2float_ru(sqrt(2.0 * ((double)wa * (double)wa + (double)wc * (double)wc)) * (1.0 + 1e-15));
 }
 
 // Twiddle tables of FFT length n (they depend on n alone): filled when the scratch set was last used for another n.
@@ -747,9 +750,9 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
     const bool want_screen = screen_log2m_supported(b->log2m);
     if (b->tab_n == n && (b->tab_screen || !want_screen)) return MUSE_OK;
     if (b->is_long) {      // the reference's transform has n entries, the twiddles are generated on the device
-        cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->twide_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
+        cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->twide_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f); cudaFree(b->sb_f);
         b->Xt = b->twM = b->twn = nullptr;
-        b->twp_f = b->twi_f = b->twide_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
+        b->twp_f = b->twi_f = b->twide_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr; b->sb_f = nullptr;
         b->tab_n = 0;
         b->tab_screen = 0;
         CU(cudaMalloc(&b->Xt, sizeof(cd) * (size_t)n));
@@ -758,9 +761,9 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
         b->tab_n = n;
         return MUSE_OK;
     }
-    cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->twide_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f);
+    cudaFree(b->Xt); cudaFree(b->twM); cudaFree(b->twn); cudaFree(b->twp_f); cudaFree(b->twi_f); cudaFree(b->twide_f); cudaFree(b->swtw); cudaFree(b->sw_f); cudaFree(b->sx_f); cudaFree(b->sb_f);
     b->Xt = b->twM = b->twn = nullptr;
-    b->twp_f = b->twi_f = b->twide_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr;
+    b->twp_f = b->twi_f = b->twide_f = nullptr; b->swtw = nullptr; b->sw_f = b->sx_f = nullptr; b->sb_f = nullptr;
     b->tab_n = 0;
     b->tab_screen = 0;
     const long double PI2 = 6.283185307179586476925286766559005768L;
@@ -806,6 +809,7 @@ static int ensure_ref_tables(muse_batch *b, int64_t ld) {
         CU(cudaMalloc(&b->swtw, sizeof(float2) * swtw.size()));
         CU(cudaMalloc(&b->sw_f, sizeof(float4) * (size_t)(M / 2)));
         CU(cudaMalloc(&b->sx_f, sizeof(float4) * (size_t)(M / 2)));
+        CU(cudaMalloc(&b->sb_f, sizeof(float) * (size_t)(M / 2)));
         CU(cudaMemcpyAsync(b->twp_f, twp.data(), sizeof(cf) * twp.size(), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(b->swtw, swtw.data(), sizeof(float2) * swtw.size(), cudaMemcpyHostToDevice, st));
     }
@@ -935,7 +939,7 @@ static int batch_create_queue(muse_ctx *ctx, muse_group *g, const double *ref, i
     b->screen_ok = 0;
     const bool screen = b->tab_screen != 0;
     if (screen) {
-        screen_tables_kernel<<<(unsigned)((M / 2 + 1 + 255) / 256), 256, 0, st>>>(b->Xt, (int)M, b->swtw, b->sw_f, b->sx_f, b->d_mid, b->d_flag);
+        screen_tables_kernel<<<(unsigned)((M / 2 + 1 + 255) / 256), 256, 0, st>>>(b->Xt, (int)M, b->swtw, b->sw_f, b->sx_f, b->sb_f, b->d_mid, b->d_flag);
         CUB(cudaGetLastError());
     }
     // one round trip: the std-zero flag of the reference and the two middle-bin values the kernels take by value
@@ -1416,6 +1420,7 @@ static ScreenParams screen_params(muse_batch *b) {
     sp.a_mid = b->a_mid;
     sp.out_U = b->d_U;
     sp.sx = b->sx_f;
+    sp.sb = b->sb_f;
     sp.twi = b->twi_f;
     sp.x_mid = b->x_mid;
     sp.row_stat = b->g->row_stat;
@@ -1508,6 +1513,7 @@ struct TablesArgs {
     const cd *Xt;
     float4 *sw, *sx;
     const int32_t *std_zero;
+    float *sb;
 };
 __global__ void screen_tables_batch_kernel(const TablesArgs *__restrict__ args, int M, const float2 *__restrict__ swtw, float *__restrict__ mids) {
     const TablesArgs a = args[blockIdx.y];
@@ -1527,6 +1533,7 @@ __global__ void screen_tables_batch_kernel(const TablesArgs *__restrict__ args, 
     const float2 w = swtw[k];
     a.sw[k] = make_float4(w.x, w.y, wa, wc);
     a.sx[k] = make_float4((float)x.x, (float)x.y, (float)c.x, (float)c.y);
+    a.sb[k] = __double2float_ru(sqrt(2.0 * ((double)wa * (double)wa + (double)wc * (double)wc)) * (1.0 + 1e-15));
 }
 
 extern "C" int muse_batch_screen_bounds(muse_batch *b, int32_t refine, int64_t max_lag, float *upper, float *lower) {
@@ -2204,7 +2211,7 @@ static int multi_run_tc_group(muse_ctx *ctx, muse_group *g, const double *refs, 
         p.twn = b->twn;
         p.out_X = b->Xt;
         p.out_flag = b->d_flag;
-        h_ta[i] = TablesArgs{b->Xt, b->sw_f, b->sx_f, b->d_flag};
+        h_ta[i] = TablesArgs{b->Xt, b->sw_f, b->sx_f, b->d_flag, b->sb_f};
         h_cut[i] = b->d_cut;
     }
     const int64_t M = bs[0]->n / 2;

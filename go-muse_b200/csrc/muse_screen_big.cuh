@@ -175,12 +175,29 @@ MUSE_HD void big_split_acc(cf zk, cf zm, float4 s, cf &acc2) {
     acc2 = pfma(mag, cf{s.z, s.w}, acc2);
 }
 
+// The pair bound of muse_screen.cuh on the same pair: |2Y_k| A[k] + |2Y_(M-k)| A[M-k] <= sqrt(|e|^2 + |d|^2) B[k'].
+MUSE_HD void big_pair_acc(cf zk, cf zm, float b, cf &acc2) {
+    const cf zmc = cconj(zm);
+    const cf e = cadd(zk, zmc);
+    const cf d = csub(zk, zmc);
+    const cf q = pfma(d, d, pmul(e, e));
+    acc2.x = fmaf(big_sqrt(q.x + q.y), b, acc2.x);
+}
+// PAIR: the cheaper, looser pair bound (what the kernel uses: 45.8 -> 43.0 ms per 1.25 M x 10080 ungrouped, 48.0 -> 46.4 ms
+// grouped, with 27 % more second stages); !PAIR: the bin-by-bin sum (MUSE_BIG_BINS builds, and the CPU emulation's reference)
+#define MUSE_BIG_ACC(zk, zm, idx)                                        \
+    do {                                                                 \
+        if constexpr (PAIR) big_pair_acc(zk, zm, sb[idx], acc2);         \
+        else big_split_acc(zk, zm, big_load_f4(sw + (idx)), acc2);       \
+    } while (0)
+
 // The thread's share of sum_k |2Y_k| A_k, from the registers big_fwd_last left.  Pair slot c2, index j:
 // k = u + 1024 j sits in lo[Perm(j)], its mirror M - k = (1024 - u) + 1024 (R-1-j) in hi[Perm(R-1-j)]; the table
 // entry is that of k' = min(k, M - k).  u == 0 (thread 0, slot 0): butterfly 0 pairs j with R - j (j = 0: DC and
 // Nyquist; j = R/2: bin M/2, its own mirror, |2Y| = 2|Z|), butterfly 512 pairs j with R-1-j.
-template <int LOG2M>
-MUSE_HD float big_split_bound(const cf *v, int t, const float4 *sw, float a_mid) {
+template <int LOG2M, bool PAIR = false>
+MUSE_HD float big_split_bound(const cf *v, int t, const float4 *sw, float a_mid, const float *sb = nullptr) {
+    (void)sb;
     using C = ScreenBigCfg<LOG2M>;
     constexpr int R = C::R, M = C::M;
     cf acc2{0.f, 0.f};
@@ -190,22 +207,22 @@ MUSE_HD float big_split_bound(const cf *v, int t, const float4 *sw, float a_mid)
         const int u = t + C::T * c2;
         const cf *lo = v + (2 * c2) * R, *hi = v + (2 * c2 + 1) * R;
         if (c2 == 0 && u == 0) {
-            big_split_acc(lo[Perm<R>::at(0)], lo[Perm<R>::at(0)], big_load_f4(sw), acc2);
+            MUSE_BIG_ACC(lo[Perm<R>::at(0)], lo[Perm<R>::at(0)], 0);
 #pragma unroll
-            for (int j = 1; j < R / 2; j++) big_split_acc(lo[Perm<R>::at(j)], lo[Perm<R>::at(R - j)], big_load_f4(sw + 1024 * j), acc2);
+            for (int j = 1; j < R / 2; j++) MUSE_BIG_ACC(lo[Perm<R>::at(j)], lo[Perm<R>::at(R - j)], 1024 * j);
             {
                 const cf z = lo[Perm<R>::at(R / 2)];
                 const cf q = pmul(z, z);
                 extra = big_sqrt(q.x + q.y) * (2.f * a_mid);
             }
 #pragma unroll
-            for (int j = 0; j < R / 2; j++) big_split_acc(hi[Perm<R>::at(j)], hi[Perm<R>::at(R - 1 - j)], big_load_f4(sw + 512 + 1024 * j), acc2);
+            for (int j = 0; j < R / 2; j++) MUSE_BIG_ACC(hi[Perm<R>::at(j)], hi[Perm<R>::at(R - 1 - j)], 512 + 1024 * j);
         } else {
 #pragma unroll
             for (int j = 0; j < R; j++) {
                 const cf a = lo[Perm<R>::at(j)], b = hi[Perm<R>::at(R - 1 - j)];
-                if (j < R / 2) big_split_acc(a, b, big_load_f4(sw + u + 1024 * j), acc2);
-                else big_split_acc(b, a, big_load_f4(sw + (M - u - 1024 * j)), acc2);
+                if (j < R / 2) MUSE_BIG_ACC(a, b, u + 1024 * j);
+                else MUSE_BIG_ACC(b, a, M - u - 1024 * j);
             }
         }
     }
@@ -410,7 +427,11 @@ score_screen_big_kernel(const ScreenParams prm) {
         big_fwd_last<LOG2M>(v, sm, t);
 
         // ---- bound ----
-        float acc = big_split_bound<LOG2M>(v, t, prm.sw, prm.a_mid);
+#if defined(MUSE_BIG_BINS)
+        float acc = big_split_bound<LOG2M, false>(v, t, prm.sw, prm.a_mid, prm.sb);
+#else
+        float acc = big_split_bound<LOG2M, true>(v, t, prm.sw, prm.a_mid, prm.sb);
+#endif
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
         if ((t & 31) == 0) red_f[0][t >> 5].x = acc;

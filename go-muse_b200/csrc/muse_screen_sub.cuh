@@ -43,6 +43,10 @@ struct ScreenSubCfg {
     // every row read and every exchange.  Measured (kernel, 11.5 GB stores, skew 0 -> 8 T): n = 128 5.17 -> 2.48 ms,
     // n = 256 3.08 -> 2.29 ms, n = 512 2.08 -> 1.92 ms, n = 1024 unchanged (MUSE_SUB_SKEW overrides, for such sweeps)
     static constexpr int SKEW = (8 * T) % 128;
+    // The cheaper pair bound (muse_screen.cuh) pays where the kernel is bound by instruction issue and costs where it is
+    // bound by HBM (it doubles the second stages).  Measured, bin-by-bin sum -> pair bound: n = 128 2.41 -> 2.21 ms,
+    // n = 256 2.17 -> 1.97 ms, n = 512 1.84 -> 1.89 ms, n = 1024 1.82 -> 1.84 ms (and n = 2048 2.18 -> 2.11 ms).
+    static constexpr bool PAIR_BOUND = LOG2T <= 2;
     static constexpr size_t EX_STRIDE = EX_SERIES + SKEW;
     static constexpr size_t EX_BYTES = (size_t)GS * EX_STRIDE;
     static size_t row_skew() {
@@ -166,8 +170,8 @@ score_screen_sub_kernel(const ScreenParams prm, const unsigned warp_bytes, const
 #pragma unroll
         for (int c = 0; c < GS; c++) Dft<T, float>::run(v + c * T);        // v[reg(m)] = Z[t + T*m]
 
-        // ---- |2Y_k| and |2Y_(M-k)| for k = t + T*m, m < 16 ----
-        cf acc2{0.f, 0.f};
+        // ---- the bound over the mirror pairs (k, M-k), k = t + T*m, m < 16 ----
+        float acc = 0.f;
 #pragma unroll
         for (int m = 0; m < P / 2; m++) {
             const cf zk = v[C::reg(m)];
@@ -178,18 +182,23 @@ score_screen_sub_kernel(const ScreenParams prm, const unsigned warp_bytes, const
             src.y = lane0 ? zs.y : zp.y;
             zm.x = __shfl_sync(0xffffffffu, src.x, partner, T);
             zm.y = __shfl_sync(0xffffffffu, src.y, partner, T);
-            const float4 sv = prm.sw[t + T * m];
             const cf zmc = cconj(zm);
             const cf e = cadd(zk, zmc);
-            const cf o = cmul_negi(csub(zk, zmc));
-            const cf wo = cmul(o, cf{sv.x, sv.y});
-            const cf y1 = cadd(e, wo);
-            const cf y2 = csub(e, wo);
-            const cf q1 = pmul(y1, y1), q2 = pmul(y2, y2);
-            const cf mag{sqrt_approx(q1.x + q1.y), sqrt_approx(q2.x + q2.y)};
-            acc2 = pfma(mag, cf{sv.z, sv.w}, acc2);
+            if constexpr (C::PAIR_BOUND) {
+                // the pair bound of score_screen_warp_kernel: |2Y_k| A[k] + |2Y_(M-k)| A[M-k] <= sqrt(|e|^2 + |d|^2) B[k]
+                const cf d = csub(zk, zmc);
+                const cf q = pfma(d, d, pmul(e, e));
+                acc = fmaf(sqrt_approx(q.x + q.y), prm.sb[t + T * m], acc);
+            } else {
+                const float4 sv = prm.sw[t + T * m];            // (w_k.x, w_k.y, A[k], A[M-k])
+                const cf o = cmul_negi(csub(zk, zmc));
+                const cf wo = cmul(o, cf{sv.x, sv.y});
+                const cf y1 = cadd(e, wo);                      // 2*Y_k
+                const cf y2 = csub(e, wo);                      // 2*conj(Y_(M-k))
+                const cf q1 = pmul(y1, y1), q2 = pmul(y2, y2);
+                acc = fmaf(sqrt_approx(q1.x + q1.y), sv.z, fmaf(sqrt_approx(q2.x + q2.y), sv.w, acc));
+            }
         }
-        float acc = acc2.x + acc2.y;
         {   // k = M/2: lane 0 of the group, slot 16
             const cf z = v[C::reg(P / 2)];
             const cf q = pmul(z, z);

@@ -107,6 +107,18 @@ static int run_case(int N, unsigned seed, int max_lag) {
     for (int t = 0; t < T; t++) big_fwd_last<LOG2M>(regs[t].data(), sm.data(), t);
     double acc = 0;
     for (int t = 0; t < T; t++) acc += big_split_bound<LOG2M>(regs[t].data(), t, sw.data(), a_mid);
+    // the pair bound the kernel takes: sum over mirror pairs of sqrt(|2Y_k|^2 + |2Y_(M-k)|^2) sqrt(A_k^2 + A_(M-k)^2), + bin M/2
+    std::vector<float> sb(M / 2);
+    long double pair_want = 0;
+    for (int k = 0; k < M / 2; k++) {
+        const long double wa = sw[k].z, wc = sw[k].w;
+        sb[k] = (float)std::sqrt((double)(2.0L * (wa * wa + wc * wc))) * (1.f + 1e-6f);
+        const long double yk = 2.0L * std::abs(yt[k]), ym2 = 2.0L * std::abs(yt[M - k]);     // |2Y_k|, |2Y_(M-k)| (k = 0: DC, Nyquist)
+        pair_want += std::sqrt((double)(yk * yk + ym2 * ym2)) * std::sqrt((double)(wa * wa + wc * wc));
+    }
+    pair_want += 2.0L * std::abs(yt[M / 2]) * a_mid;
+    double acc_pair = 0;
+    for (int t = 0; t < T; t++) acc_pair += big_split_bound<LOG2M, true>(regs[t].data(), t, sw.data(), a_mid, sb.data());
     for (int t = 0; t < T; t++) big_pointwise<LOG2M>(regs[t].data(), t, sw.data(), sx.data(), x_mid);
     for (int t = 0; t < T; t++) big_inv_pass0<LOG2M>(regs[t].data(), sm.data(), t, twi.data());
     for (int t = 0; t < T; t++) big_inv_pass1_load<LOG2M>(regs[t].data(), sm.data(), t);
@@ -122,7 +134,9 @@ static int run_case(int N, unsigned seed, int max_lag) {
     }
     const double e_bound = std::fabs(acc - (double)bound) / ysd;
     const double e_in = std::fabs(k_in - w_in) / ysd, e_out = std::fabs(k_out - w_out) / ysd;
-    const bool ok = e_bound < 2e-5 && e_in < 2e-5 && e_out < 2e-5;
+    const double e_pair = std::fabs(acc_pair - (double)pair_want) / ysd;
+    const bool ok = e_bound < 2e-5 && e_in < 2e-5 && e_out < 2e-5 && e_pair < 2e-5 && acc_pair >= acc * (1.0 - 1e-6);
+    printf("pair bound %.6f (err %.2e)  ", (double)pair_want / ysd, e_pair);
     printf("n=%5d N=%5d max_lag=%4d  bound %.6f (err %.2e)  in %.6f (err %.2e)  out %.6f (err %.2e)  %s\n", n, N, max_lag,
            (double)bound / ysd, e_bound, w_in / ysd, e_in, w_out / ysd, e_out, ok ? "ok" : "FAIL");
     return ok ? 0 : 1;

@@ -17,7 +17,7 @@ from test_gpu_screen import _adversarial  # noqa: E402
 SLACK = 2e-4
 ctx = mb.default_context(0)
 rows = []
-for N in (300, 480, 512, 1000, 1024, 1026, 1440, 1441, 2047, 2048, 2500, 4096, 5000, 8192, 10080, 10081, 16384):
+for N in (66, 100, 128, 200, 255, 256, 300, 480, 512, 1000, 1024, 1026, 1440, 1441, 2047, 2048, 2500, 4096, 5000, 8192, 10080, 10081, 16384):
     rng = np.random.default_rng(1000 + N)
     S = 12000 if N <= 2048 else 3000
     Y = _adversarial(rng, S, N)
