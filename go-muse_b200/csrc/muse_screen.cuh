@@ -95,6 +95,29 @@ struct ScreenParams {
     signed char *out_W;   // grouped runs: [count] 1 = peak certainly inside the lag window, -1 = certainly outside, 0 = undecided
 };
 
+// ---- maxima of |cc'| inside / outside the lag window (rotated index: (idx - win_lo) mod n <= win_len) ----
+// A register pair r holds (cc'[idx + 1], cc'[idx]).  The pairs of one ROW of the transform's output (one register slot
+// over the threads of a series) cover row_len consecutive lags starting at `off`; whether any of them can be inside
+// the window depends on the row alone, i.e. on kernel parameters: the test runs on the uniform datapath and all but the
+// two or three rows the window touches take one 3-input max per pair instead of two compares, two masks and four
+// selects.  Used by the block kernel of muse_screen_big.cuh (C4: 43.0 -> 42.1 ms ungrouped, 46.1 -> 45.0 ms grouped); in the
+// warp kernels the 32 uniform branches cost more than they save (C3 2.10 -> 2.17 ms, C5's second stages 39.3 -> 42.3 ms).
+MUSE_HD bool window_row_hit(int off, int row_len, int win_lo, int win_len, int n) {
+    const int d = (off - win_lo) & (n - 1);
+    return d <= win_len || d > n - row_len;
+}
+MUSE_HD void window_pair(cx<float> r, int idx, int win_len, int nmask, bool hit, float &m_in, float &m_out) {
+    const float a0 = fabsf(r.y), a1 = fabsf(r.x);
+    if (hit) {
+        const bool in0 = (idx & nmask) <= win_len;
+        const bool in1 = ((idx + 1) & nmask) <= win_len;
+        m_in = fmaxf(m_in, fmaxf(in0 ? a0 : 0.f, in1 ? a1 : 0.f));
+        m_out = fmaxf(m_out, fmaxf(in0 ? 0.f : a0, in1 ? 0.f : a1));
+    } else {
+        m_out = fmaxf(m_out, fmaxf(a0, a1));
+    }
+}
+
 #if defined(__CUDACC__)
 
 template <int T>

@@ -347,13 +347,9 @@ MUSE_HD void big_window_max(const cf *v, int t, int win_lo, int win_len, float &
     const int base = 2 * t - win_lo;
 #pragma unroll
     for (int j = 0; j < 32; j++) {
-        const cf r = v[Perm<32>::at(j)];
         const int off = 2 * C::T * j;
-        const bool in0 = ((base + off) & (2 * C::M - 1)) <= win_len;
-        const bool in1 = ((base + off + 1) & (2 * C::M - 1)) <= win_len;
-        const float a0 = fabsf(r.y), a1 = fabsf(r.x);
-        m_in = fmaxf(m_in, fmaxf(in0 ? a0 : 0.f, in1 ? a1 : 0.f));
-        m_out = fmaxf(m_out, fmaxf(in0 ? 0.f : a0, in1 ? 0.f : a1));
+        window_pair(v[Perm<32>::at(j)], base + off, win_len, 2 * C::M - 1, window_row_hit(off, 2 * C::T, win_lo, win_len, 2 * C::M), m_in,
+                    m_out);
     }
 }
 
