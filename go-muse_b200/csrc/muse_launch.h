@@ -30,6 +30,11 @@ cudaError_t launch_screen_sub3(const ScreenParams &p, int sm_count, cudaStream_t
 cudaError_t launch_screen_sub4(const ScreenParams &p, int sm_count, cudaStream_t st);
 // n = 4096 .. 16384 (muse_screen_big.cuh)
 cudaError_t launch_screen_big(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st);
+// n = 16384: nz = rows of 256 complex slots that hold samples, 17 .. 32, four per translation unit
+cudaError_t launch_screen_big13_a(int nz, const ScreenParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_screen_big13_b(int nz, const ScreenParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_screen_big13_c(int nz, const ScreenParams &p, int sm_count, cudaStream_t st);
+cudaError_t launch_screen_big13_d(int nz, const ScreenParams &p, int sm_count, cudaStream_t st);
 // n = 16384 at twice the occupancy (muse_screen_wide.cuh); its twiddle tables are fill_wide_twiddles'
 cudaError_t launch_screen_wide(const ScreenParams &p, int sm_count, cudaStream_t st);
 // the same pass for up to ScreenMultiCfg::QC reference queries at once (n = 2048)
