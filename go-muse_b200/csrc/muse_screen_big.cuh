@@ -45,7 +45,23 @@ struct ScreenBigCfg {
     // exchange buffer: forward and inverse pass 1' -> 2' use pad5 (one spare element per 32), inverse pass 0' -> 1'
     // uses padR (one spare element per R)
     static constexpr int SM_ELEMS = M + (M >> LR) + 2;
+    static constexpr size_t EX_BYTES = ((size_t)SM_ELEMS * 8 + 127) / 128 * 128;
+    // Table loads were the kernel's long-scoreboard stalls: two blocks' exchange buffers leave 64 KB of L1, and only 35 % of
+    // the table sectors hit it.  Measured per 1.25 M x 10080 (ungrouped / grouped), tables in shared memory: none 39.9 / 42.9 ms,
+    // forward twiddles 38.8 / 41.3 ms (the default), + sb 40.4 / 43.2 ms, + inverse twiddles 41.0 / 43.5 ms (what is left of L1
+    // is then too small for the rest).
+#ifndef MUSE_BIG_SMEM_TW
+#define MUSE_BIG_SMEM_TW 1
+#endif
+#if MUSE_BIG_SMEM_TW
+    // the forward passes' twiddles (TWF0, TWF1: 22.5 KB at n = 16384) ride in shared memory behind the exchange buffer;
+    // MUSE_BIG_SMEM_TW = 2: the pair-bound weights sb too (16 KB); 3: the inverse passes' twiddles instead (16 KB)
+    static constexpr int TW_SMEM = MUSE_BIG_SMEM_TW == 3 ? (10 * T + 31 * (T / 32) + 1024 + 31 * 32) : (10 * T + 31 * (T / 32));
+    static constexpr size_t SB_SMEM = MUSE_BIG_SMEM_TW == 2 ? (size_t)(M / 2) * 4 : 0;
+    static constexpr size_t SMEM = EX_BYTES + (size_t)TW_SMEM * 8 + SB_SMEM;
+#else
     static constexpr size_t SMEM = (size_t)SM_ELEMS * 8;
+#endif
     // fp32 twiddle tables of this kernel, ONE array (fill_big_twiddles), sized to stay L1-resident next to two blocks'
     // exchange buffers (a full W_M^(j t) table is 64 KB at n = 16384 and every load of it went to L2):
     //   forward pass 0: W_M^(j t) = W_M^(8 a t) * W_M^(b t), j = 8 a + b:   A [3 x T] (a = 1..3), B [7 x T] (b = 1..7)
@@ -376,6 +392,21 @@ score_screen_big_kernel(const ScreenParams prm) {
     __shared__ float2 red_f[2][NW];                  // block reductions, double-buffered by use
     __shared__ unsigned bc_word[2];                  // running cut-off and the group's running lower bound, from thread 0
     cf *sm = reinterpret_cast<cf *>(smem_raw);
+#if MUSE_BIG_SMEM_TW
+    cf *s_tw = reinterpret_cast<cf *>(smem_raw + C::EX_BYTES);
+    for (int i = threadIdx.x; i < C::TW_SMEM; i += C::T) s_tw[i] = prm.twi[i];
+    float *s_sb = reinterpret_cast<float *>(s_tw + C::TW_SMEM);
+    if (C::SB_SMEM)
+        for (int i = threadIdx.x; i < C::M / 2; i += C::T) s_sb[i] = prm.sb[i];
+    __syncthreads();
+    const cf *twf = s_tw;
+    const cf *twinv = MUSE_BIG_SMEM_TW == 3 ? s_tw : prm.twi;
+    const float *sbp = C::SB_SMEM ? s_sb : prm.sb;
+#else
+    const cf *twf = prm.twi;
+    const cf *twinv = prm.twi;
+    const float *sbp = prm.sb;
+#endif
 
     const int t = threadIdx.x;
     const int N = prm.N;
@@ -428,19 +459,19 @@ if constexpr (NZ > 0) {
         }
 
         // ---- forward FFT_M; ends with Z in registers in mirror-paired order ----
-        big_fwd_pass0<LOG2M, NZ == 0 ? 32 : NZ>(v, sm, t, prm.twi);
+        big_fwd_pass0<LOG2M, NZ == 0 ? 32 : NZ>(v, sm, t, twf);
         __syncthreads();
         big_load_stride_t<LOG2M>(v, sm, t);
         __syncthreads();
-        big_fwd_pass1<LOG2M>(v, sm, t, prm.twi);
+        big_fwd_pass1<LOG2M>(v, sm, t, twf);
         __syncthreads();
         big_fwd_last<LOG2M>(v, sm, t);
 
         // ---- bound ----
 #if defined(MUSE_BIG_BINS)
-        float acc = big_split_bound<LOG2M, false>(v, t, prm.sw, prm.a_mid, prm.sb);
+        float acc = big_split_bound<LOG2M, false>(v, t, prm.sw, prm.a_mid, sbp);
 #else
-        float acc = big_split_bound<LOG2M, true>(v, t, prm.sw, prm.a_mid, prm.sb);
+        float acc = big_split_bound<LOG2M, true>(v, t, prm.sw, prm.a_mid, sbp);
 #endif
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -463,11 +494,11 @@ if constexpr (NZ > 0) {
         signed char W = 0;
         if (U >= cut_now && U >= lg_now && U < 1.5f) {               // block-uniform
             big_pointwise<LOG2M>(v, t, prm.sw, prm.sx, prm.x_mid);
-            big_inv_pass0<LOG2M>(v, sm, t, prm.twi);
+            big_inv_pass0<LOG2M>(v, sm, t, twinv);
             __syncthreads();
             big_inv_pass1_load<LOG2M>(v, sm, t);
             __syncthreads();
-            big_inv_pass1<LOG2M>(v, sm, t, prm.twi);
+            big_inv_pass1<LOG2M>(v, sm, t, twinv);
             __syncthreads();
             big_load_stride_t<LOG2M>(v, sm, t);
             Dft<32, float>::run(v);
