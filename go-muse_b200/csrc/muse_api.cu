@@ -1174,6 +1174,7 @@ struct RunArgs {
     double threshold;
     int32_t sign_filter, mode, signed_scores;
     int32_t list_only;   // fused runs: the caller reads scores only through the exact list (no NaN fill of the score array)
+    int32_t group_cut;   // grouped fused runs whose top-N is final here (one GPU): members below the top_n-th certain group need no exact score
 };
 
 struct Rec {
@@ -1634,7 +1635,15 @@ static int score_fused_grouped(muse_batch *b, const RunArgs &a) {
         group_lower_bound_kernel<<<blocks, 256, 0, st>>>(gt, kc, b->d_L, S, b->d_slot);
         b->timing.n_launches++;
     }
-    group_contenders_kernel<<<blocks, 256, 0, st>>>(gt, b->d_U, S, b->d_slot, thr_lo, b->d_list, b->d_counters + 2);
+    const unsigned *cut_bits = nullptr;
+    if (running && a.group_cut && a.top_n > 0 && a.top_n < 0x7fffffff && !getenv("MUSE_NO_GROUP_CUT")) {
+        group_uncertain_kernel<<<blocks, 256, 0, st>>>(gt, b->d_U, b->d_W, S, b->d_slot);
+        group_cut_count_kernel<<<(unsigned)((gt.slots + 255) / 256), 256, 0, st>>>(gt, a.threshold, b->d_cut + 4);
+        group_cut_find_kernel<<<1, 32, 0, st>>>(b->d_cut + 4, (int)a.top_n, b->d_cut);
+        b->timing.n_launches += 3;
+        cut_bits = b->d_cut;
+    }
+    group_contenders_kernel<<<blocks, 256, 0, st>>>(gt, b->d_U, S, b->d_slot, thr_lo, b->d_list, b->d_counters + 2, cut_bits);
     b->timing.n_launches++;
     CU(cudaGetLastError());
     unsigned long long *h_n = reinterpret_cast<unsigned long long *>(b->h_pin);
@@ -1793,6 +1802,7 @@ extern "C" int muse_batch_run_ex(muse_batch *b, const int32_t *key_cols, int32_t
     if (top_n < 0) top_n = 0;
     CU(cudaSetDevice(b->ctx->device));
     RunArgs a{key_cols, n_key_cols, max_lag, top_n, threshold, sign_filter, mode, signed_scores};
+    a.group_cut = 1;
     *n_out = 0;
     if (device_topn_applies(b, a)) {
         // ungrouped: filter and top-N on the device, ONE copy of top_n records to the host

@@ -13,6 +13,7 @@
 
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#include "muse_screen.cuh"
 
 namespace muse {
 
@@ -106,11 +107,21 @@ __global__ void group_lower_bound_kernel(GroupTable gt, KeyCols kc, const float 
 // best lower bound (the true representative always qualifies, and so does every member that ties it)
 // A member whose upper bound is below thr_lo (<= the threshold) cannot be the representative of a group that passes
 // results.go:46-52 -- if it were, the whole group would fail -- so it is left out as well.
+// cut_bits (may be NULL): float bits of a lower bound on the top_n-th best group that certainly passes the filter
+// (group_cut_find_kernel): a member below it cannot be the representative of a group of the top-N.
 __global__ void group_contenders_kernel(GroupTable gt, const float *__restrict__ upper, int64_t S,
                                         const int64_t *__restrict__ slot_of, float thr_lo, int32_t *__restrict__ out,
-                                        unsigned long long *n) {
+                                        unsigned long long *n, const unsigned *__restrict__ cut_bits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool take = i < S && upper[i] >= thr_lo && upper[i] >= __uint_as_float((unsigned)gt.gmax[slot_of[i]]);
+    if (cut_bits) thr_lo = fmaxf(thr_lo, __uint_as_float(*cut_bits));
+    bool take = false;
+    if (i < S) {
+        const unsigned long long g = gt.gmax[slot_of[i]];
+        take = upper[i] >= thr_lo && upper[i] >= __uint_as_float((unsigned)g);
+        // every possible representative of the group has its peak certainly outside the lag window: the group fails
+        // results.go:46-48 whatever the exact scores are (flags of group_uncertain_kernel; only set in that mode)
+        if (cut_bits && !((g >> 33) & 1ull)) take = false;
+    }
     const unsigned mask = __ballot_sync(0xffffffffu, take);
     if (mask == 0u) return;
     const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
@@ -118,6 +129,56 @@ __global__ void group_contenders_kernel(GroupTable gt, const float *__restrict__
     if (lane == leader) base = atomicAdd(n, (unsigned long long)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (take) out[base + __popc(mask & ((1u << lane) - 1u))] = (int32_t)i;
+}
+
+// ---- a cut-off for grouped single-GPU runs -----------------------------------------------------------------------
+// After the screening pass a group's running lower bound L_g (low word of gmax) bounds its score from below (muse_batch.go:87-89:
+// the group's score is its best member's).  The group certainly PASSES results.go:46-52 when L_g reaches the threshold and
+// every member that can still be its representative (upper bound >= L_g) has its peak certainly inside the lag window
+// (out_W == 1).  The top_n-th largest L_g among those groups is a lower bound on the score of the last group Results will
+// keep, so members below it need no exact score: a group whose true best member lies below it is ranked behind top_n
+// groups that are scored exactly, whatever score its other members give it.  (Not for shard partials: a group's
+// representative may sit in another shard.)
+// 1. flag the groups with a possible representative that is not certainly inside the window (bit 32 of gmax) / not certainly
+//    outside it (bit 33: a group without it certainly fails the filter and needs no exact score either)
+__global__ void group_uncertain_kernel(GroupTable gt, const float *__restrict__ upper, const signed char *__restrict__ W, int64_t S,
+                                       const int64_t *__restrict__ slot_of) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const int64_t s = slot_of[i];
+    const float Lg = __uint_as_float((unsigned)gt.gmax[s]);
+    if (!(upper[i] < Lg)) {                                  // NaN / undecided bounds count as possible
+        const unsigned long long f = (W[i] != 1 ? 1ull << 32 : 0ull) | (W[i] != -1 ? 1ull << 33 : 0ull);
+        atomicOr(&gt.gmax[s], f);
+    }
+}
+// 2. count the certain groups' lower bounds in the three-level histogram of the running cut-off (muse_screen.cuh)
+__global__ void group_cut_count_kernel(GroupTable gt, double threshold, unsigned *__restrict__ hist) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= gt.slots) return;
+    const unsigned long long g = gt.gmax[s];
+    if ((g >> 32) & 1ull) return;
+    const float L = __uint_as_float((unsigned)g);
+    if (!(L > 0.f) || (double)L < threshold) return;
+    int bin = (int)(L * (float)MUSE_CUT_BINS);
+    bin = bin < 0 ? 0 : (bin >= MUSE_CUT_BINS ? MUSE_CUT_BINS - 1 : bin);
+    unsigned *coarse = hist, *mid = coarse + 64, *fine = mid + 64 * 64;
+    atomicAdd(&fine[bin], 1u);
+    atomicAdd(&mid[bin >> 6], 1u);
+    atomicAdd(&coarse[bin >> 12], 1u);
+}
+// 3. one warp: the lower edge of the bin that holds the top_n-th largest counted bound (nothing when fewer were counted)
+__global__ void group_cut_find_kernel(const unsigned *__restrict__ hist, int top_n, unsigned *__restrict__ cut_bits) {
+    const int t = threadIdx.x;
+    const unsigned *coarse = hist, *mid = coarse + 64, *fine = mid + 64 * 64;
+    unsigned need = (unsigned)top_n;
+    const int c = cut_level(coarse, t, need);
+    if (c < 0) return;
+    const int m = cut_level(mid + c * 64, t, need);
+    if (m < 0) return;
+    const int f = cut_level(fine + (c * 64 + m) * 64, t, need);
+    if (f < 0) return;
+    if (t == 0) atomicMax(cut_bits, __float_as_uint((float)((c * 64 + m) * 64 + f) / (float)MUSE_CUT_BINS));
 }
 
 // pass 2: lowest series index among the members that hold the group max

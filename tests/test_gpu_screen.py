@@ -214,7 +214,7 @@ def test_grouped_screened_run_equals_exact_run(ctx, N):
     store.append(Y, np.stack([graph, host, colo, rnd], axis=1))
     b = mb.DeviceBatch(ctx, store, ref)
     for cols in ([0], [1], [0, 2], [2], [3, 0]):
-        for max_lag, top_n, thr in ((60, 100, 0.5), (15, 10, 0.0), (N, 2000, 0.2)):
+        for max_lag, top_n, thr in ((60, 100, 0.5), (15, 10, 0.0), (N, 2000, 0.2), (60, 3, 0.0), (N, 1, 0.9), (5, 7, 0.3)):
             e = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_EXACT)
             s = b.run(cols, max_lag, top_n, thr, mode=mb.MODE_SCREEN)
             t = b.timing()
@@ -224,6 +224,12 @@ def test_grouped_screened_run_equals_exact_run(ctx, N):
     # the point of it: far fewer fp64 scorings than series
     b.run([0], 60, 100, 0.5, mode=mb.MODE_SCREEN)
     assert b.timing().n_rescored < 0.6 * S
+    if N > 2048:
+        # n = 4096 .. 16384: a short top-N needs exact scores only for groups that can reach it (group_cut_find_kernel)
+        b.run([3, 0], N, 2000, 0.0, mode=mb.MODE_SCREEN)
+        many = b.timing().n_rescored
+        b.run([3, 0], N, 5, 0.0, mode=mb.MODE_SCREEN)
+        assert b.timing().n_rescored < many
     # sharded partials (F2: unfiltered group representatives) out of the screened path: every group whose representative
     # reaches the threshold is there unchanged; below it the screened path may name another member (or none) -- a member
     # whose bound is under the threshold is never scored, and such a group fails results.go:46-52 after any merge
