@@ -210,7 +210,7 @@ def test_screen_error_survey_keeps_its_margins():
     path = os.path.join(ROOT, "profiles", "screen_error_survey.json")
     d = json.load(open(path))
     slack = d["slack"]
-    assert slack == 2e-4
+    assert slack == 1e-4
     lens = {r["fft_len"] for r in d["rows"]}
     assert {512, 1024, 2048, 4096, 8192, 16384} <= lens
     assert any(r["N"] & 1 for r in d["rows"])                  # odd lengths are part of the survey

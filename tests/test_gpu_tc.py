@@ -48,9 +48,9 @@ def test_tensor_core_bounds_dominate_and_track_the_fp32_bound(ctx, N, S, Q):
         with np.errstate(invalid="ignore", divide="ignore"):
             Yf = np.abs(np.fft.rfft(np.concatenate([np.zeros((S, n - N)), z(Y)], axis=1), axis=1))
         bins = (Yf * (X * w)[None, :]).sum(axis=1) / n
-        assert np.all(U[q][dec] <= bins[dec] * 1.0005 + 2.1e-4)
-        assert np.all(U[q][dec] >= bins[dec] * 0.9999 + 1.9e-4)
-        assert np.all(u32[dec] >= bins[dec] * 0.9999 + 1.9e-4)
+        assert np.all(U[q][dec] <= bins[dec] * 1.0005 + 1.1e-4)
+        assert np.all(U[q][dec] >= bins[dec] * 0.9999 + 0.9e-4)
+        assert np.all(u32[dec] >= bins[dec] * 0.9999 + 0.9e-4)
         b.close()
     store.close()
 

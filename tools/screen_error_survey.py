@@ -14,7 +14,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "go-muse_b200"), os.path.join(ROOT, "te
 import muse_b200 as mb  # noqa: E402
 from test_gpu_screen import _adversarial  # noqa: E402
 
-SLACK = 2e-4
+SLACK = 1e-4
 ctx = mb.default_context(0)
 rows = []
 for N in (66, 100, 128, 200, 255, 256, 300, 480, 512, 1000, 1024, 1026, 1440, 1441, 2047, 2048, 2500, 4096, 5000, 8192, 10080, 10081, 16384):
