@@ -1143,23 +1143,25 @@ extern "C" int muse_batch_xcorr(muse_batch *b, int64_t local_index, double *cc, 
     p.twn = b->twn;
     p.out_score = d_cc;
     p.out_flag = b->d_flag;
-    if (b->is_long) {
-        rc = ensure_long_work(b, 1);
-        if (rc) {
-            cudaFree(d_cc);
-            return rc;
-        }
-        LongParams lp = long_params(b, p.slab, 1, nullptr, 0);
-        lp.out_score = d_cc;
-        CU(launch_long(MODE_CC, lp, b->d_long, b->long_pairs, bstream(b)));
-    } else {
-        CU(launch_exact(MODE_CC, b->log2m, p, bstream(b)));
-    }
     int32_t flag = 0;
-    CU(cudaMemcpyAsync(cc, d_cc, sizeof(double) * (size_t)b->n, cudaMemcpyDeviceToHost, bstream(b)));
-    CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, bstream(b)));
-    CU(cudaStreamSynchronize(bstream(b)));
+    auto body = [&]() -> int {      // d_cc is freed on every path out of here
+        if (b->is_long) {
+            int rcl = ensure_long_work(b, 1);
+            if (rcl) return rcl;
+            LongParams lp = long_params(b, p.slab, 1, nullptr, 0);
+            lp.out_score = d_cc;
+            CU(launch_long(MODE_CC, lp, b->d_long, b->long_pairs, bstream(b)));
+        } else {
+            CU(launch_exact(MODE_CC, b->log2m, p, bstream(b)));
+        }
+        CU(cudaMemcpyAsync(cc, d_cc, sizeof(double) * (size_t)b->n, cudaMemcpyDeviceToHost, bstream(b)));
+        CU(cudaMemcpyAsync(&flag, b->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, bstream(b)));
+        CU(cudaStreamSynchronize(bstream(b)));
+        return MUSE_OK;
+    };
+    rc = body();
     cudaFree(d_cc);
+    if (rc) return rc;
     if (std_zero) *std_zero = flag;
     return MUSE_OK;
 }
