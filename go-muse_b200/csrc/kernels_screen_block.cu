@@ -22,9 +22,8 @@ static cudaError_t launch_screen_block_t(const ScreenParams &p, int sm_count, cu
 
 cudaError_t launch_screen_block(int log2m, const ScreenParams &p, int sm_count, cudaStream_t st) {
     switch (log2m) {
-        case 13: return launch_screen_block_t<13, 2>(p, sm_count, st);
-        case 12: return launch_screen_block_t<12, 4>(p, sm_count, st);
-        case 11: return launch_screen_block_t<11, 8>(p, sm_count, st);
+        // n = 4096 .. 16384 moved to muse_screen_big.cuh, n = 512 / 1024 to muse_screen_sub.cuh: what is left here is round 1's
+        // kernel for A/B runs of those two sizes (MUSE_BLOCK_SMALL=1)
         case 9: return launch_screen_block_t<9, 16>(p, sm_count, st);
         case 8: return launch_screen_block_t<8, 16>(p, sm_count, st);
     }
